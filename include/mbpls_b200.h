@@ -1,0 +1,163 @@
+/*
+ * mbpls_b200 -- C ABI of the B200 (sm_100a) kernels behind the MB-PLS latent-variable fitting path.
+ *
+ * The reference (DTUComputeStatisticsAndDataAnalysis/MBPLS v1.0.4) is pure Python and has NO plugin /
+ * FFI / operator interface to mirror: its boundary is the sklearn-style class
+ * `mbpls.mbpls.MBPLS` (mbpls/mbpls.py:22).  This header therefore *defines* the entry points a binding
+ * for that class calls; every function cites the region of mbpls/mbpls.py whose numpy / scipy /
+ * scikit-learn calls it replaces.  The Python host class `mbpls_b200.MBPLS` binds them with ctypes
+ * (mbpls_b200/_cabi.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in `_host` or the doc says otherwise.
+ *  - All matrices are float64 and FEATURE-MAJOR: a p x ld array with one feature (one column of the
+ *    reference's n x p matrix) per row, ld >= n, ld % 16 == 0, padding [n, ld) zero.  Result matrices
+ *    are COMPONENT-MAJOR (K x p or K x ld).  n-vectors have at least ld elements.
+ *  - `stream` is a cudaStream_t passed as void*.  Functions never allocate, never synchronise and keep
+ *    no global state; they return 0, a negative MBPLS_ERR_* code for bad arguments, or
+ *    1000 + cudaError_t for a launch failure.
+ *  - `done` arguments point at the int ctrl[MBPLS_CTRL_DONE] of a NIPALS component; when it is
+ *    non-zero the kernel returns immediately (lets the host enqueue trips in batches).
+ */
+#ifndef MBPLS_B200_H
+#define MBPLS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBPLS_ABI_VERSION 1
+
+/* indices into the per-fit scalar / control buffers */
+#define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
+#define MBPLS_SCAL_DIFF 1  /* last diff_t (mbpls.py:887) */
+#define MBPLS_SCAL_TT 2    /* ts'ts */
+#define MBPLS_SCAL_VV 3    /* v'v */
+#define MBPLS_SCAL_COUNT 8
+#define MBPLS_CTRL_DONE 0  /* 1 once diff_t <= max_tol (mbpls.py:841) */
+#define MBPLS_CTRL_TRIPS 1 /* completed trips of the while loop for this component */
+#define MBPLS_CTRL_COUNT 4
+
+/* nipals_convergence_norm: matrix-norm semantics of np.linalg.norm on an n x 1 array (mbpls.py:887) */
+#define MBPLS_NORM_L2 0  /* ord = 2, -2, 'fro', 'nuc' */
+#define MBPLS_NORM_L1 1  /* ord = 1, -1 */
+#define MBPLS_NORM_MAX 2 /* ord = inf */
+#define MBPLS_NORM_MIN 3 /* ord = -inf */
+
+int mbpls_abi_version(void);
+
+/* ---- ingest (mbpls.py:301-323 check_array copies, :379 hstack) ---------------------------------- */
+/* row-major chunk (rows x cols, leading dim lds) -> feature-major dst[c*ld + row0 + r] */
+int mbpls_transpose_in_f64(const double* src, long lds, int rows, int cols, double* dst, long ld, int row0, void* stream);
+/* feature-major -> row-major */
+int mbpls_transpose_out_f64(const double* src, long ld, int rows, int cols, double* dst, long ldd, int row0, void* stream);
+
+/* ---- NaN census: MBPLS.check_sparsity_level (mbpls.py:255-271) ----------------------------------
+ * col_nan[j] = number of NaNs in feature j; row_flag[b*ldf + i] = 1 if sample i has a NaN in block b
+ * (row_flag must be zeroed by the caller). block_off: B+1 ascending local feature offsets. */
+int mbpls_nan_census_f64(const double* Xt, long ld, int n, int p, const int* block_off, int B, int* col_nan,
+                         unsigned char* row_flag, long ldf, void* stream);
+
+/* ---- StandardScaler.fit_transform on every feature, in place (mbpls.py:307,314,325-326) ----------
+ * Outputs per feature: mean_, var_, scale_, n_samples_seen_ and nansum(z^2) (feeds varx, :826-829).
+ * mode 0: feature-resident bulk-copy pipeline (1 read + 1 write) when a feature fits in shared
+ * memory, otherwise the global-memory fallback; mode 1 forces the fallback. */
+int mbpls_standardize_fit_f64(double* Xt, long ld, int n, int p, double* mean, double* var, double* scale,
+                              long long* seen, double* zss, int mode, void* stream);
+/* StandardScaler.transform on new data (mbpls.py:1097,1103,1125,1369,1372) */
+int mbpls_standardize_apply_f64(double* Xt, long ld, int n, int p, const double* mean, const double* scale, void* stream);
+/* y_scaler_.inverse_transform (mbpls.py:1384,1386) on a feature-major q x ld array */
+int mbpls_scaler_inverse_f64(double* Zt, long ld, int n, int q, const double* mean, const double* scale, void* stream);
+/* nansum(x_j^2) per feature: (X**2).sum() / np.nansum (mbpls.py:826-830, :943-945) */
+int mbpls_feature_sumsq_f64(const double* Xt, long ld, int n, int p, double* out, void* stream);
+/* deterministic segmented sum out[s] = sum v[off[s]:off[s+1]] */
+int mbpls_segsum_f64(const double* v, const int* off, int nseg, double* out, void* stream);
+
+/* ---- NIPALS inner loop (mbpls.py:841-914) -------------------------------------------------------- */
+int mbpls_xtu_feats_per_cta(int p);
+int mbpls_xtu_num_ctas(int p); /* rows of norm_part */
+
+/* w[j] = x_j . u / u'u (mbpls.py:847,856); NaN mode: masked ratio for features with NaN (:848-852).
+ * uu == NULL: no division for fully observed features (the loadings of :920,:928).
+ * norm_part[cta*B + b] = partial ||w_b||^2 (may be NULL). */
+int mbpls_nipals_xtu_f64(const double* Xt, long ld, int n, int p, const double* u, const double* uu, const int* block_off,
+                         int B, double* w, double* norm_part, int nanmode, const int* done, void* stream);
+/* same partial norms for a w produced elsewhere (fused deflation) */
+int mbpls_block_sumsq_parts_f64(const double* w, int p, const int* block_off, int B, double* norm_part, const int* done,
+                                void* stream);
+/* Tnum[s][i] = sum_{j in split s} w_j x_ij (mbpls.py:866,875); NaN mode also Tden[s][i] = masked sum of
+ * w_j^2 (:867-872).  split s covers local features [split_f0[s], split_f1[s]) of a single block. */
+int mbpls_nipals_xw_f64(const double* Xt, long ld, int n, const double* w, const int* split_f0, const int* split_f1,
+                        int nsplit, double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream);
+/* red = [B x ldt numerators | B x ldt denominators (NaN mode) | B squared block-weight norms]:
+ * fixed-order sums over the splits of each block / over the xtu CTAs.  This is the buffer that is
+ * all-reduced over NVLink when features are sharded across GPUs. */
+int mbpls_nipals_reduce_partials_f64(const double* Tnum, const double* Tden, long ldt, int n, int B,
+                                     const int* block_split_off, const double* norm_part, int n_norm_parts, double* red,
+                                     int nanmode, const int* done, void* stream);
+static inline long mbpls_red_elems(int B, long ldt, int nanmode) { return (long)(nanmode ? 2 : 1) * B * ldt + B; }
+
+/* u <- u0, u'u, trips = 0, diff = 1, done = 0 (mbpls.py:832-840) */
+int mbpls_nipals_begin_component_f64(const double* u0, int n, double* u, double* scal, int* ctrl, void* stream);
+
+typedef struct mbpls_epilogue_args {
+  int n, B, q, nanmode, norm_kind;
+  long ldt, ldf;
+  double max_tol;
+  const double* red;             /* reduced partials, layout above */
+  const double* Yt;              /* q x ldt */
+  const unsigned char* row_flag; /* B x ldf, NaN mode */
+  const unsigned char* ycol_flag;/* q, NaN mode: Y column has a NaN */
+  double* T;                     /* B x ldt  block scores t_b of this trip (mbpls.py:863-875) */
+  double* u;                     /* n  in: u of this trip, out: next u (:901-913) */
+  double* ts;                    /* n  superscores (:882-883) */
+  double* ts_old;                /* n  superscores_old (:888) */
+  double* a;                     /* B  superweights (:879-880) */
+  double* v;                     /* q  Y weights (:890-899) */
+  double* scal;                  /* MBPLS_SCAL_COUNT */
+  int* ctrl;                     /* MBPLS_CTRL_COUNT */
+  double* diff_trace;            /* optional diff_t per trip */
+  int diff_trace_len;
+} mbpls_epilogue_args;
+/* `args` is a HOST pointer; the struct is passed to the kernel by value. */
+int mbpls_nipals_epilogue_f64(const mbpls_epilogue_args* args_host, void* stream);
+
+typedef struct mbpls_record_args {
+  int n, p, B, q, nanmode;
+  long ldt, T_block_stride;
+  const int* block_off;
+  const double *w, *red, *T, *ts, *u, *v, *a;
+  double *Wt_k, *W_k, *Ts_k, *U_k, *T_k, *V_k, *A_k;
+} mbpls_record_args;
+/* append the converged component (mbpls.py:975-983): W_non_normal_, W_, Ts_, U_, T_, V_, A_ */
+int mbpls_nipals_record_component_f64(const mbpls_record_args* args_host, void* stream);
+
+/* p_j = x_j . ts (masked ratio for features with NaN) and X <- X - ts p' in place (mbpls.py:917-930,
+ * :968-969).  pss[j] = p_j^2.  If u0 != NULL also w_next[j] = x_j(deflated) . u0 / u0'u0, i.e. the first
+ * weights of the next component (:847,856 with u = u0).  mode as in mbpls_standardize_fit_f64. */
+int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* ts, const double* u0, const double* u0u0,
+                               double* P_k, double* w_next, double* pss, int nanmode, int mode, void* stream);
+
+/* ---- finalisation and new-data paths (mbpls.py:986-989, :1110-1117, :1379-1386) -------------------- */
+/* Cpart[chunk][i*K2 + j] = sum_{f in chunk} A[i][f] * Bm[j][f]; A is K1 x p (lda), Bm is K2 x p (ldb).
+ * Returns the number of chunks via mbpls_gram_num_chunks; reduce with mbpls_reduce_chunks_f64. */
+int mbpls_gram_num_chunks(int p);
+int mbpls_gram_partial_f64(const double* A, long lda, int K1, const double* Bm, long ldb, int K2, int p, double* Cpart,
+                           void* stream);
+int mbpls_reduce_chunks_f64(const double* Cpart, int nchunks, int len, double* C, void* stream);
+/* out[c][j] = sum_k (in[k][j] * rowscale[k]) * M[k*C + c]   (R_ = W pinv(P'W), beta_ = R_ V_') */
+int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const double* rowscale, const double* M, int C,
+                             double* out, long ldout, void* stream);
+/* out_part[s][c][i] = sum_{j in split s} nan0(Xt[j][i]) * Bm[c][j]   (X.dot(beta_), X.dot(R_), X_b.dot(W_b)) */
+int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
+                          const int* split_f1, int nsplit, double* out_part, long ldo, void* stream);
+/* X_b <- X_b - ts p_b' for new data (transform, mbpls.py:1145,1204); NaNs stay NaN */
+int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, const double* pvec, void* stream);
+/* column norms / scaling of a C x ld feature-major array over n samples */
+int mbpls_rows_sumsq_f64(const double* M, long ld, int rows, int n, double* out, void* stream);
+int mbpls_rows_scale_f64(double* M, long ld, int rows, int n, const double* scale, int divide, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBPLS_B200_H */

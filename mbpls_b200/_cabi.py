@@ -1,0 +1,121 @@
+"""ctypes binding of ``libmbpls_b200.so`` (the C ABI declared in ``include/mbpls_b200.h``).
+
+The library is the product's only compute path: if it is missing, or a call returns a non-zero
+status, this module raises -- there is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
+
+ABI_VERSION = 1
+
+# indices shared with the header
+SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
+CTRL_DONE, CTRL_TRIPS, CTRL_COUNT = 0, 1, 4
+NORM_L2, NORM_L1, NORM_MAX, NORM_MIN = 0, 1, 2, 3
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_long
+_d = C.c_double
+
+
+class EpilogueArgs(C.Structure):
+    _fields_ = [
+        ("n", _i), ("B", _i), ("q", _i), ("nanmode", _i), ("norm_kind", _i),
+        ("ldt", _l), ("ldf", _l),
+        ("max_tol", _d),
+        ("red", _p), ("Yt", _p), ("row_flag", _p), ("ycol_flag", _p),
+        ("T", _p), ("u", _p), ("ts", _p), ("ts_old", _p), ("a", _p), ("v", _p),
+        ("scal", _p), ("ctrl", _p), ("diff_trace", _p), ("diff_trace_len", _i),
+    ]
+
+
+class RecordArgs(C.Structure):
+    _fields_ = [
+        ("n", _i), ("p", _i), ("B", _i), ("q", _i), ("nanmode", _i),
+        ("ldt", _l), ("T_block_stride", _l),
+        ("block_off", _p),
+        ("w", _p), ("red", _p), ("T", _p), ("ts", _p), ("u", _p), ("v", _p), ("a", _p),
+        ("Wt_k", _p), ("W_k", _p), ("Ts_k", _p), ("U_k", _p), ("T_k", _p), ("V_k", _p), ("A_k", _p),
+    ]
+
+
+# name -> argtypes; every function returns int.  Keep in sync with include/mbpls_b200.h
+# (tests/test_cabi.py parses the header and checks that every declared symbol is exported and listed here).
+SIGNATURES = {
+    "mbpls_abi_version": [],
+    "mbpls_transpose_in_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
+    "mbpls_transpose_out_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
+    "mbpls_nan_census_f64": [_p, _l, _i, _i, _p, _i, _p, _p, _l, _p],
+    "mbpls_standardize_fit_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p],
+    "mbpls_standardize_apply_f64": [_p, _l, _i, _i, _p, _p, _p],
+    "mbpls_scaler_inverse_f64": [_p, _l, _i, _i, _p, _p, _p],
+    "mbpls_feature_sumsq_f64": [_p, _l, _i, _i, _p, _p],
+    "mbpls_segsum_f64": [_p, _p, _i, _p, _p],
+    "mbpls_xtu_feats_per_cta": [_i],
+    "mbpls_xtu_num_ctas": [_i],
+    "mbpls_nipals_xtu_f64": [_p, _l, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p, _p],
+    "mbpls_block_sumsq_parts_f64": [_p, _i, _p, _i, _p, _p, _p],
+    "mbpls_nipals_xw_f64": [_p, _l, _i, _p, _p, _p, _i, _p, _p, _l, _i, _p, _p],
+    "mbpls_nipals_reduce_partials_f64": [_p, _p, _l, _i, _i, _p, _p, _i, _p, _i, _p, _p],
+    "mbpls_nipals_begin_component_f64": [_p, _i, _p, _p, _p, _p],
+    "mbpls_nipals_epilogue_f64": [C.POINTER(EpilogueArgs), _p],
+    "mbpls_nipals_record_component_f64": [C.POINTER(RecordArgs), _p],
+    "mbpls_loadings_deflate_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "mbpls_gram_num_chunks": [_i],
+    "mbpls_gram_partial_f64": [_p, _l, _i, _p, _l, _i, _i, _p, _p],
+    "mbpls_reduce_chunks_f64": [_p, _i, _i, _p, _p],
+    "mbpls_right_multiply_f64": [_p, _l, _i, _i, _p, _p, _i, _p, _l, _p],
+    "mbpls_skinny_gemm_f64": [_p, _l, _i, _p, _l, _i, _p, _p, _i, _p, _l, _p],
+    "mbpls_rank1_update_f64": [_p, _l, _i, _i, _p, _p, _p],
+    "mbpls_rows_sumsq_f64": [_p, _l, _i, _i, _p, _p],
+    "mbpls_rows_scale_f64": [_p, _l, _i, _i, _p, _i, _p],
+}
+
+# functions whose int return value is a plain number, not a status
+_PLAIN = {"mbpls_abi_version", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks"}
+
+
+class MbplsCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise MbplsCudaError(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). mbpls_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    if lib.mbpls_abi_version() != ABI_VERSION:
+        raise MbplsCudaError("ABI version mismatch between _cabi.py and libmbpls_b200.so; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> int:
+    """Invoke an entry point; status-returning functions raise on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name in _PLAIN:
+        return rc
+    if rc != 0:
+        if rc >= 1000:
+            raise MbplsCudaError(f"{name}: CUDA error {rc - 1000}")
+        raise MbplsCudaError(f"{name}: invalid argument (status {rc})")
+    return 0

@@ -1,0 +1,146 @@
+// Shared device helpers for the mbpls_b200 kernels (sm_100a only).
+//
+// Layout convention used by every kernel in this library ("feature-major"):
+//   Xt  : p x ld doubles, one *feature* (a column of the reference's n x p matrix,
+//         mbpls/mbpls.py:379) per row, ld >= n and ld % 16 == 0 so each feature starts on a
+//         128-byte boundary and can be moved with one 1-D bulk (TMA) copy.
+//   Yt  : q x ld, same convention.  n-vectors (u, ts, t_b) are plain arrays of length >= ld.
+// Padding elements [n, ld) are zero and are never used in arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define MBPLS_FULL_MASK 0xffffffffu
+
+namespace mbpls {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MBPLS_FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(MBPLS_FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(MBPLS_FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_or(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(MBPLS_FULL_MASK, v, o);
+  return v;
+}
+
+// Deterministic block-wide sum of `NV` values per thread.  `scratch` must hold 32*NV doubles.
+// Every thread gets the result.  Two __syncthreads per call.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();  // protect scratch from a previous call's readers
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w * NV + k];  // fixed order -> bitwise reproducible
+    v[k] = s;
+  }
+}
+
+__device__ __forceinline__ double block_sum1(double x, double* scratch) {
+  double v[1] = {x};
+  block_sum<1>(v, scratch);
+  return v[0];
+}
+
+// ---- mbarrier + 1-D bulk async copies (TMA engine; SASS: UBLKCP / SYNCS) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, both addresses 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// streaming 16-byte load that does not pollute L1 (X is read once per pass)
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// block index of local feature j given B+1 ascending offsets (B is small)
+__device__ __forceinline__ int block_of(const int* __restrict__ off, int B, int j) {
+  int b = 0;
+  while (b + 1 < B && j >= off[b + 1]) ++b;
+  return b;
+}
+
+}  // namespace mbpls
+
+// error codes of the C ABI (include/mbpls_b200.h)
+#define MBPLS_OK 0
+#define MBPLS_ERR_ARG (-1)
+#define MBPLS_ERR_SIZE (-2)
+#define MBPLS_CUDA_ERR(e) (1000 + static_cast<int>(e))
+#define MBPLS_RETURN_LAST()                                  \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    return e__ == cudaSuccess ? MBPLS_OK : MBPLS_CUDA_ERR(e__); \
+  } while (0)

@@ -1,0 +1,252 @@
+// Finalisation and new-data kernels:
+//   R_ = W pinv(P'W), beta_ = R_ V_'                       (mbpls/mbpls.py:986-989, :642-643, :737-738)
+//   Ts = X R_, y_hat = X beta_, T_b = X_b W_b               (:1110-1117, :1142-1155, :1379-1386)
+// All small-matrix contractions over the feature axis are two-stage (per-chunk partial, fixed-order
+// sum) so results are bitwise reproducible.
+#include "launch.cuh"
+#include "../../include/mbpls_b200.h"
+
+using namespace mbpls;
+
+#define GRAM_CHUNK 2048
+#define GRAM_TILE 32
+
+// Cpart[chunk][i*K2+j] = sum_{f in chunk} A[i][f] * Bm[j][f]
+__global__ void __launch_bounds__(256)
+gram_partial_kernel(const double* __restrict__ A, long lda, int K1, const double* __restrict__ Bm, long ldb, int K2, int p,
+                    double* __restrict__ Cpart) {
+  extern __shared__ double sm[];
+  double* sA = sm;                                  // K1 x (GRAM_TILE+1)
+  double* sB = sm + static_cast<size_t>(K1) * (GRAM_TILE + 1);  // K2 x (GRAM_TILE+1)
+  const int f_begin = blockIdx.x * GRAM_CHUNK, f_end = min(p, f_begin + GRAM_CHUNK);
+  const int nout = K1 * K2;
+  // each thread owns outputs o = tid, tid+256, ... (at most 16 for K1=K2=64)
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (int f0 = f_begin; f0 < f_end; f0 += GRAM_TILE) {
+    const int nf = min(GRAM_TILE, f_end - f0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < (K1 + K2) * GRAM_TILE; e += blockDim.x) {
+      const int row = e / GRAM_TILE, f = e % GRAM_TILE;
+      double v = 0.0;
+      if (f < nf) v = row < K1 ? A[static_cast<size_t>(row) * lda + f0 + f] : Bm[static_cast<size_t>(row - K1) * ldb + f0 + f];
+      if (row < K1) sA[row * (GRAM_TILE + 1) + f] = v;
+      else sB[(row - K1) * (GRAM_TILE + 1) + f] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int o = threadIdx.x + k * 256;
+      if (o < nout) {
+        const int i = o / K2, j = o % K2;
+        double s = acc[k];
+#pragma unroll 8
+        for (int f = 0; f < GRAM_TILE; ++f) s = fma(sA[i * (GRAM_TILE + 1) + f], sB[j * (GRAM_TILE + 1) + f], s);
+        acc[k] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int o = threadIdx.x + k * 256;
+    if (o < nout) Cpart[static_cast<size_t>(blockIdx.x) * nout + o] = acc[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_chunks_kernel(const double* __restrict__ Cpart, int nchunks, int len, double* __restrict__ C) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += Cpart[static_cast<size_t>(c) * len + o];
+  C[o] = s;
+}
+
+// out[c][j] = sum_k in[k][j] * rowscale[k] * M[k*C + c]
+__global__ void __launch_bounds__(256)
+right_multiply_kernel(const double* __restrict__ in, long ldin, int K, int p, const double* __restrict__ rowscale,
+                      const double* __restrict__ M, int C, double* __restrict__ out, long ldout) {
+  extern __shared__ double sM[];  // K x C, pre-scaled
+  for (int e = threadIdx.x; e < K * C; e += blockDim.x) sM[e] = M[e] * (rowscale ? rowscale[e / C] : 1.0);
+  __syncthreads();
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
+    for (int c = 0; c < C; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) s = fma(in[static_cast<size_t>(k) * ldin + j], sM[k * C + c], s);
+      out[static_cast<size_t>(c) * ldout + j] = s;
+    }
+  }
+}
+
+// out_part[(s*C + c0 + c)*ldo + i] = sum_{j in split s} nan0(Xt[j][i]) * Bm[(c0+c)*ldb + j],  c < NC
+template <int NC>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* __restrict__ Bm, long ldb, int C, int c0,
+                   const int* __restrict__ split_f0, const int* __restrict__ split_f1, double* __restrict__ out_part,
+                   long ldo) {
+  const int s = blockIdx.y;
+  const int f0 = split_f0[s], f1 = split_f1[s];
+  const int r = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (r >= n) return;
+  const int nc = min(NC, C - c0);
+  double ax[NC], ay[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) ax[c] = ay[c] = 0.0;
+  const double* __restrict__ xp = Xt + r;
+  int j = f0;
+  for (; j + 4 <= f1; j += 4) {
+    double2 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[k] = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j + k) * ld));
+      if (isnan(x[k].x)) x[k].x = 0.0;
+      if (isnan(x[k].y)) x[k].y = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < nc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double bv = __ldg(Bm + static_cast<size_t>(c0 + c) * ldb + j + k);
+          ax[c] = fma(x[k].x, bv, ax[c]);
+          ay[c] = fma(x[k].y, bv, ay[c]);
+        }
+      }
+    }
+  }
+  for (; j < f1; ++j) {
+    double2 x = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j) * ld));
+    if (isnan(x.x)) x.x = 0.0;
+    if (isnan(x.y)) x.y = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < nc) {
+        const double bv = __ldg(Bm + static_cast<size_t>(c0 + c) * ldb + j);
+        ax[c] = fma(x.x, bv, ax[c]);
+        ay[c] = fma(x.y, bv, ay[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < nc) {
+      double* o = out_part + (static_cast<size_t>(s) * C + c0 + c) * ldo + r;
+      *reinterpret_cast<double2*>(o) = make_double2(ax[c], ay[c]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank1_update_kernel(double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ ts,
+                    const double* __restrict__ pvec) {
+  const int j = blockIdx.y;
+  if (j >= p) return;
+  const double pj = pvec[j];
+  double* x = Xt + static_cast<size_t>(j) * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    x[i] = __dsub_rn(x[i], __dmul_rn(ts[i], pj));
+}
+
+__global__ void __launch_bounds__(256) rows_sumsq_kernel(const double* __restrict__ M, long ld, int n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const double* m = M + static_cast<size_t>(blockIdx.x) * ld;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(m[i], m[i], s);
+  s = block_sum1(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+rows_scale_kernel(double* __restrict__ M, long ld, int n, const double* __restrict__ scale, int divide) {
+  double* m = M + static_cast<size_t>(blockIdx.y) * ld;
+  const double s = scale[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m[i] = divide ? m[i] / s : m[i] * s;
+}
+
+extern "C" {
+
+int mbpls_abi_version(void) { return MBPLS_ABI_VERSION; }
+
+int mbpls_gram_num_chunks(int p) { return p <= 0 ? 0 : (p + GRAM_CHUNK - 1) / GRAM_CHUNK; }
+
+int mbpls_gram_partial_f64(const double* A, long lda, int K1, const double* Bm, long ldb, int K2, int p, double* Cpart,
+                           void* stream) {
+  if (!A || !Bm || !Cpart || K1 < 1 || K2 < 1) return MBPLS_ERR_ARG;
+  if (K1 > 64 || K2 > 64) return MBPLS_ERR_SIZE;
+  if (p <= 0) return MBPLS_OK;
+  const int grid = mbpls_gram_num_chunks(p);
+  const size_t smem = static_cast<size_t>(K1 + K2) * (GRAM_TILE + 1) * sizeof(double);
+  gram_partial_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_reduce_chunks_f64(const double* Cpart, int nchunks, int len, double* C, void* stream) {
+  if (!Cpart || !C || nchunks < 0 || len < 0) return MBPLS_ERR_ARG;
+  if (len == 0) return MBPLS_OK;
+  reduce_chunks_kernel<<<(len + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(Cpart, nchunks, len, C);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const double* rowscale, const double* M, int C,
+                             double* out, long ldout, void* stream) {
+  if (!in || !M || !out || K < 1 || C < 1) return MBPLS_ERR_ARG;
+  if (static_cast<size_t>(K) * C * sizeof(double) > 48 * 1024) return MBPLS_ERR_SIZE;
+  if (p <= 0) return MBPLS_OK;
+  int grid = (p + 255) / 256;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  right_multiply_kernel<<<grid, 256, static_cast<size_t>(K) * C * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+      in, ldin, K, p, rowscale, M, C, out, ldout);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
+                          const int* split_f1, int nsplit, double* out_part, long ldo, void* stream) {
+  if (!Xt || !Bm || !split_f0 || !split_f1 || !out_part || C < 1 || (ld % 2) != 0 || (ldo % 2) != 0) return MBPLS_ERR_ARG;
+  if (nsplit == 0 || n == 0) return MBPLS_OK;
+  if (nsplit > 65535) return MBPLS_ERR_SIZE;
+  dim3 grid((n + 511) / 512, nsplit);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    const int nc = C - c0;
+    if (nc >= 16 || nc > 8) skinny_gemm_kernel<16><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+    else if (nc > 4) skinny_gemm_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+    else if (nc > 2) skinny_gemm_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+    else if (nc > 1) skinny_gemm_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+    else skinny_gemm_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, const double* pvec, void* stream) {
+  if (!Xt || !ts || !pvec) return MBPLS_ERR_ARG;
+  if (p == 0 || n == 0) return MBPLS_OK;
+  int gx = (n + 255) / 256;
+  if (gx > 64) gx = 64;
+  for (int j0 = 0; j0 < p; j0 += 65535) {
+    const int pj = (p - j0) < 65535 ? (p - j0) : 65535;
+    dim3 grid(gx, pj);
+    rank1_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt + static_cast<size_t>(j0) * ld, ld, n, pj, ts,
+                                                                            pvec + j0);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_rows_sumsq_f64(const double* M, long ld, int rows, int n, double* out, void* stream) {
+  if (!M || !out || rows < 0) return MBPLS_ERR_ARG;
+  if (rows == 0) return MBPLS_OK;
+  rows_sumsq_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(M, ld, n, out);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_rows_scale_f64(double* M, long ld, int rows, int n, const double* scale, int divide, void* stream) {
+  if (!M || !scale || rows < 0 || rows > 65535) return MBPLS_ERR_ARG;
+  if (rows == 0 || n == 0) return MBPLS_OK;
+  int gx = (n + 255) / 256;
+  if (gx > 256) gx = 256;
+  dim3 grid(gx, rows);
+  rows_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(M, ld, n, scale, divide);
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"

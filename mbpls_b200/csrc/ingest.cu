@@ -1,0 +1,341 @@
+// Ingest + preprocessing kernels: row-major -> feature-major transpose, NaN census, fused
+// column standardisation (the reference's StandardScaler.fit_transform, mbpls/mbpls.py:307,314,
+// 325-326), standardise-apply for new data (:1097,:1369), per-feature sums of squares
+// (varx / varxblocks, :822-830, :938-945).
+#include "stream.cuh"
+#include "launch.cuh"
+
+using namespace mbpls;
+
+// ------------------------------------------------------------------------------------------
+// transpose: src is a row-major chunk (rows x cols, leading dim lds) of one block; it lands in
+// the feature-major matrix at features [0, cols) (dst already offset to the block) and samples
+// [row0, row0 + rows).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_in_kernel(const double* __restrict__ src, long lds, int rows, int cols,
+                                                           double* __restrict__ dst, long ld, int row0) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[static_cast<size_t>(r) * lds + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < rows && c < cols) dst[static_cast<size_t>(c) * ld + row0 + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// feature-major -> row-major (used to hand standardised blocks back when copy=False and for tests)
+__global__ void __launch_bounds__(256) transpose_out_kernel(const double* __restrict__ src, long ld, int rows, int cols,
+                                                            double* __restrict__ dst, long ldd, int row0) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[static_cast<size_t>(c) * ld + row0 + r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < rows && c < cols) dst[static_cast<size_t>(r) * ldd + c] = tile[tx][ty + 8 * k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NaN census (mbpls/mbpls.py:255-271): per-feature NaN count and per-(block,row) NaN flag.
+// One warp per feature; row flags are idempotent byte stores (every writer stores 1).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) census_kernel(const double* __restrict__ Xt, long ld, int n, int p,
+                                                     const int* __restrict__ block_off, int B,
+                                                     int* __restrict__ col_nan, unsigned char* __restrict__ row_flag,
+                                                     long ldf) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
+    const int b = block_of(block_off, B, j);
+    const double* x = Xt + static_cast<size_t>(j) * ld;
+    int cnt = 0;
+    for (int i = lane; i < n; i += 32) {
+      if (isnan(x[i])) {
+        ++cnt;
+        row_flag[static_cast<size_t>(b) * ldf + i] = 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(MBPLS_FULL_MASK, cnt, o);
+    if (lane == 0) col_nan[j] = cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Standardisation arithmetic shared by the fused (smem-resident) and the fallback kernels.
+// scikit-learn semantics: nan-aware mean, corrected two-pass population variance, near-constant
+// features get scale 1 (sklearn/preprocessing/_data.py::_is_constant_feature).
+// ------------------------------------------------------------------------------------------
+struct ScalerOut {
+  double* mean;
+  double* var;
+  double* scale;
+  long long* seen;  // observed (non-NaN) count per feature == n_samples_seen_
+  double* zss;      // nansum of the standardised feature squared (for varx)
+};
+
+__device__ __forceinline__ void finish_stats(double cnt, double sum, double& mean) { mean = sum / cnt; }
+
+__device__ __forceinline__ double scale_from(double cnt, double mean, double corr, double ssq, double& var) {
+  ssq -= corr * corr / cnt;
+  var = ssq / cnt;
+  const double eps = 2.220446049250313e-16;
+  const double bound = cnt * eps * var + (cnt * mean * eps) * (cnt * mean * eps);
+  return (var <= bound) ? 1.0 : sqrt(var);
+}
+
+// T threads (a warp, or the whole CTA) cooperate on one resident feature.
+template <bool CTA_WIDE>
+__device__ __forceinline__ void standardize_resident(double* x, int n, int j, const ScalerOut& o, double* scratch) {
+  const int tid = CTA_WIDE ? threadIdx.x : (threadIdx.x & 31);
+  const int nt = CTA_WIDE ? blockDim.x : 32;
+  double v[2] = {0.0, 0.0};  // count, sum
+  for (int i = tid; i < n; i += nt) {
+    const double xi = x[i];
+    if (!isnan(xi)) {
+      v[0] += 1.0;
+      v[1] += xi;
+    }
+  }
+  if (CTA_WIDE) block_sum<2>(v, scratch);
+  else { v[0] = warp_sum(v[0]); v[1] = warp_sum(v[1]); }
+  const double cnt = v[0], mean = v[1] / v[0];
+  double c[2] = {0.0, 0.0};  // correction, sum of squares
+  for (int i = tid; i < n; i += nt) {
+    const double d = x[i] - mean;
+    if (!isnan(d)) {
+      c[0] += d;
+      c[1] += d * d;
+    }
+  }
+  if (CTA_WIDE) block_sum<2>(c, scratch);
+  else { c[0] = warp_sum(c[0]); c[1] = warp_sum(c[1]); }
+  double var;
+  const double scale = scale_from(cnt, mean, c[0], c[1], var);
+  double z[1] = {0.0};
+  for (int i = tid; i < n; i += nt) {
+    double zi = x[i] - mean;
+    zi = zi / scale;
+    x[i] = zi;
+    if (!isnan(zi)) z[0] += zi * zi;
+  }
+  if (CTA_WIDE) block_sum<1>(z, scratch);
+  else z[0] = warp_sum(z[0]);
+  if (tid == 0) {
+    o.mean[j] = mean;
+    o.var[j] = var;
+    o.scale[j] = scale;
+    o.seen[j] = static_cast<long long>(cnt);
+    o.zss[j] = z[0];
+  }
+}
+
+template <bool CTA_WIDE>
+struct StandardizeOp {
+  int n;
+  long ld;
+  ScalerOut out;
+  double* scratch;
+  __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    if (CTA_WIDE) {
+      for (int f = 0; f < nf; ++f) standardize_resident<true>(slab + static_cast<size_t>(f) * ld, n, f0 + f, out, scratch);
+    } else {
+      const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      for (int f = warp; f < nf; f += nw) standardize_resident<false>(slab + static_cast<size_t>(f) * ld, n, f0 + f, out, nullptr);
+    }
+  }
+};
+
+template <bool CTA_WIDE>
+__global__ void __launch_bounds__(256) standardize_fused_kernel(double* __restrict__ Xt, StreamShape sh, int n, ScalerOut out) {
+  __shared__ double scratch[64];
+  StandardizeOp<CTA_WIDE> op{n, sh.ld, out, scratch};
+  stream_feature_slabs<true>(Xt, sh, op);
+}
+
+// Fallback for features too long for shared memory: one CTA per feature straight from global
+// memory (3 reads + 1 write instead of 1 + 1).
+__global__ void __launch_bounds__(256) standardize_global_kernel(double* __restrict__ Xt, long ld, int n, int p, ScalerOut out) {
+  __shared__ double scratch[64];
+  for (int j = blockIdx.x; j < p; j += gridDim.x) {
+    standardize_resident<true>(Xt + static_cast<size_t>(j) * ld, n, j, out, scratch);
+    __syncthreads();
+  }
+}
+
+// transform() of a fitted scaler on new data: z = (x - mean_j) / scale_j, in place, feature-major.
+__global__ void __launch_bounds__(256) standardize_apply_kernel(double* __restrict__ Xt, long ld, int n, int p,
+                                                                const double* __restrict__ mean,
+                                                                const double* __restrict__ scale) {
+  const int j = blockIdx.y;
+  if (j >= p) return;
+  const double m = mean[j], s = scale[j];
+  double* x = Xt + static_cast<size_t>(j) * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double z = x[i] - m;
+    x[i] = z / s;
+  }
+}
+
+// inverse_transform for predictions: y = z * scale_c + mean_c (feature-major q x ld)
+__global__ void __launch_bounds__(256) scaler_inverse_kernel(double* __restrict__ Zt, long ld, int n, int q,
+                                                             const double* __restrict__ mean,
+                                                             const double* __restrict__ scale) {
+  const int c = blockIdx.y;
+  if (c >= q) return;
+  const double m = mean[c], s = scale[c];
+  double* z = Zt + static_cast<size_t>(c) * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double v = z[i] * s;
+    z[i] = v + m;
+  }
+}
+
+// nansum(x_j^2) per feature, one warp per feature.
+__global__ void __launch_bounds__(256) feature_sumsq_kernel(const double* __restrict__ Xt, long ld, int n, int p,
+                                                            double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
+    const double* x = Xt + static_cast<size_t>(j) * ld;
+    double s0 = 0.0, s1 = 0.0;
+    int i = lane;
+    for (; i + 32 < n; i += 64) {
+      const double a = x[i], b = x[i + 32];
+      if (!isnan(a)) s0 += a * a;
+      if (!isnan(b)) s1 += b * b;
+    }
+    if (i < n) {
+      const double a = x[i];
+      if (!isnan(a)) s0 += a * a;
+    }
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) out[j] = s;
+  }
+}
+
+// Deterministic segmented sum: out[s] = sum(v[off[s] .. off[s+1])), one CTA per segment.
+__global__ void __launch_bounds__(256) segsum_kernel(const double* __restrict__ v, const int* __restrict__ off,
+                                                     double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int s = blockIdx.x;
+  const int a = off[s], b = off[s + 1];
+  double acc = 0.0;
+  for (int i = a + threadIdx.x; i < b; i += blockDim.x) acc += v[i];
+  acc = block_sum1(acc, scratch);
+  if (threadIdx.x == 0) out[s] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int mbpls_transpose_in_f64(const double* src, long lds, int rows, int cols, double* dst, long ld, int row0, void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0) return MBPLS_ERR_ARG;
+  if (rows == 0 || cols == 0) return MBPLS_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_in_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, dst, ld, row0);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_transpose_out_f64(const double* src, long ld, int rows, int cols, double* dst, long ldd, int row0, void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0) return MBPLS_ERR_ARG;
+  if (rows == 0 || cols == 0) return MBPLS_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_out_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, rows, cols, dst, ldd, row0);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nan_census_f64(const double* Xt, long ld, int n, int p, const int* block_off, int B, int* col_nan,
+                         unsigned char* row_flag, long ldf, void* stream) {
+  if (!Xt || !block_off || !col_nan || !row_flag || B < 1) return MBPLS_ERR_ARG;
+  if (p == 0 || n == 0) return MBPLS_OK;
+  int grid = (p + 7) / 8;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  census_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, block_off, B, col_nan, row_flag, ldf);
+  MBPLS_RETURN_LAST();
+}
+
+// mode: 0 = auto (fused smem-resident pipeline when a feature fits, else global fallback),
+//       1 = force the global-memory fallback.
+int mbpls_standardize_fit_f64(double* Xt, long ld, int n, int p, double* mean, double* var, double* scale,
+                              long long* seen, double* zss, int mode, void* stream) {
+  if (!Xt || !mean || !var || !scale || !seen || !zss || ld < n || (ld % 16) != 0) return MBPLS_ERR_ARG;
+  if (p == 0 || n == 0) return MBPLS_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScalerOut out{mean, var, scale, seen, zss};
+  StreamShape sh;
+  bool cta_wide = false;
+  if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
+    const size_t smem = stream_smem_bytes(sh);
+    const int grid = stream_grid(sh, smem);
+    if (cta_wide) {
+      cudaFuncSetAttribute(standardize_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      standardize_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, n, out);
+    } else {
+      cudaFuncSetAttribute(standardize_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      standardize_fused_kernel<false><<<grid, 256, smem, st>>>(Xt, sh, n, out);
+    }
+  } else {
+    int grid = p < num_sms() * 8 ? p : num_sms() * 8;
+    standardize_global_kernel<<<grid, 256, 0, st>>>(Xt, ld, n, p, out);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_standardize_apply_f64(double* Xt, long ld, int n, int p, const double* mean, const double* scale, void* stream) {
+  if (!Xt || !mean || !scale) return MBPLS_ERR_ARG;
+  if (p == 0 || n == 0) return MBPLS_OK;
+  int gx = (n + 255) / 256;
+  if (gx > 64) gx = 64;
+  for (int j0 = 0; j0 < p; j0 += 65535) {
+    const int pj = (p - j0) < 65535 ? (p - j0) : 65535;
+    dim3 grid(gx, pj);
+    standardize_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt + static_cast<size_t>(j0) * ld, ld, n, pj,
+                                                                                 mean + j0, scale + j0);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_scaler_inverse_f64(double* Zt, long ld, int n, int q, const double* mean, const double* scale, void* stream) {
+  if (!Zt || !mean || !scale || q > 65535) return MBPLS_ERR_ARG;
+  if (q == 0 || n == 0) return MBPLS_OK;
+  int gx = (n + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, q);
+  scaler_inverse_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Zt, ld, n, q, mean, scale);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_feature_sumsq_f64(const double* Xt, long ld, int n, int p, double* out, void* stream) {
+  if (!Xt || !out) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  int grid = (p + 7) / 8;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  feature_sumsq_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, out);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_segsum_f64(const double* v, const int* off, int nseg, double* out, void* stream) {
+  if (!v || !off || !out || nseg < 0) return MBPLS_ERR_ARG;
+  if (nseg == 0) return MBPLS_OK;
+  segsum_kernel<<<nseg, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, off, out);
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"

@@ -1,0 +1,687 @@
+// NIPALS inner loop of multiblock PLS (mbpls/mbpls.py:809-993), dense and NaN-masked.
+//
+// One trip of the reference's `while diff_t > max_tol` loop (:841-914) is three launches:
+//   xtu      : w~_j = x_j . u / u'u for every local feature j (+ per-CTA partial sums of w~_j^2 per block)
+//   xw       : partial t~_b = sum_j w~_j x_j over a split of block b's features, for a chunk of samples
+//   epilogue : fixed-order reduction of the partials, block-weight normalisation (deferred scalar),
+//              superweights, superscore, convergence metric, Y weights and Y scores (:877-914)
+// and one component is closed by `loadings_deflate` (:917-930, :968-969), which keeps each feature
+// resident in shared memory between the loading dot product and the rank-1 update (1 read + 1 write),
+// and can also emit the next component's first w~ (u restarts from the same Y column every
+// component, :838, and Y is never deflated, :971-972).
+//
+// Every kernel starts with `if (*done) return;` so the host may enqueue trips in batches without
+// reading the convergence flag after each one: trips launched after convergence are no-ops and the
+// state left in device memory is exactly the state at loop exit.
+#include "launch.cuh"
+#include "../../include/mbpls_b200.h"
+
+using namespace mbpls;
+
+// ------------------------------------------------------------------------------------------
+// xtu: one warp handles two features at a time, lanes stride along the sample axis with 16-byte
+// loads, four loads per feature in flight.  NaN mode accumulates the masked denominator in the same
+// pass (mbpls/mbpls.py:848-852); a column that turns out to be fully observed uses the plain u'u
+// exactly like the reference's dense branch (:847).
+// ------------------------------------------------------------------------------------------
+template <bool NANMODE>
+__device__ __forceinline__ void dot_accum(const double2 x, const double2 u, double& num, double& den, int& sawnan) {
+  if (NANMODE) {
+    const bool ox = !isnan(x.x), oy = !isnan(x.y);
+    num = fma(ox ? x.x : 0.0, u.x, num);
+    num = fma(oy ? x.y : 0.0, u.y, num);
+    den = fma(ox ? u.x : 0.0, u.x, den);
+    den = fma(oy ? u.y : 0.0, u.y, den);
+    sawnan |= (!ox) | (!oy);
+  } else {
+    num = fma(x.x, u.x, num);
+    num = fma(x.y, u.y, num);
+  }
+}
+
+template <bool NANMODE>
+__global__ void __launch_bounds__(256)
+xtu_kernel(const double* __restrict__ Xt, long ld, int n, int p, int feats_per_cta, const double* __restrict__ u,
+           const double* __restrict__ uu_ptr,  // plain denominator u'u; nullptr -> 1 (loadings, :920)
+           const int* __restrict__ block_off, int B, double* __restrict__ w, double* __restrict__ norm_part,
+           const int* __restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ double wsm[];  // feats_per_cta doubles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int f_begin = blockIdx.x * feats_per_cta;
+  const int f_end = min(p, f_begin + feats_per_cta);
+  const double uu = uu_ptr ? *uu_ptr : 1.0;
+  const int n2 = n >> 1;
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(u);
+
+  for (int j = f_begin + 2 * warp; j < f_end; j += 2 * nw) {
+    const bool two = (j + 1 < f_end);
+    const double2* __restrict__ x0 = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(j) * ld);
+    const double2* __restrict__ x1 = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(two ? j + 1 : j) * ld);
+    double na[2] = {0.0, 0.0}, nb[2] = {0.0, 0.0}, da[2] = {0.0, 0.0}, db[2] = {0.0, 0.0};
+    int nan0 = 0, nan1 = 0;
+    int i = lane;
+    for (; i + 96 < n2; i += 128) {
+      double2 a[4], b[4], uv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = ld_stream(x0 + i + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b[k] = ld_stream(x1 + i + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) uv[k] = u2[i + 32 * k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dot_accum<NANMODE>(a[k], uv[k], na[k & 1], da[k & 1], nan0);
+        dot_accum<NANMODE>(b[k], uv[k], nb[k & 1], db[k & 1], nan1);
+      }
+    }
+    for (; i < n2; i += 32) {
+      const double2 uv = u2[i];
+      dot_accum<NANMODE>(ld_stream(x0 + i), uv, na[0], da[0], nan0);
+      dot_accum<NANMODE>(ld_stream(x1 + i), uv, nb[0], db[0], nan1);
+    }
+    if ((n & 1) && lane == 0) {  // odd tail element
+      const double ut = u[n - 1];
+      const double xa = Xt[static_cast<size_t>(j) * ld + n - 1];
+      const double xb = Xt[static_cast<size_t>(two ? j + 1 : j) * ld + n - 1];
+      dot_accum<NANMODE>(make_double2(xa, 0.0), make_double2(ut, 0.0), na[0], da[0], nan0);
+      dot_accum<NANMODE>(make_double2(xb, 0.0), make_double2(ut, 0.0), nb[0], db[0], nan1);
+    }
+    const double num0 = warp_sum(na[0] + na[1]);
+    const double num1 = warp_sum(nb[0] + nb[1]);
+    double w0, w1;
+    if (NANMODE) {
+      const double den0 = warp_sum(da[0] + da[1]);
+      const double den1 = warp_sum(db[0] + db[1]);
+      nan0 = warp_or(nan0);
+      nan1 = warp_or(nan1);
+      w0 = nan0 ? num0 / den0 : num0 / uu;
+      w1 = nan1 ? num1 / den1 : num1 / uu;
+      if (!uu_ptr) {  // loadings: dense columns are not divided (:920), masked ones are (:923-925)
+        w0 = nan0 ? num0 / den0 : num0;
+        w1 = nan1 ? num1 / den1 : num1;
+      }
+    } else {
+      w0 = uu_ptr ? num0 / uu : num0;
+      w1 = uu_ptr ? num1 / uu : num1;
+    }
+    if (lane == 0) {
+      w[j] = w0;
+      wsm[j - f_begin] = w0;
+      if (two) {
+        w[j + 1] = w1;
+        wsm[j + 1 - f_begin] = w1;
+      }
+    }
+  }
+  if (!norm_part) return;
+  __syncthreads();
+  // per-CTA partial of ||w~_b||^2 for every block, fixed order inside the CTA
+  for (int b = warp; b < B; b += nw) {
+    const int lo = max(block_off[b], f_begin), hi = min(block_off[b + 1], f_end);
+    double s = 0.0;
+    for (int j = lo + lane; j < hi; j += 32) {
+      const double v = wsm[j - f_begin];
+      s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) norm_part[static_cast<size_t>(blockIdx.x) * B + b] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// xw: each thread owns two consecutive samples; the CTA walks the features of its split eight at a
+// time (eight independent 16-byte loads in flight per thread) and accumulates w~_j * x_ij in
+// registers.  NaN mode also accumulates the masked sum of w~_j^2 (mbpls/mbpls.py:867-872).
+// grid = (sample chunks of 512, splits); partials go to Tnum[split][ld] (and Tden).
+// ------------------------------------------------------------------------------------------
+template <bool NANMODE>
+__global__ void __launch_bounds__(256)
+xw_kernel(const double* __restrict__ Xt, long ld, int n, const double* __restrict__ w,
+          const int* __restrict__ split_f0, const int* __restrict__ split_f1, double* __restrict__ Tnum,
+          double* __restrict__ Tden, long ldt, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int s = blockIdx.y;
+  const int f0 = split_f0[s], f1 = split_f1[s];
+  const int r = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (r >= n) return;
+  const double* __restrict__ xp = Xt + r;
+  double nx = 0.0, ny = 0.0, dx = 0.0, dy = 0.0;
+  int j = f0;
+  for (; j + 8 <= f1; j += 8) {
+    double2 x[8];
+    double wj[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j + k) * ld));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wj[k] = __ldg(w + j + k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (NANMODE) {
+        const bool ox = !isnan(x[k].x), oy = !isnan(x[k].y);
+        const double w2 = wj[k] * wj[k];
+        nx = fma(ox ? x[k].x : 0.0, wj[k], nx);
+        ny = fma(oy ? x[k].y : 0.0, wj[k], ny);
+        dx += ox ? w2 : 0.0;
+        dy += oy ? w2 : 0.0;
+      } else {
+        nx = fma(x[k].x, wj[k], nx);
+        ny = fma(x[k].y, wj[k], ny);
+      }
+    }
+  }
+  for (; j < f1; ++j) {
+    const double2 x = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j) * ld));
+    const double wj = __ldg(w + j);
+    if (NANMODE) {
+      const bool ox = !isnan(x.x), oy = !isnan(x.y);
+      const double w2 = wj * wj;
+      nx = fma(ox ? x.x : 0.0, wj, nx);
+      ny = fma(oy ? x.y : 0.0, wj, ny);
+      dx += ox ? w2 : 0.0;
+      dy += oy ? w2 : 0.0;
+    } else {
+      nx = fma(x.x, wj, nx);
+      ny = fma(x.y, wj, ny);
+    }
+  }
+  double* tn = Tnum + static_cast<size_t>(s) * ldt + r;
+  *reinterpret_cast<double2*>(tn) = make_double2(nx, ny);  // r is even and r+1 < ldt (ld % 16 == 0)
+  if (NANMODE) {
+    double* td = Tden + static_cast<size_t>(s) * ldt + r;
+    *reinterpret_cast<double2*>(td) = make_double2(dx, dy);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce_partials: red[b][i] = sum over the splits of block b (ascending split index) of Tnum, same
+// for Tden; red tail holds ||w~_b||^2 = sum over xtu CTAs (ascending) of norm_part.  `red` is the
+// buffer that is all-reduced across GPUs when features are sharded.
+// layout of red: [B][ldt] numerators | [B][ldt] denominators (NaN mode only) | [B] squared norms
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* __restrict__ Tnum, const double* __restrict__ Tden, long ldt, int n, int B,
+                       const int* __restrict__ block_split_off, const double* __restrict__ norm_part, int n_norm_parts,
+                       double* __restrict__ red, int nanmode, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int b = blockIdx.y;
+  const int s0 = block_split_off[b], s1 = block_split_off[b + 1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double a = 0.0, d = 0.0;
+    for (int s = s0; s < s1; ++s) a += Tnum[static_cast<size_t>(s) * ldt + i];
+    red[static_cast<size_t>(b) * ldt + i] = a;
+    if (nanmode) {
+      for (int s = s0; s < s1; ++s) d += Tden[static_cast<size_t>(s) * ldt + i];
+      red[static_cast<size_t>(B + b) * ldt + i] = d;
+    }
+  }
+  if (blockIdx.x == 0) {  // squared block-weight norm: fixed-order tree over the xtu CTAs
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < n_norm_parts; c += blockDim.x) acc += norm_part[static_cast<size_t>(c) * B + b];
+    acc = block_sum1(acc, scratch);
+    if (threadIdx.x == 0) red[static_cast<size_t>(nanmode ? 2 * B : B) * ldt + b] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// begin_component: u <- u0 (mbpls/mbpls.py:832-838), u'u, trip counter 0, diff 1, done 0.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+begin_component_kernel(const double* __restrict__ u0, int n, double* __restrict__ u, double* __restrict__ scal,
+                       int* __restrict__ ctrl) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = u0[i];
+    u[i] = v;
+    acc = fma(v, v, acc);
+  }
+  acc = block_sum1(acc, scratch);
+  if (threadIdx.x == 0) {
+    scal[MBPLS_SCAL_UU] = acc;
+    scal[MBPLS_SCAL_DIFF] = 1.0;
+    ctrl[MBPLS_CTRL_DONE] = 0;
+    ctrl[MBPLS_CTRL_TRIPS] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue: single CTA, fixed-order reductions -> bitwise reproducible on every GPU.
+// ------------------------------------------------------------------------------------------
+#define EPI_MAXB 64
+#define EPI_MAXQ 64
+
+__global__ void __launch_bounds__(1024) nipals_epilogue_kernel(mbpls_epilogue_args a) {
+  int* ctrl = a.ctrl;
+  if (ctrl[MBPLS_CTRL_DONE]) return;
+  __shared__ double scratch[32 * 4];
+  __shared__ double s_norm[EPI_MAXB], s_a[EPI_MAXB], s_v[EPI_MAXQ], s_vnum[EPI_MAXQ], s_vden[EPI_MAXQ];
+  __shared__ double s_sc[8];
+  const int n = a.n, B = a.B, q = a.q;
+  const long ldt = a.ldt;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nan = a.nanmode;
+  const double* red_num = a.red;
+  const double* red_den = a.red + static_cast<size_t>(B) * ldt;
+  const double* red_nrm = a.red + static_cast<size_t>(nan ? 2 * B : B) * ldt;
+  const double uu = a.scal[MBPLS_SCAL_UU];
+
+  if (tid < B) s_norm[tid] = sqrt(red_nrm[tid]);
+  __syncthreads();
+
+  // phase 1: block scores t_b (:862-875) and T'u (:879)
+  for (int b = 0; b < B; ++b) {
+    const double nb = s_norm[b];
+    double acc = 0.0;
+    double* tb = a.T + static_cast<size_t>(b) * ldt;
+    for (int i = tid; i < n; i += nt) {
+      const double num = red_num[static_cast<size_t>(b) * ldt + i];
+      double t;
+      if (nan && a.row_flag[static_cast<size_t>(b) * a.ldf + i]) t = nb * num / red_den[static_cast<size_t>(b) * ldt + i];
+      else t = num / nb;
+      tb[i] = t;
+      acc = fma(t, a.u[i], acc);
+    }
+    acc = block_sum1(acc, scratch);
+    if (tid == 0) s_a[b] = acc / uu;
+  }
+  __syncthreads();
+  if (tid == 0) {  // superweights to unit length (:880)
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) s = fma(s_a[b], s_a[b], s);
+    s = sqrt(s);
+    for (int b = 0; b < B; ++b) {
+      s_a[b] /= s;
+      a.a[b] = s_a[b];
+    }
+  }
+  __syncthreads();
+
+  // phase 2: superscore ts = T a, normalised (:882-883)
+  double ss = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    double t = 0.0;
+    for (int b = 0; b < B; ++b) t = fma(a.T[static_cast<size_t>(b) * ldt + i], s_a[b], t);
+    a.ts[i] = t;
+    ss = fma(t, t, ss);
+  }
+  ss = block_sum1(ss, scratch);
+  const double tsn = sqrt(ss);
+
+  // phase 3: normalise, convergence metric against ts_old (:884-888), ts'ts
+  double v4[4] = {0.0, 0.0, 0.0, 0.0};  // sum d^2, sum |d|, (unused), ts'ts
+  double dmax = 0.0, dmin = INFINITY;
+  for (int i = tid; i < n; i += nt) {
+    const double t = a.ts[i] / tsn;
+    const double d = a.ts_old[i] - t;
+    a.ts[i] = t;
+    a.ts_old[i] = t;
+    v4[0] = fma(d, d, v4[0]);
+    v4[1] += fabs(d);
+    dmax = fmax(dmax, fabs(d));
+    dmin = fmin(dmin, fabs(d));
+    v4[3] = fma(t, t, v4[3]);
+  }
+  block_sum<4>(v4, scratch);
+  dmax = warp_max(dmax);
+  dmin = warp_min(dmin);
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    scratch[tid >> 5] = dmax;
+    scratch[32 + (tid >> 5)] = dmin;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0, mn = INFINITY;
+    for (int wv = 0; wv < (nt >> 5); ++wv) {
+      mx = fmax(mx, scratch[wv]);
+      mn = fmin(mn, scratch[32 + wv]);
+    }
+    double diff;
+    switch (a.norm_kind) {
+      case MBPLS_NORM_L1: diff = v4[1]; break;
+      case MBPLS_NORM_MAX: diff = mx; break;
+      case MBPLS_NORM_MIN: diff = mn; break;
+      default: diff = sqrt(v4[0]);
+    }
+    s_sc[0] = diff;
+  }
+  __syncthreads();
+  const double tt = v4[3];
+
+  // phase 4: Y weights v = Y'ts / ts'ts (:890-899), masked for Y columns with NaN
+  for (int c = 0; c < q; ++c) {
+    const double* y = a.Yt + static_cast<size_t>(c) * ldt;
+    double nd[2] = {0.0, 0.0};
+    const bool masked = nan && a.ycol_flag[c];
+    for (int i = tid; i < n; i += nt) {
+      const double yi = y[i], t = a.ts[i];
+      if (masked) {
+        if (!isnan(yi)) {
+          nd[0] = fma(yi, t, nd[0]);
+          nd[1] = fma(t, t, nd[1]);
+        }
+      } else {
+        nd[0] = fma(yi, t, nd[0]);
+      }
+    }
+    block_sum<2>(nd, scratch);
+    if (tid == 0) s_v[c] = masked ? nd[0] / nd[1] : nd[0] / tt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int c = 0; c < q; ++c) {
+      s = fma(s_v[c], s_v[c], s);
+      a.v[c] = s_v[c];
+    }
+    s_sc[1] = s;
+  }
+  __syncthreads();
+  const double vv = s_sc[1];
+
+  // phase 5: Y scores u = Y v / v'v, normalised (:901-913).  NaN mode: rows flagged in the *last X
+  // block* use observed Y columns only (the reference indexes sparse_X_info_[block] at :903).
+  double un = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    double val;
+    if (nan && a.row_flag[static_cast<size_t>(B - 1) * a.ldf + i]) {
+      double num = 0.0, den = 0.0;
+      for (int c = 0; c < q; ++c) {
+        const double yi = a.Yt[static_cast<size_t>(c) * ldt + i];
+        if (!isnan(yi)) {
+          num = fma(yi, s_v[c], num);
+          den = fma(s_v[c], s_v[c], den);
+        }
+      }
+      val = num / den;
+    } else {
+      double num = 0.0;
+      for (int c = 0; c < q; ++c) num = fma(a.Yt[static_cast<size_t>(c) * ldt + i], s_v[c], num);
+      val = num / vv;
+    }
+    a.u[i] = val;
+    un = fma(val, val, un);
+  }
+  un = block_sum1(un, scratch);
+  const double unorm = sqrt(un);
+  double uu_new = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    const double val = a.u[i] / unorm;
+    a.u[i] = val;
+    uu_new = fma(val, val, uu_new);
+  }
+  uu_new = block_sum1(uu_new, scratch);
+  if (tid == 0) {
+    const int trips = ctrl[MBPLS_CTRL_TRIPS] + 1;
+    ctrl[MBPLS_CTRL_TRIPS] = trips;
+    a.scal[MBPLS_SCAL_UU] = uu_new;
+    a.scal[MBPLS_SCAL_TT] = tt;
+    a.scal[MBPLS_SCAL_VV] = vv;
+    if (trips > 1) {  // the first trip has nothing to compare with (:884-885)
+      a.scal[MBPLS_SCAL_DIFF] = s_sc[0];
+      if (!(s_sc[0] > a.max_tol)) ctrl[MBPLS_CTRL_DONE] = 1;
+    }
+    if (a.diff_trace && trips <= a.diff_trace_len) a.diff_trace[trips - 1] = trips > 1 ? s_sc[0] : 1.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// record_component: append the converged component to the result arrays (mbpls/mbpls.py:975-983).
+// Component-major storage: Wt/W/P are K x p_local, Ts/U are K x ldt, T is B x K x ldt.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+record_component_kernel(mbpls_record_args a) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gsz = gridDim.x * blockDim.x;
+  const double* red_nrm = a.red + static_cast<size_t>(a.nanmode ? 2 * a.B : a.B) * a.ldt;
+  for (int j = gid; j < a.p; j += gsz) {
+    const int b = block_of(a.block_off, a.B, j);
+    const double wt = a.w[j];
+    a.Wt_k[j] = wt;
+    a.W_k[j] = wt / sqrt(red_nrm[b]);
+  }
+  for (int i = gid; i < a.n; i += gsz) {
+    a.Ts_k[i] = a.ts[i];
+    a.U_k[i] = a.u[i];
+    for (int b = 0; b < a.B; ++b) a.T_k[static_cast<size_t>(b) * a.T_block_stride + i] = a.T[static_cast<size_t>(b) * a.ldt + i];
+  }
+  if (gid < a.q) a.V_k[gid] = a.v[gid];
+  if (gid < a.B) a.A_k[gid] = a.a[gid] * a.a[gid];
+}
+
+// ------------------------------------------------------------------------------------------
+// loadings + deflation on a resident feature (mbpls/mbpls.py:917-930, :968-969) and, optionally,
+// the first w~ of the next component (:847/:856 with u = u0).
+// ------------------------------------------------------------------------------------------
+struct DeflateParams {
+  int n;
+  long ld;
+  int nanmode;
+  const double* ts;
+  const double* u0;       // may be null (no fused next-XtU)
+  const double* u0u0;     // device scalar u0'u0
+  double* P_k;            // p_local loadings out
+  double* w_next;         // p_local next w~ out (if u0)
+  double* pss;            // p_local: p_j^2 (for explained variance), always written
+};
+
+template <bool CTA_WIDE>
+__device__ __forceinline__ void deflate_resident(double* x, int j, const DeflateParams& P, double* scratch) {
+  const int tid = CTA_WIDE ? threadIdx.x : (threadIdx.x & 31);
+  const int nt = CTA_WIDE ? blockDim.x : 32;
+  const int n = P.n;
+  double v[3] = {0.0, 0.0, 0.0};  // num, masked ts'ts, NaN seen
+  for (int i = tid; i < n; i += nt) {
+    const double xi = x[i], t = P.ts[i];
+    if (P.nanmode) {
+      if (!isnan(xi)) {
+        v[0] = fma(xi, t, v[0]);
+        v[1] = fma(t, t, v[1]);
+      } else {
+        v[2] = 1.0;
+      }
+    } else {
+      v[0] = fma(xi, t, v[0]);
+    }
+  }
+  if (CTA_WIDE) block_sum<3>(v, scratch);
+  else { v[0] = warp_sum(v[0]); v[1] = warp_sum(v[1]); v[2] = warp_sum(v[2]); }
+  const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
+  double w[3] = {0.0, 0.0, 0.0};  // next: num, masked u0'u0, NaN seen
+  for (int i = tid; i < n; i += nt) {
+    const double xi = __dsub_rn(x[i], __dmul_rn(P.ts[i], pj));  // not contracted: the reference rounds ts*p first (:969)
+    x[i] = xi;
+    if (P.u0) {
+      const double uv = P.u0[i];
+      if (P.nanmode) {
+        if (!isnan(xi)) {
+          w[0] = fma(xi, uv, w[0]);
+          w[1] = fma(uv, uv, w[1]);
+        } else {
+          w[2] = 1.0;
+        }
+      } else {
+        w[0] = fma(xi, uv, w[0]);
+      }
+    }
+  }
+  if (P.u0) {
+    if (CTA_WIDE) block_sum<3>(w, scratch);
+    else { w[0] = warp_sum(w[0]); w[1] = warp_sum(w[1]); w[2] = warp_sum(w[2]); }
+  }
+  if (tid == 0) {
+    P.P_k[j] = pj;
+    P.pss[j] = pj * pj;
+    if (P.u0) P.w_next[j] = (P.nanmode && w[2] > 0.0) ? w[0] / w[1] : w[0] / *P.u0u0;
+  }
+}
+
+template <bool CTA_WIDE>
+struct DeflateOp {
+  DeflateParams P;
+  double* scratch;
+  __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    if (CTA_WIDE) {
+      for (int f = 0; f < nf; ++f) deflate_resident<true>(slab + static_cast<size_t>(f) * P.ld, f0 + f, P, scratch);
+    } else {
+      const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      for (int f = warp; f < nf; f += nw) deflate_resident<false>(slab + static_cast<size_t>(f) * P.ld, f0 + f, P, nullptr);
+    }
+  }
+};
+
+template <bool CTA_WIDE>
+__global__ void __launch_bounds__(256) loadings_deflate_fused_kernel(double* __restrict__ Xt, StreamShape sh, DeflateParams P) {
+  __shared__ double scratch[96];
+  DeflateOp<CTA_WIDE> op{P, scratch};
+  stream_feature_slabs<true>(Xt, sh, op);
+}
+
+// global-memory fallback (feature too long for shared memory): 2 reads + 1 write
+__global__ void __launch_bounds__(256) loadings_deflate_global_kernel(double* __restrict__ Xt, int p, DeflateParams P) {
+  __shared__ double scratch[96];
+  for (int j = blockIdx.x; j < p; j += gridDim.x) {
+    deflate_resident<true>(Xt + static_cast<size_t>(j) * P.ld, j, P, scratch);
+    __syncthreads();
+  }
+}
+
+// w~ produced by the fused deflation has no per-CTA norm partials; this computes ||w~_b||^2 directly.
+__global__ void __launch_bounds__(256)
+block_sumsq_parts_kernel(const double* __restrict__ w, int p, int feats_per_cta, const int* __restrict__ block_off, int B,
+                         double* __restrict__ norm_part, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int f_begin = blockIdx.x * feats_per_cta, f_end = min(p, f_begin + feats_per_cta);
+  for (int b = warp; b < B; b += nw) {
+    const int lo = max(block_off[b], f_begin), hi = min(block_off[b + 1], f_end);
+    double s = 0.0;
+    for (int j = lo + lane; j < hi; j += 32) {
+      const double v = w[j];
+      s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) norm_part[static_cast<size_t>(blockIdx.x) * B + b] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int mbpls_xtu_feats_per_cta(int p) {
+  // ~32 CTAs per SM worth of work items keeps the tail short; multiple of 16 (8 warps x 2 features)
+  long target = (static_cast<long>(p) + static_cast<long>(num_sms()) * 32 - 1) / (static_cast<long>(num_sms()) * 32);
+  long f = ((target + 15) / 16) * 16;
+  if (f < 16) f = 16;
+  if (f > 4096) f = 4096;
+  return static_cast<int>(f);
+}
+
+int mbpls_xtu_num_ctas(int p) {
+  const int f = mbpls_xtu_feats_per_cta(p);
+  return (p + f - 1) / f;
+}
+
+int mbpls_nipals_xtu_f64(const double* Xt, long ld, int n, int p, const double* u, const double* uu, const int* block_off,
+                         int B, double* w, double* norm_part, int nanmode, const int* done, void* stream) {
+  if (!Xt || !u || !w || !block_off || B < 1 || (ld % 2) != 0) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  const int f = mbpls_xtu_feats_per_cta(p);
+  const int grid = (p + f - 1) / f;
+  const size_t smem = static_cast<size_t>(f) * sizeof(double);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nanmode) xtu_kernel<true><<<grid, 256, smem, st>>>(Xt, ld, n, p, f, u, uu, block_off, B, w, norm_part, done);
+  else xtu_kernel<false><<<grid, 256, smem, st>>>(Xt, ld, n, p, f, u, uu, block_off, B, w, norm_part, done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_block_sumsq_parts_f64(const double* w, int p, const int* block_off, int B, double* norm_part, const int* done,
+                                void* stream) {
+  if (!w || !block_off || !norm_part) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  const int f = mbpls_xtu_feats_per_cta(p);
+  const int grid = (p + f - 1) / f;
+  block_sumsq_parts_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, p, f, block_off, B, norm_part, done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_xw_f64(const double* Xt, long ld, int n, const double* w, const int* split_f0, const int* split_f1,
+                        int nsplit, double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream) {
+  if (!Xt || !w || !split_f0 || !split_f1 || !Tnum || (nanmode && !Tden) || (ld % 2) != 0 || (ldt % 2) != 0) return MBPLS_ERR_ARG;
+  if (nsplit == 0 || n == 0) return MBPLS_OK;
+  if (nsplit > 65535) return MBPLS_ERR_SIZE;
+  dim3 grid((n + 511) / 512, nsplit);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nanmode) xw_kernel<true><<<grid, 256, 0, st>>>(Xt, ld, n, w, split_f0, split_f1, Tnum, Tden, ldt, done);
+  else xw_kernel<false><<<grid, 256, 0, st>>>(Xt, ld, n, w, split_f0, split_f1, Tnum, Tden, ldt, done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_reduce_partials_f64(const double* Tnum, const double* Tden, long ldt, int n, int B,
+                                     const int* block_split_off, const double* norm_part, int n_norm_parts, double* red,
+                                     int nanmode, const int* done, void* stream) {
+  if (!Tnum || !block_split_off || !norm_part || !red || B < 1 || B > 65535) return MBPLS_ERR_ARG;
+  dim3 grid((n + 255) / 256, B);
+  reduce_partials_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Tnum, Tden, ldt, n, B, block_split_off, norm_part,
+                                                                             n_norm_parts, red, nanmode, done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_begin_component_f64(const double* u0, int n, double* u, double* scal, int* ctrl, void* stream) {
+  if (!u0 || !u || !scal || !ctrl) return MBPLS_ERR_ARG;
+  begin_component_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(u0, n, u, scal, ctrl);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_epilogue_f64(const mbpls_epilogue_args* args, void* stream) {
+  if (!args || !args->red || !args->T || !args->u || !args->ts || !args->ts_old || !args->Yt || !args->a || !args->v ||
+      !args->scal || !args->ctrl)
+    return MBPLS_ERR_ARG;
+  if (args->B < 1 || args->B > EPI_MAXB || args->q < 1 || args->q > EPI_MAXQ) return MBPLS_ERR_SIZE;
+  if (args->nanmode && (!args->row_flag || !args->ycol_flag)) return MBPLS_ERR_ARG;
+  nipals_epilogue_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*args);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_record_component_f64(const mbpls_record_args* args, void* stream) {
+  if (!args) return MBPLS_ERR_ARG;
+  const int m = args->p > args->n ? args->p : args->n;
+  int grid = (m + 255) / 256;
+  if (grid < 1) grid = 1;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  record_component_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*args);
+  MBPLS_RETURN_LAST();
+}
+
+// mode: 0 = auto (resident pipeline when a feature fits in shared memory), 1 = global fallback
+int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* ts, const double* u0, const double* u0u0,
+                               double* P_k, double* w_next, double* pss, int nanmode, int mode, void* stream) {
+  if (!Xt || !ts || !P_k || !pss || (u0 && (!u0u0 || !w_next)) || ld < n || (ld % 16) != 0) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss};
+  StreamShape sh;
+  bool cta_wide = false;
+  if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
+    const size_t smem = stream_smem_bytes(sh);
+    const int grid = stream_grid(sh, smem);
+    if (cta_wide) {
+      cudaFuncSetAttribute(loadings_deflate_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      loadings_deflate_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, P);
+    } else {
+      cudaFuncSetAttribute(loadings_deflate_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      loadings_deflate_fused_kernel<false><<<grid, 256, smem, st>>>(Xt, sh, P);
+    }
+  } else {
+    int grid = p < num_sms() * 8 ? p : num_sms() * 8;
+    loadings_deflate_global_kernel<<<grid, 256, 0, st>>>(Xt, p, P);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"

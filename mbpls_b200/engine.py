@@ -1,0 +1,448 @@
+"""Device-side driver of the MB-PLS fit path: allocates through PyTorch, launches the sm_100a
+kernels through the C ABI (``_cabi``), and -- when features are sharded over several GPUs -- issues
+the small NCCL all-reduces.  PyTorch is plumbing here (memory, streams, ``torch.distributed``); every
+arithmetic step on the path is one of the kernels in ``csrc/``.
+
+Layouts (see ``include/mbpls_b200.h``): matrices are feature-major ``p x ld`` (``ld = n`` rounded up
+to 16), results component-major ``K x p`` / ``K x ld``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import call
+
+F64 = torch.float64
+
+
+def round_ld(n: int) -> int:
+    return max(16, (int(n) + 15) // 16 * 16)
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(device=None) -> torch.device:
+    """The product path needs a CUDA device and the built library; fail loudly otherwise."""
+    _cabi.load()
+    if not torch.cuda.is_available():
+        raise _cabi.MbplsCudaError("mbpls_b200 requires a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _cabi.MbplsCudaError("mbpls_b200 requires a CUDA device; got %r" % (device,))
+    return device
+
+
+# --------------------------------------------------------------------------------------------- #
+# sharding of the concatenated feature axis: contiguous, near-equal ranges
+# irrespective of block boundaries; every rank keeps a (block, local range) table.
+# --------------------------------------------------------------------------------------------- #
+@dataclass
+class ShardMap:
+    sizes: List[int]            # global block sizes p_b
+    rank: int = 0
+    world: int = 1
+    lo: int = 0                 # global feature range owned by this rank
+    hi: int = 0
+    local_ranges: List[tuple] = field(default_factory=list)  # per block: (start, stop) *within the block*
+    block_off: List[int] = field(default_factory=list)       # B+1 local offsets
+
+    @staticmethod
+    def build(sizes: Sequence[int], rank: int = 0, world: int = 1) -> "ShardMap":
+        sizes = [int(s) for s in sizes]
+        p = sum(sizes)
+        per = -(-p // world)
+        lo, hi = min(p, rank * per), min(p, (rank + 1) * per)
+        m = ShardMap(sizes=sizes, rank=rank, world=world, lo=lo, hi=hi)
+        off, g0 = [0], 0
+        for pb in sizes:
+            a, b = max(lo, g0), min(hi, g0 + pb)
+            if b > a:
+                m.local_ranges.append((a - g0, b - g0))
+                off.append(off[-1] + (b - a))
+            else:
+                m.local_ranges.append((0, 0))
+                off.append(off[-1])
+            g0 += pb
+        m.block_off = off
+        return m
+
+    @property
+    def p_local(self) -> int:
+        return self.block_off[-1]
+
+    @property
+    def p_global(self) -> int:
+        return sum(self.sizes)
+
+
+def _i32(vals, device):
+    return torch.tensor(list(vals), dtype=torch.int32, device=device)
+
+
+# --------------------------------------------------------------------------------------------- #
+# ingest: host / device arrays -> feature-major device matrix
+# --------------------------------------------------------------------------------------------- #
+_STAGE_BYTES = 64 << 20
+
+
+def _upload_rows(dst_t: torch.Tensor, ld: int, src, r0: int, device, stage):
+    """src: 2-D (rows x cols) torch CPU tensor view (row-major, arbitrary row stride)."""
+    rows, cols = src.shape
+    if rows == 0 or cols == 0:
+        return
+    dev_chunk = src.to(device, non_blocking=False) if stage is None else stage(src)
+    if dev_chunk.stride(1) != 1:
+        dev_chunk = dev_chunk.contiguous()
+    call("mbpls_transpose_in_f64", ptr(dev_chunk), dev_chunk.stride(0), rows, cols, ptr(dst_t), ld, r0,
+         stream_ptr(device))
+
+
+def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, device) -> None:
+    """Copy columns [c0, c1) of one n x p_b block into ``dst`` ((c1-c0) x ld, feature-major)."""
+    ld = dst.shape[1]
+    cols = c1 - c0
+    if cols <= 0:
+        return
+    if isinstance(block, torch.Tensor):
+        t = block
+        if t.dtype != F64:
+            t = t.to(F64)
+        view = t[:, c0:c1]
+        if t.is_cuda:
+            if view.stride(0) == 1 and view.shape[0] > 0:  # column-major (= feature-major) device tensor
+                dst[:, :n].copy_(view.t())
+            else:
+                if view.stride(1) != 1:
+                    view = view.contiguous()
+                call("mbpls_transpose_in_f64", ptr(view), view.stride(0), n, cols, ptr(dst), ld, 0, stream_ptr(device))
+                torch.cuda.current_stream(device).synchronize()  # `view` may be a temporary
+            return
+        src = view
+    else:
+        arr = np.asarray(block)
+        if arr.dtype != np.float64:
+            arr = arr.astype(np.float64)
+        view_np = arr[:, c0:c1]
+        if view_np.strides[0] == 8 and n > 1:  # Fortran order: already feature-major on the host
+            dst[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(view_np.T)))
+            return
+        if view_np.strides[1] != 8:
+            view_np = np.ascontiguousarray(view_np)
+        src = torch.from_numpy(view_np)
+    # row-major host data: chunk over rows, transpose on the device
+    rows_per = max(1, _STAGE_BYTES // max(8 * cols, 1))
+    for r0 in range(0, n, rows_per):
+        r1 = min(n, r0 + rows_per)
+        _upload_rows(dst, ld, src[r0:r1], r0, device, None)
+    torch.cuda.current_stream(device).synchronize()
+
+
+def alloc_feature_major(p: int, n: int, device) -> torch.Tensor:
+    ld = round_ld(n)
+    t = torch.empty((max(p, 1), ld), dtype=F64, device=device)[:p]
+    if ld > n:
+        t[:, n:].zero_()
+    return t
+
+
+def ingest_blocks(blocks, n: int, shard: ShardMap, device) -> torch.Tensor:
+    Xt = alloc_feature_major(shard.p_local, n, device)
+    for b, blk in enumerate(blocks):
+        c0, c1 = shard.local_ranges[b]
+        if c1 > c0:
+            o0, o1 = shard.block_off[b], shard.block_off[b + 1]
+            ingest_feature_major(blk, n, c0, c1, Xt[o0:o1], device)
+    return Xt
+
+
+# --------------------------------------------------------------------------------------------- #
+# preprocessing
+# --------------------------------------------------------------------------------------------- #
+@dataclass
+class ScalerStats:
+    mean: torch.Tensor
+    var: torch.Tensor
+    scale: torch.Tensor
+    seen: torch.Tensor   # int64
+    zss: torch.Tensor    # nansum(z^2) per feature
+
+
+def standardize_fit(Xt: torch.Tensor, n: int, mode: int = 0) -> ScalerStats:
+    p, ld = Xt.shape
+    dev = Xt.device
+    st = ScalerStats(*(torch.empty(max(p, 1), dtype=F64, device=dev) for _ in range(3)),
+                     torch.empty(max(p, 1), dtype=torch.int64, device=dev),
+                     torch.empty(max(p, 1), dtype=F64, device=dev))
+    call("mbpls_standardize_fit_f64", ptr(Xt), ld, n, p, ptr(st.mean), ptr(st.var), ptr(st.scale), ptr(st.seen),
+         ptr(st.zss), mode, stream_ptr(dev))
+    return st
+
+
+def standardize_apply(Xt: torch.Tensor, n: int, mean: torch.Tensor, scale: torch.Tensor) -> None:
+    p, ld = Xt.shape
+    call("mbpls_standardize_apply_f64", ptr(Xt), ld, n, p, ptr(mean), ptr(scale), stream_ptr(Xt.device))
+
+
+def feature_sumsq(Xt: torch.Tensor, n: int) -> torch.Tensor:
+    p, ld = Xt.shape
+    out = torch.empty(max(p, 1), dtype=F64, device=Xt.device)
+    call("mbpls_feature_sumsq_f64", ptr(Xt), ld, n, p, ptr(out), stream_ptr(Xt.device))
+    return out
+
+
+def segsum(v: torch.Tensor, off_dev: torch.Tensor, nseg: int) -> torch.Tensor:
+    out = torch.empty(max(nseg, 1), dtype=F64, device=v.device)
+    call("mbpls_segsum_f64", ptr(v), ptr(off_dev), nseg, ptr(out), stream_ptr(v.device))
+    return out[:nseg]
+
+
+def nan_census(Xt: torch.Tensor, n: int, block_off_dev: torch.Tensor, B: int):
+    """Returns (col_nan int32[p], row_flag uint8[B x ldf])."""
+    p, ld = Xt.shape
+    dev = Xt.device
+    col_nan = torch.zeros(max(p, 1), dtype=torch.int32, device=dev)
+    row_flag = torch.zeros((B, ld), dtype=torch.uint8, device=dev)
+    call("mbpls_nan_census_f64", ptr(Xt), ld, n, p, ptr(block_off_dev), B, ptr(col_nan), ptr(row_flag), ld,
+         stream_ptr(dev))
+    return col_nan[:p], row_flag
+
+
+# --------------------------------------------------------------------------------------------- #
+# split table for the sample-owning kernels (xw, skinny_gemm)
+# --------------------------------------------------------------------------------------------- #
+def make_splits(block_off: Sequence[int], n: int, sm_count: int, ctas_per_sm: int = 8, min_feats: int = 64):
+    """Cut every block's local feature range into pieces so that (row chunks x splits) fills the GPU."""
+    B = len(block_off) - 1
+    p = block_off[-1]
+    row_chunks = max(1, -(-n // 512))
+    target = max(1, (sm_count * ctas_per_sm) // row_chunks)
+    f0, f1, bso = [], [], [0]
+    for b in range(B):
+        a, e = block_off[b], block_off[b + 1]
+        pb = e - a
+        if pb > 0:
+            nb = max(1, min(int(round(target * pb / max(p, 1))) or 1, max(1, pb // min_feats)))
+            step = -(-pb // nb)
+            step = -(-step // 8) * 8
+            s = a
+            while s < e:
+                f0.append(s)
+                f1.append(min(e, s + step))
+                s += step
+        bso.append(len(f0))
+    return f0, f1, bso
+
+
+def allreduce_(t: torch.Tensor, group) -> None:
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, group=group)
+
+
+def norm_kind_of(ord_) -> int:
+    """Matrix-norm semantics of ``np.linalg.norm(n x 1 array, ord)`` (mbpls/mbpls.py:887, SURVEY a6')."""
+    if ord_ is None or ord_ in (2, -2, "fro", "nuc"):
+        return _cabi.NORM_L2
+    if ord_ in (1, -1):
+        return _cabi.NORM_L1
+    if ord_ == np.inf:
+        return _cabi.NORM_MAX
+    if ord_ == -np.inf:
+        return _cabi.NORM_MIN
+    raise ValueError("Invalid norm order for matrices.")
+
+
+# --------------------------------------------------------------------------------------------- #
+# NIPALS
+# --------------------------------------------------------------------------------------------- #
+@dataclass
+class NipalsResult:
+    Wt: torch.Tensor   # K x p_local   un-normalised block weights (W_non_normal_)
+    W: torch.Tensor    # K x p_local   block-normalised weights (W_)
+    P: torch.Tensor    # K x p_local   loadings
+    Ts: torch.Tensor   # K x ld
+    U: torch.Tensor    # K x ld
+    Tb: torch.Tensor   # B x K x ld
+    V: torch.Tensor    # K x q
+    A: torch.Tensor    # K x B  (squared superweights)
+    pssb: torch.Tensor  # K x B  local sum of p_j^2 per block
+    tt: List[float]
+    vv: List[float]
+    n_iter: List[int]
+    diff: List[float]
+
+
+def sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[int], n_components: int, *,
+               u0: torch.Tensor, nanmode: bool = False, row_flag: Optional[torch.Tensor] = None,
+               ycol_flag: Optional[torch.Tensor] = None, max_tol: float = 1e-14, norm_kind: int = 0,
+               max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
+               trips_per_sync: Optional[int] = None) -> NipalsResult:
+    """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
+
+    Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
+    """
+    dev = Xt.device
+    st = stream_ptr(dev)
+    p, ld = Xt.shape
+    B = len(block_off) - 1
+    q = Yt.shape[0]
+    K = int(n_components)
+    nan = 1 if nanmode else 0
+    boff = _i32(block_off, dev)
+    f0, f1, bso = make_splits(block_off, n, sm_count(dev))
+    nsplit = len(f0)
+    sf0, sf1, sbso = _i32(f0, dev), _i32(f1, dev), _i32(bso, dev)
+    nparts = call("mbpls_xtu_num_ctas", p) if p > 0 else 0
+
+    def buf(*shape, dtype=F64, zero=False):
+        shape = tuple(max(int(s), 1) for s in shape)
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+
+    w = buf(p)
+    norm_part = buf(max(nparts, 1) * B, zero=True)
+    Tnum = buf(nsplit, ld, zero=True)
+    Tden = buf(nsplit, ld, zero=True) if nan else None
+    nred = (2 if nan else 1) * B * ld + B
+    red = buf(nred, zero=True)
+    T = buf(B, ld, zero=True)
+    u, ts, ts_old = buf(ld, zero=True), buf(ld, zero=True), buf(ld, zero=True)
+    a, v = buf(B), buf(q)
+    scal = buf(_cabi.SCAL_COUNT, zero=True)
+    ctrl = buf(_cabi.CTRL_COUNT, dtype=torch.int32, zero=True)
+    pss = buf(p)
+    scal_h = torch.empty(_cabi.SCAL_COUNT, dtype=F64).pin_memory()
+    ctrl_h = torch.empty(_cabi.CTRL_COUNT, dtype=torch.int32).pin_memory()
+    u0u0 = buf(1)
+    call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
+
+    res = NipalsResult(Wt=buf(K, p), W=buf(K, p), P=buf(K, p), Ts=buf(K, ld, zero=True), U=buf(K, ld, zero=True),
+                       Tb=buf(B, K, ld, zero=True), V=buf(K, q), A=buf(K, B), pssb=buf(K, B, zero=True),
+                       tt=[], vv=[], n_iter=[], diff=[])
+
+    epi = _cabi.EpilogueArgs(n=n, B=B, q=q, nanmode=nan, norm_kind=norm_kind, ldt=ld, ldf=ld, max_tol=float(max_tol),
+                             red=red.data_ptr(), Yt=Yt.data_ptr(),
+                             row_flag=row_flag.data_ptr() if nan else None,
+                             ycol_flag=ycol_flag.data_ptr() if nan else None,
+                             T=T.data_ptr(), u=u.data_ptr(), ts=ts.data_ptr(), ts_old=ts_old.data_ptr(),
+                             a=a.data_ptr(), v=v.data_ptr(), scal=scal.data_ptr(), ctrl=ctrl.data_ptr(),
+                             diff_trace=None, diff_trace_len=0)
+    done_p = ptr(ctrl)  # ctrl[MBPLS_CTRL_DONE] is element 0
+
+    if trips_per_sync is None:
+        est_ms = 2.0 * p * ld * 8 / 5e12 * 1e3
+        trips_per_sync = 1 if est_ms > 1.0 else 4
+    w_ready = False  # True when w already holds the first weights of the coming component
+
+    for k in range(K):
+        call("mbpls_nipals_begin_component_f64", ptr(u0), n, ptr(u), ptr(scal), ptr(ctrl), st)
+        launched = 0
+        while True:
+            for _ in range(trips_per_sync):
+                if launched == 0 and w_ready:
+                    call("mbpls_block_sumsq_parts_f64", ptr(w), p, ptr(boff), B, ptr(norm_part), done_p, st)
+                else:
+                    call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(scal), ptr(boff), B, ptr(w),
+                         ptr(norm_part), nan, done_p, st)
+                call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit, ptr(Tnum), ptr(Tden),
+                     ld, nan, done_p, st)
+                call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
+                     nparts, ptr(red), nan, done_p, st)
+                allreduce_(red, group)
+                call("mbpls_nipals_epilogue_f64", C.byref(epi), st)
+                launched += 1
+            ctrl_h.copy_(ctrl, non_blocking=True)
+            scal_h.copy_(scal, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            if int(ctrl_h[_cabi.CTRL_DONE]) or int(ctrl_h[_cabi.CTRL_TRIPS]) >= max_iter:
+                break
+        res.n_iter.append(int(ctrl_h[_cabi.CTRL_TRIPS]))
+        res.diff.append(float(scal_h[_cabi.SCAL_DIFF]))
+        res.tt.append(float(scal_h[_cabi.SCAL_TT]))
+        res.vv.append(float(scal_h[_cabi.SCAL_VV]))
+        rec = _cabi.RecordArgs(n=n, p=p, B=B, q=q, nanmode=nan, ldt=ld, T_block_stride=K * ld,
+                               block_off=boff.data_ptr(), w=w.data_ptr(), red=red.data_ptr(), T=T.data_ptr(),
+                               ts=ts.data_ptr(), u=u.data_ptr(), v=v.data_ptr(), a=a.data_ptr(),
+                               Wt_k=res.Wt[k].data_ptr(), W_k=res.W[k].data_ptr(), Ts_k=res.Ts[k].data_ptr(),
+                               U_k=res.U[k].data_ptr(), T_k=res.Tb[0, k].data_ptr(), V_k=res.V[k].data_ptr(),
+                               A_k=res.A[k].data_ptr())
+        call("mbpls_nipals_record_component_f64", C.byref(rec), st)
+        last = (k == K - 1)
+        fuse = fuse_next_xtu and not last
+        call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts), ptr(u0) if fuse else None,
+             ptr(u0u0) if fuse else None, ptr(res.P[k]), ptr(w) if fuse else None, ptr(pss), nan, deflate_mode, st)
+        w_ready = fuse
+        if p > 0:
+            call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
+    return res
+
+
+# --------------------------------------------------------------------------------------------- #
+# small contractions over the feature axis
+# --------------------------------------------------------------------------------------------- #
+def gram(A: torch.Tensor, Bm: torch.Tensor, p: int, group=None) -> torch.Tensor:
+    """A (K1 x p) . Bm (K2 x p)^T -> K1 x K2, deterministic two-stage reduction (+ all-reduce)."""
+    dev = A.device
+    K1, K2 = A.shape[0], Bm.shape[0]
+    out = torch.zeros((K1, K2), dtype=F64, device=dev)
+    if p > 0:
+        nch = call("mbpls_gram_num_chunks", p)
+        part = torch.empty((nch, K1 * K2), dtype=F64, device=dev)
+        call("mbpls_gram_partial_f64", ptr(A), A.stride(0), K1, ptr(Bm), Bm.stride(0), K2, p, ptr(part), stream_ptr(dev))
+        call("mbpls_reduce_chunks_f64", ptr(part), nch, K1 * K2, ptr(out), stream_ptr(dev))
+    allreduce_(out, group)
+    return out
+
+
+def rows_sumsq(M: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    rows = M.shape[0]
+    out = torch.zeros(max(rows, 1), dtype=F64, device=M.device)
+    if n > 0:
+        call("mbpls_rows_sumsq_f64", ptr(M), M.stride(0), rows, n, ptr(out), stream_ptr(M.device))
+    allreduce_(out, group)
+    return out[:rows]
+
+
+def right_multiply(inp: torch.Tensor, p: int, rowscale: Optional[torch.Tensor], M: torch.Tensor) -> torch.Tensor:
+    """out[c][j] = sum_k inp[k][j] * rowscale[k] * M[k][c]  ->  C x p."""
+    K, Cc = M.shape
+    out = torch.empty((Cc, max(p, 1)), dtype=F64, device=inp.device)
+    M = M.contiguous()
+    call("mbpls_right_multiply_f64", ptr(inp), inp.stride(0), K, p, ptr(rowscale), ptr(M), Cc, ptr(out), out.stride(0),
+         stream_ptr(inp.device))
+    return out[:, :p]
+
+
+def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[int], group=None) -> torch.Tensor:
+    """out[c][i] = sum_j nan0(Xt[j][i]) * Bm[c][j]  ->  C x ld (feature-major result)."""
+    dev = Xt.device
+    p, ld = Xt.shape
+    Cc = Bm.shape[0]
+    out = torch.zeros((Cc, ld), dtype=F64, device=dev)
+    if p > 0 and n > 0:
+        f0, f1, _ = make_splits(block_off, n, sm_count(dev))
+        ns = len(f0)
+        part = torch.zeros((ns, Cc * ld), dtype=F64, device=dev)
+        call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(_i32(f0, dev)), ptr(_i32(f1, dev)),
+             ns, ptr(part), ld, stream_ptr(dev))
+        call("mbpls_reduce_chunks_f64", ptr(part), ns, Cc * ld, ptr(out), stream_ptr(dev))
+    allreduce_(out, group)
+    return out

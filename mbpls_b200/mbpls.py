@@ -1,0 +1,529 @@
+"""Drop-in for ``mbpls.mbpls.MBPLS`` (reference: mbpls/mbpls.py:22-1437) whose fit / predict /
+transform bodies run on a B200 through the hand-written sm_100a kernels of ``csrc/``.
+
+The surface is the reference's: same constructor signature and defaults (mbpls.py:243-253), same
+methods (fit :273, transform :1052, predict :1337, fit_transform :1412, fit_predict :1418, r2_score
+:1424, explained_variance_score :1431, inherited score/get_params/set_params), same fitted
+attributes with the same shapes and list-vs-array conventions (SURVEY.md section 8a contract table),
+same warnings and exception types.  Inputs may be numpy arrays / array-likes (as in the reference) or
+torch tensors, including CUDA tensors that are already column-major (feature-major), which are
+consumed without a layout change.
+
+Extras that are *not* in the reference (none of them constructor parameters, so ``sklearn.clone``
+and ``get_params`` behave identically): ``n_iter_`` (NIPALS trips per component), ``set_runtime``.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional
+
+import numpy as np
+import torch
+from sklearn import metrics
+from sklearn.base import BaseEstimator, MultiOutputMixin, RegressorMixin, TransformerMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.preprocessing import StandardScaler
+
+from . import _cabi
+from . import engine as E
+from .engine import F64, ShardMap, call, ptr, stream_ptr
+
+__all__ = ["MBPLS"]
+
+_SPARSITY_MSG = ("The sparsity of your data is likely to high for this algorithm. This can cause either convergence"
+                 "problems or crash the algorithm.")
+
+_RUNTIME_DEFAULTS = dict(
+    device=None,          # torch device (default: current CUDA device)
+    group=None,           # torch.distributed process group: shard the feature axis over its ranks
+    materialize=True,     # copy fitted attributes to numpy at the end of fit (False: on first access)
+    fuse_next_xtu=True,   # loadings+deflation pass also emits the next component's first weights
+    deflate_mode=0,       # 0 auto (smem-resident pipeline), 1 force global-memory fallback
+    standardize_mode=0,   # idem for the standardisation pass
+    trips_per_sync=None,  # NIPALS trips enqueued per convergence-flag readback (None: auto)
+    max_iter=1_000_000,   # safety cap on NIPALS trips; the reference loop is unbounded (mbpls.py:841)
+)
+
+
+def _is_block_list(X) -> bool:
+    return isinstance(X, list) and not isinstance(X[0], list)  # mbpls.py:301
+
+
+def _shape2(a):
+    if isinstance(a, torch.Tensor):
+        return tuple(a.shape)
+    return tuple(np.shape(a))
+
+
+def _as_2d_source(a, what: str):
+    """Array-like -> numpy float64 view / torch tensor with 2 dims (no copy when already float64)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = np.asarray(a)
+        if t.dtype != np.float64:
+            try:
+                t = t.astype(np.float64)
+            except (TypeError, ValueError) as exc:
+                raise ValueError(f"could not convert {what} to float64") from exc
+    if t.ndim != 2:
+        raise ValueError(f"Expected 2D array, got {t.ndim}D array instead ({what}).")
+    if t.shape[0] < 1 or t.shape[1] < 1:
+        raise ValueError(f"Found array with {t.shape[0]} sample(s) and {t.shape[1]} feature(s) while a minimum of 1 is required.")
+    return t
+
+
+class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
+    """(Multiblock) PLS regression on a B200; see the module docstring and the reference docstring
+    (mbpls/mbpls.py:23-241) for parameter and attribute semantics."""
+
+    def __init__(self, n_components=2, full_svd=False, method='NIPALS', standardize=True, max_tol=1e-14,
+                 nipals_convergence_norm=2, calc_all=True, sparse_data=False, copy=True):
+        self.n_components = n_components
+        self.full_svd = full_svd
+        self.method = method
+        self.standardize = standardize
+        self.max_tol = max_tol
+        self.nipals_convergence_norm = nipals_convergence_norm
+        self.calc_all = calc_all
+        self.sparse_data = sparse_data
+        self.copy = copy
+
+    # ------------------------------------------------------------------ runtime plumbing
+    def set_runtime(self, **kw) -> "MBPLS":
+        rt = self._runtime()
+        for k, v in kw.items():
+            if k not in _RUNTIME_DEFAULTS:
+                raise TypeError(f"unknown runtime option {k!r}")
+            rt[k] = v
+        return self
+
+    def _runtime(self) -> dict:
+        rt = self.__dict__.get("_rt")
+        if rt is None:
+            rt = dict(_RUNTIME_DEFAULTS)
+            self.__dict__["_rt"] = rt
+        return rt
+
+    def __getstate__(self):
+        self._materialize_all()
+        state = dict(self.__dict__)
+        for k in ("_rt", "_dev", "_lazy", "_dev_scalers"):
+            state.pop(k, None)
+        return state
+
+    def __getattr__(self, name):
+        # only called when normal lookup fails: lazily materialised fitted attributes
+        lazy = self.__dict__.get("_lazy")
+        if lazy and name in lazy:
+            self._materialize_all()
+            return self.__dict__[name]
+        raise AttributeError(f"{type(self).__name__!r} object has no attribute {name!r}")
+
+    def _materialize_all(self):
+        lazy = self.__dict__.get("_lazy")
+        if lazy:
+            self.__dict__["_lazy"] = None
+            for name, fn in lazy.items():
+                self.__dict__[name] = fn()
+
+    def _group_info(self):
+        group = self._runtime()["group"]
+        if group is None:
+            return None, 0, 1
+        import torch.distributed as dist
+        return group, dist.get_rank(group), dist.get_world_size(group)
+
+    def _gather_features(self, t_local: torch.Tensor, shard: ShardMap) -> np.ndarray:
+        """K x p_local device tensor -> K x p_global numpy array (same on every rank)."""
+        group, rank, world = self._group_info()
+        if world == 1:
+            return t_local[:, :shard.p_local].cpu().numpy()
+        import torch.distributed as dist
+        per = -(-shard.p_global // world)
+        K = t_local.shape[0]
+        pad = torch.zeros((K, per), dtype=t_local.dtype, device=t_local.device)
+        pad[:, :shard.p_local] = t_local[:, :shard.p_local]
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        full = torch.cat(parts, dim=1)[:, :shard.p_global]
+        return full.cpu().numpy()
+
+    # ------------------------------------------------------------------ NaN census (mbpls.py:255-271)
+    def check_sparsity_level(self, data):
+        """Reference-compatible census of one host array; the fit path uses the device census kernel."""
+        data = np.asarray(data, dtype=np.float64)
+        nanmask = np.isnan(data)
+        return self._census_from_flags(nanmask.any(axis=1), nanmask.any(axis=0))
+
+    @staticmethod
+    def _census_from_flags(row_has: np.ndarray, col_has: np.ndarray):
+        if col_has.sum() / col_has.size > 0.5:
+            warnings.warn(_SPARSITY_MSG)
+        if row_has.sum() / row_has.size > 0.5:
+            warnings.warn(_SPARSITY_MSG)
+        return (np.where(row_has)[0], np.where(col_has)[0], np.where(~row_has)[0], np.where(~col_has)[0])
+
+    # ------------------------------------------------------------------ ingest shared by fit / predict / transform
+    def _ingest(self, X, n_expected: Optional[int], shard: Optional[ShardMap], device, what="X"):
+        blocks = X if _is_block_list(X) else [X]
+        blocks = [_as_2d_source(b, what) for b in blocks]
+        n = blocks[0].shape[0]
+        want = n if n_expected is None else int(n_expected)
+        for b in blocks:
+            if int(b.shape[0]) != want:  # check_consistent_length, mbpls.py:309,322
+                raise ValueError("Found input variables with inconsistent numbers of samples: %r"
+                                 % [int(b.shape[0]), want])
+        sizes = [int(b.shape[1]) for b in blocks]
+        if shard is None:
+            _, rank, world = self._group_info()
+            shard = ShardMap.build(sizes, rank, world)
+        elif list(shard.sizes) != sizes:
+            raise ValueError("X has %r features per block, but MBPLS was fitted with %r" % (sizes, list(shard.sizes)))
+        Xt = E.ingest_blocks(blocks, n, shard, device)
+        return Xt, n, shard
+
+    # ------------------------------------------------------------------ fit (mbpls.py:273-1050)
+    def fit(self, X, Y):
+        if self.sparse_data is True and self.method != 'NIPALS':  # mbpls.py:286-290
+            warnings.warn("The parameter sparse data was set to 'True', but the chosen method is not 'NIPALS'."
+                          "The method will be set to 'NIPALS'")
+            self.method = 'NIPALS'
+        if self.method not in ('NIPALS', 'UNIPALS', 'KERNEL', 'SIMPLS'):
+            raise NameError('Method you called is unknown')  # mbpls.py:1050
+        rt = self._runtime()
+        device = E.require_cuda(rt["device"])
+        group, rank, world = self._group_info()
+        sparse = bool(self.sparse_data)
+        self.__dict__["_lazy"] = None
+        self.__dict__["_dev"] = None
+        self.__dict__["_dev_scalers"] = None
+
+        with torch.cuda.device(device):
+            # ---- Y (mbpls.py:293-298)
+            Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
+            if Ysrc.ndim == 1:
+                Ysrc = Ysrc.reshape(-1, 1)
+            Ysrc = _as_2d_source(Ysrc, "Y")
+            n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
+            # ---- X blocks (mbpls.py:299-347)
+            Xt, n_x, shard = self._ingest(X, n, None, device)
+            B = len(shard.sizes)
+            ld = Xt.shape[1]
+            Yt = E.alloc_feature_major(q, n, device)
+            E.ingest_feature_major(Ysrc, n, 0, q, Yt, device)
+            boff_dev = E._i32(shard.block_off, device)
+
+            row_flag = ycol_flag = None
+            if sparse:
+                row_flag, ycol_flag = self._fit_census(Xt, Yt, n, q, shard, boff_dev, group)
+            elif not self.standardize:
+                self._require_finite(Xt, Yt)
+
+            # ---- standardisation (mbpls.py:299-326)
+            zss = None
+            if self.standardize:
+                xs = E.standardize_fit(Xt, n, rt["standardize_mode"])
+                ys = E.standardize_fit(Yt, n, rt["standardize_mode"])
+                if not sparse:
+                    ok = bool((xs.seen[:shard.p_local] == n).all()) and bool(torch.isfinite(xs.zss[:shard.p_local]).all()) \
+                        and bool((ys.seen[:q] == n).all()) and bool(torch.isfinite(ys.zss[:q]).all())
+                    self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
+                self._store_scalers(xs, ys, shard, q)
+                zss = xs.zss
+                self.__dict__["_dev_scalers"] = (xs.mean[:shard.p_local], xs.scale[:shard.p_local], ys.mean[:q], ys.scale[:q])
+            self.num_blocks_ = B
+
+            if self.method == 'NIPALS':
+                self._fit_nipals(Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device)
+            else:
+                from . import crossmethods
+                crossmethods.fit(self, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
+        if rt["materialize"]:
+            self._materialize_all()
+        return self
+
+    # ---- helpers of fit
+    def _raise_if_any_rank(self, bad: bool, msg: str, group):
+        if group is not None:
+            import torch.distributed as dist
+            flag = torch.tensor([1 if bad else 0], device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(flag, group=group)
+            bad = bool(flag.item())
+        if bad:
+            raise ValueError(msg)
+
+    def _require_finite(self, Xt, Yt):
+        ok = bool(torch.isfinite(Xt).all()) and bool(torch.isfinite(Yt).all())
+        self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", self._runtime()["group"])
+
+    def _fit_census(self, Xt, Yt, n, q, shard, boff_dev, group):
+        """sparse_X_info_ / sparse_Y_info_ (mbpls.py:294-296, 304-313) from the device census."""
+        B = len(shard.sizes)
+        if bool(torch.isinf(Xt).any()) or bool(torch.isinf(Yt).any()):
+            raise ValueError("Input contains infinity or a value too large for dtype('float64').")
+        col_nan, row_flag = E.nan_census(Xt, n, boff_dev, B)
+        if group is not None:
+            import torch.distributed as dist
+            rf = row_flag.to(torch.int32)
+            dist.all_reduce(rf, op=dist.ReduceOp.MAX, group=group)
+            row_flag.copy_(rf.to(torch.uint8))
+        one = E._i32([0, q], Yt.device)
+        ycol_nan, yrow_flag = E.nan_census(Yt, n, one, 1)
+        col_full = self._gather_features(col_nan.view(1, -1).to(F64), shard)[0] > 0
+        rows = row_flag[:, :n].cpu().numpy().astype(bool)
+        self.sparse_Y_info_ = {'Y': self._census_from_flags(yrow_flag[0, :n].cpu().numpy().astype(bool),
+                                                            (ycol_nan[:q] > 0).cpu().numpy())}
+        self.sparse_X_info_ = {}
+        g0 = 0
+        for b, pb in enumerate(shard.sizes):
+            self.sparse_X_info_[b] = self._census_from_flags(rows[b], col_full[g0:g0 + pb])
+            g0 += pb
+        return row_flag, (ycol_nan[:q] > 0).to(torch.uint8).contiguous()
+
+    def _store_scalers(self, xs, ys, shard, q):
+        mean = self._gather_features(xs.mean.view(1, -1), shard)[0]
+        var = self._gather_features(xs.var.view(1, -1), shard)[0]
+        scale = self._gather_features(xs.scale.view(1, -1), shard)[0]
+        seen = self._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
+        self.x_scalers_ = []
+        g0 = 0
+        for pb in shard.sizes:
+            self.x_scalers_.append(_make_scaler(mean[g0:g0 + pb], var[g0:g0 + pb], scale[g0:g0 + pb], seen[g0:g0 + pb]))
+            g0 += pb
+        self.y_scaler_ = _make_scaler(ys.mean[:q].cpu().numpy(), ys.var[:q].cpu().numpy(), ys.scale[:q].cpu().numpy(),
+                                      ys.seen[:q].cpu().numpy())
+
+    def _block_sums(self, per_feature: torch.Tensor, boff_dev, B, group) -> np.ndarray:
+        s = E.segsum(per_feature, boff_dev, B).clone()
+        E.allreduce_(s, group)
+        return s.cpu().numpy()
+
+    # ---- NIPALS (mbpls.py:809-993)
+    def _fit_nipals(self, Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device):
+        rt = self._runtime()
+        B, K = len(shard.sizes), int(self.n_components)
+        sparse = bool(self.sparse_data)
+        p_loc = shard.p_local
+        varxb = vary = None
+        if self.calc_all:  # mbpls.py:822-830, :938-945
+            if zss is None:
+                zss = E.feature_sumsq(Xt, n)
+            varxb = self._block_sums(zss, boff_dev, B, group)
+            vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
+        # initial Y-score vector (mbpls.py:832-838)
+        if sparse:
+            dense_cols = self.sparse_Y_info_['Y'][3]
+            if len(dense_cols) == 0:
+                u0 = torch.zeros(Xt.shape[1], dtype=F64, device=device)
+                u0[:n] = torch.from_numpy(np.random.rand(n)).to(device)
+                if group is not None:
+                    import torch.distributed as dist
+                    dist.broadcast(u0, src=dist.get_global_rank(group, 0), group=group)
+            else:
+                u0 = Yt[int(dense_cols[0])]
+        else:
+            u0 = Yt[0]
+        res = E.nipals_fit(Xt, Yt, n, shard.block_off, K, u0=u0, nanmode=sparse, row_flag=row_flag, ycol_flag=ycol_flag,
+                           max_tol=self.max_tol, norm_kind=E.norm_kind_of(self.nipals_convergence_norm),
+                           max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
+                           deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"])
+        self.n_iter_ = list(res.n_iter)
+        if any(it >= rt["max_iter"] for it in res.n_iter):
+            warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
+        # ---- finalise (mbpls.py:985-989): W = concat(W_non_normal_)/colnorm, R = W pinv(P'W), beta = R V'
+        Wt, P = res.Wt[:, :p_loc], res.P[:, :p_loc]
+        colnorm = torch.sqrt(E.rows_sumsq(Wt, p_loc, group))
+        PtW = E.gram(P, Wt, p_loc, group) / colnorm.view(1, -1)
+        M = torch.from_numpy(np.linalg.pinv(PtW.cpu().numpy())).to(device)  # K x K control step on the host
+        R = E.right_multiply(Wt, p_loc, 1.0 / colnorm, M)
+        beta = E.right_multiply(R, p_loc, None, res.V[:, :q].contiguous())
+        self.__dict__["_dev"] = dict(shard=shard, R=R, beta=beta, W=res.W[:, :p_loc], P=P, V=res.V[:, :q])
+
+        # ---- small host-side bookkeeping
+        A = res.A[:, :B].cpu().numpy().T.copy()  # B x K
+        self.A_ = A
+        if self.calc_all:
+            pssb = res.pssb[:, :B].clone()
+            E.allreduce_(pssb, group)
+            pssb = pssb.cpu().numpy()  # K x B
+            tt, vv = np.asarray(res.tt), np.asarray(res.vv)
+            self.explained_var_x_ = [float(tt[k] * pssb[k].sum() / varxb.sum()) for k in range(K)]
+            self.explained_var_y_ = [float(tt[k] * vv[k] / vary) for k in range(K)]
+            self.explained_var_xblocks_ = (tt[None, :] * pssb.T) / varxb[:, None]
+            self.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
+        else:
+            self.explained_var_x_, self.explained_var_y_ = [], []
+            self.explained_var_xblocks_ = np.empty((B, 0))
+            self.A_corrected_ = np.empty((B, 0))
+        self.W_concat_ = np.empty((shard.p_global, 0))
+
+        bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
+
+        def split_T(full):  # K x p_global -> list of p_b x K
+            return [np.ascontiguousarray(full[:, bounds[b]:bounds[b + 1]].T) for b in range(B)]
+
+        lazy = {
+            "Ts_": lambda: np.ascontiguousarray(res.Ts[:, :n].cpu().numpy().T),
+            "U_": lambda: np.ascontiguousarray(res.U[:, :n].cpu().numpy().T),
+            "V_": lambda: np.ascontiguousarray(res.V[:, :q].cpu().numpy().T),
+            "T_": lambda: [np.ascontiguousarray(res.Tb[b, :, :n].cpu().numpy().T) for b in range(B)],
+            "W_": lambda: split_T(self._gather_features(res.W, shard)),
+            "W_non_normal_": lambda: split_T(self._gather_features(res.Wt, shard)),
+            "P_": lambda: split_T(self._gather_features(res.P, shard)),
+            "R_": lambda: np.ascontiguousarray(self._gather_features(R, shard).T),
+            "beta_": lambda: np.ascontiguousarray(self._gather_features(beta, shard).T),
+        }
+        self.__dict__["_lazy"] = lazy
+
+    # ------------------------------------------------------------------ new-data paths
+    def _check_is_fitted(self):
+        lazy = self.__dict__.get("_lazy")
+        if "beta_" not in self.__dict__ and not (lazy and "beta_" in lazy):
+            raise NotFittedError("This MBPLS instance is not fitted yet. Call 'fit' with appropriate arguments "
+                                 "before using this estimator.")
+
+    def _device_model(self, device):
+        """Fitted matrices on the device (kept from fit, or rebuilt from the numpy attributes)."""
+        dev = self.__dict__.get("_dev")
+        if dev is not None and dev["R"].device == device:
+            return dev
+        _, rank, world = self._group_info()
+        P_ = self.P_
+        sizes = [int(pb.shape[0]) for pb in P_]
+        shard = ShardMap.build(sizes, rank, world)
+
+        def up(full_pk):  # p_global x K numpy -> K x p_local device
+            return torch.from_numpy(np.ascontiguousarray(full_pk[shard.lo:shard.hi].T)).to(device)
+
+        dev = dict(shard=shard, R=up(self.R_), beta=up(self.beta_), P=up(np.concatenate(P_, axis=0)),
+                   V=torch.from_numpy(np.ascontiguousarray(self.V_.T)).to(device))
+        if isinstance(self.W_, list):
+            dev["W"] = up(np.concatenate(self.W_, axis=0))
+        self.__dict__["_dev"] = dev
+        return dev
+
+    def _device_scalers(self, shard, device):
+        sc = self.__dict__.get("_dev_scalers")
+        if sc is not None and sc[0].device == device:
+            return sc
+        mean = np.concatenate([np.atleast_1d(s.mean_) for s in self.x_scalers_])[shard.lo:shard.hi]
+        scale = np.concatenate([np.atleast_1d(s.scale_) for s in self.x_scalers_])[shard.lo:shard.hi]
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+        sc = (t(mean), t(scale), t(np.atleast_1d(self.y_scaler_.mean_)), t(np.atleast_1d(self.y_scaler_.scale_)))
+        self.__dict__["_dev_scalers"] = sc
+        return sc
+
+    def _prepare_new_X(self, X, device):
+        dev = self._device_model(device)
+        shard = dev["shard"]
+        Xt, m, _ = self._ingest(X, None, shard, device)
+        if not self.sparse_data:
+            self._require_finite(Xt, Xt[:0])
+        elif bool(torch.isinf(Xt).any()):
+            raise ValueError("Input contains infinity or a value too large for dtype('float64').")
+        if self.standardize:
+            mean, scale, _, _ = self._device_scalers(shard, device)
+            E.standardize_apply(Xt, m, mean, scale)
+        return dev, shard, Xt, m
+
+    def predict(self, X, copy=True):
+        """y_hat = inverse_scale(scale(X) . beta_)  (mbpls.py:1337-1410); NaN entries count as zero after
+        scaling (:1379-1383)."""
+        self._check_is_fitted()
+        device = E.require_cuda(self._runtime()["device"])
+        group, _, _ = self._group_info()
+        with torch.cuda.device(device):
+            dev, shard, Xt, m = self._prepare_new_X(X, device)
+            q = dev["beta"].shape[0]
+            Yh = E.skinny_gemm(Xt, m, dev["beta"], shard.block_off, group)
+            if self.standardize:
+                _, _, ymean, yscale = self._device_scalers(shard, device)
+                call("mbpls_scaler_inverse_f64", ptr(Yh), Yh.shape[1], m, q, ptr(ymean), ptr(yscale), stream_ptr(device))
+            return np.ascontiguousarray(Yh[:, :m].cpu().numpy().T)
+
+    def transform(self, X, Y=None, return_block_scores=False, copy=True):
+        """Superscores (and block scores / Y scores) of new data (mbpls.py:1052-1335)."""
+        self._check_is_fitted()
+        device = E.require_cuda(self._runtime()["device"])
+        group, _, _ = self._group_info()
+        with torch.cuda.device(device):
+            dev, shard, Xt, m = self._prepare_new_X(X, device)
+            K = dev["R"].shape[0]
+            Ts_dev = E.skinny_gemm(Xt, m, dev["R"], shard.block_off, group)  # K x ld   (:1110-1117)
+            Ts = np.ascontiguousarray(Ts_dev[:, :m].cpu().numpy().T)
+            out = [Ts]
+            if self.method != 'SIMPLS' and return_block_scores:  # :1126-1155
+                B = len(shard.sizes)
+                T = []
+                for b in range(B):
+                    o0, o1 = shard.block_off[b], shard.block_off[b + 1]
+                    Xb = Xt[o0:o1]
+                    cols = []
+                    for k in range(K):
+                        if k > 0 and o1 > o0:
+                            call("mbpls_rank1_update_f64", ptr(Xb), Xb.shape[1], m, o1 - o0, ptr(Ts_dev[k - 1]),
+                                 ptr(dev["P"][k - 1, o0:o1]), stream_ptr(device))
+                        tk = E.skinny_gemm(Xb, m, dev["W"][k:k + 1, o0:o1], [0, o1 - o0], group)
+                        cols.append(tk[0, :m])
+                    T.append(np.ascontiguousarray(torch.stack(cols, dim=1).cpu().numpy()))
+                out.append(T)
+            if Y is not None:  # :1119-1125, :1156-1166
+                Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
+                if Ysrc.ndim == 1:
+                    Ysrc = Ysrc.reshape(-1, 1)
+                Ysrc = _as_2d_source(Ysrc, "Y")
+                q = int(Ysrc.shape[1])
+                Yt = E.alloc_feature_major(q, m, device)
+                E.ingest_feature_major(Ysrc, m, 0, q, Yt, device)
+                if not self.sparse_data:
+                    self._require_finite(Yt, Yt[:0])
+                if self.standardize:
+                    _, _, ymean, yscale = self._device_scalers(shard, device)
+                    E.standardize_apply(Yt, m, ymean, yscale)
+                Ur = E.skinny_gemm(Yt, m, dev["V"], [0, q], None)  # K x ld
+                nrm = torch.sqrt(E.rows_sumsq(Ur, m))
+                call("mbpls_rows_scale_f64", ptr(Ur), Ur.shape[1], K, m, ptr(nrm), 1, stream_ptr(device))
+                out.append(np.ascontiguousarray(Ur[:, :m].cpu().numpy().T))
+        return out[0] if len(out) == 1 else tuple(out)
+
+    # ------------------------------------------------------------------ convenience (mbpls.py:1412-1437)
+    def fit_transform(self, X, y=None, **fit_params):
+        return self.fit(X, y, **fit_params).transform(X, y)
+
+    def fit_predict(self, X, Y, **fit_params):
+        return self.fit(X, Y, **fit_params).predict(X)
+
+    def r2_score(self, X, Y):
+        if self.standardize:
+            return metrics.r2_score(Y, self.predict(X))
+        return metrics.r2_score(Y, self.predict(X), sample_weight=None, multioutput='variance_weighted')
+
+    def explained_variance_score(self, X, Y):
+        if self.standardize:
+            return metrics.explained_variance_score(Y, self.predict(X))
+        return metrics.explained_variance_score(Y, self.predict(X), sample_weight=None,
+                                                multioutput='variance_weighted')
+
+
+def _make_scaler(mean, var, scale, seen) -> StandardScaler:
+    """A scikit-learn StandardScaler carrying statistics computed on the device, so that
+    ``x_scalers_[b].transform / inverse_transform`` work exactly as with the reference (notebooks use them)."""
+    sc = StandardScaler(with_mean=True, with_std=True)
+    sc.mean_ = np.array(mean, dtype=np.float64)
+    sc.var_ = np.array(var, dtype=np.float64)
+    sc.scale_ = np.array(scale, dtype=np.float64)
+    seen = np.array(seen, dtype=np.int64)
+    sc.n_samples_seen_ = seen[0] if seen.size and np.ptp(seen) == 0 else seen
+    sc.n_features_in_ = int(sc.mean_.shape[0])
+    return sc
+
+
+def _bip_corrected(a, sizes):
+    """Block importances corrected for block size (mbpls.py:950-963): O(B) host bookkeeping."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    if a.size == 1:
+        return np.array([1.0])
+    sizes = np.asarray(sizes, dtype=np.float64)
+    corrected = a * (1.0 - sizes / sizes.sum())
+    return corrected / corrected.sum()

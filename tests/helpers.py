@@ -1,0 +1,85 @@
+"""Shared test helpers: golden-fixture loading and sign-aligned comparison."""
+from __future__ import annotations
+
+import ast
+import glob
+import os
+import warnings
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+UNSIGNED_SUFFIXES = ("beta_", "A_", "A_corrected_", "explained_var_xblocks_", "explained_var_x_", "explained_var_y_")
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.shape != b.shape:
+        return np.inf
+    if a.size == 0:
+        return 0.0
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+def col_err(o, r):
+    """Per-component relative error after sign alignment (columns are components)."""
+    return max(min(rel_err(o[:, k], r[:, k]), rel_err(-o[:, k], r[:, k])) for k in range(r.shape[1]))
+
+
+def live_cases():
+    return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "live_*.npz")))
+
+
+def load_live(name):
+    z = np.load(os.path.join(GOLDEN, f"live_{name}.npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    kwargs = eval(str(d["meta/kwargs"]), {"inf": np.inf, "np": np})  # repr of a plain dict written by make_golden
+    single = bool(d["meta/single_array"])
+    nb = len([k for k in d if k.startswith("in/X/")])
+    X = [d[f"in/X/{b}"] for b in range(nb)]
+    Xt = [d[f"in/Xt/{b}"] for b in range(nb)]
+    if single:
+        X, Xt = X[0], Xt[0]
+    ref = {k: v for k, v in d.items() if not k.startswith(("in/", "meta/"))}
+    return X, d["in/Y"], Xt, d["in/Yt"], kwargs, ref
+
+
+def snapshot_model(m, Xt, Yt):
+    """Same keys as oracle.make_golden.run_model, for any estimator with the reference's surface."""
+    from oracle.make_golden import snapshot
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        snap = snapshot(m)
+        if hasattr(m, "n_iter_"):
+            snap["n_iter_"] = np.asarray(m.n_iter_, dtype=np.int64)
+        if m.method != "SIMPLS":
+            Ts, T, U = m.transform(Xt, Yt, return_block_scores=True)
+            for b, arr in enumerate(T):
+                snap[f"tr_T/{b}"] = np.asarray(arr)
+        else:
+            Ts, U = m.transform(Xt, Yt)
+        snap["tr_Ts"], snap["tr_U"] = np.asarray(Ts), np.asarray(U)
+        snap["predict"] = np.asarray(m.predict(Xt))
+    return snap
+
+
+def compare(ours, ref, tol, what, skip=()):
+    worst, worst_key = 0.0, None
+    for key, r in ref.items():
+        if key in skip or key == "n_iter_":
+            continue
+        assert key in ours, f"{what}: missing {key}"
+        o = np.asarray(ours[key])
+        assert o.shape == r.shape, f"{what}: shape of {key}: {o.shape} vs {r.shape}"
+        if r.dtype.kind in "iub":
+            assert np.array_equal(o, r), f"{what}: integer mismatch in {key}"
+            continue
+        signed = r.ndim == 2 and r.shape[1] > 0 and not key.endswith(UNSIGNED_SUFFIXES) and "predict" not in key \
+            and not key.startswith(("xs_", "ys_"))
+        e = col_err(o, r) if signed else rel_err(o, r)
+        if e > worst:
+            worst, worst_key = e, key
+        assert e <= tol, f"{what}: {key} rel err {e:.3e} > {tol:g}"
+    return worst, worst_key
