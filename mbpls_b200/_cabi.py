@@ -86,6 +86,7 @@ class MbplsCudaError(RuntimeError):
 
 
 _lib = None
+launch_count = 0  # kernel-launching entry-point calls since import (bench.py reports the delta as gpu_launches)
 
 
 def load():
@@ -110,10 +111,12 @@ def load():
 
 def call(name: str, *args) -> int:
     """Invoke an entry point; status-returning functions raise on failure."""
+    global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
     if name in _PLAIN:
         return rc
+    launch_count += 1
     if rc != 0:
         if rc >= 1000:
             raise MbplsCudaError(f"{name}: CUDA error {rc - 1000}")

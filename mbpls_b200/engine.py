@@ -100,56 +100,68 @@ def _i32(vals, device):
 _STAGE_BYTES = 64 << 20
 
 
-def _upload_rows(dst_t: torch.Tensor, ld: int, src, r0: int, device, stage):
-    """src: 2-D (rows x cols) torch CPU tensor view (row-major, arbitrary row stride)."""
-    rows, cols = src.shape
-    if rows == 0 or cols == 0:
-        return
-    dev_chunk = src.to(device, non_blocking=False) if stage is None else stage(src)
-    if dev_chunk.stride(1) != 1:
-        dev_chunk = dev_chunk.contiguous()
-    call("mbpls_transpose_in_f64", ptr(dev_chunk), dev_chunk.stride(0), rows, cols, ptr(dst_t), ld, r0,
-         stream_ptr(device))
-
-
 def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, device) -> None:
-    """Copy columns [c0, c1) of one n x p_b block into ``dst`` ((c1-c0) x ld, feature-major)."""
+    """Copy columns [c0, c1) of one n x p_b block into ``dst`` ((c1-c0) x ld, feature-major).
+
+    Row-major sources (what ``check_array`` yields in the reference, mbpls.py:310) are streamed in row
+    chunks through one reusable device staging buffer and transposed by ``mbpls_transpose_in_f64``;
+    copies and kernels are stream-ordered, so pinned host sources run at PCIe rate without host syncs.
+    Column-major sources (numpy Fortran order, or ``t().contiguous().t()`` torch views) are already
+    feature-major and are copied straight in.
+    """
     ld = dst.shape[1]
     cols = c1 - c0
     if cols <= 0:
         return
     if isinstance(block, torch.Tensor):
-        t = block
-        if t.dtype != F64:
-            t = t.to(F64)
-        view = t[:, c0:c1]
-        if t.is_cuda:
-            if view.stride(0) == 1 and view.shape[0] > 0:  # column-major (= feature-major) device tensor
-                dst[:, :n].copy_(view.t())
-            else:
-                if view.stride(1) != 1:
-                    view = view.contiguous()
-                call("mbpls_transpose_in_f64", ptr(view), view.stride(0), n, cols, ptr(dst), ld, 0, stream_ptr(device))
-                torch.cuda.current_stream(device).synchronize()  # `view` may be a temporary
-            return
-        src = view
+        t = block if block.dtype == F64 else block.to(F64)
     else:
         arr = np.asarray(block)
         if arr.dtype != np.float64:
             arr = arr.astype(np.float64)
-        view_np = arr[:, c0:c1]
-        if view_np.strides[0] == 8 and n > 1:  # Fortran order: already feature-major on the host
-            dst[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(view_np.T)))
-            return
-        if view_np.strides[1] != 8:
-            view_np = np.ascontiguousarray(view_np)
-        src = torch.from_numpy(view_np)
-    # row-major host data: chunk over rows, transpose on the device
-    rows_per = max(1, _STAGE_BYTES // max(8 * cols, 1))
+        if not arr.flags.writeable:
+            arr = arr.copy()
+        t = torch.from_numpy(arr)
+    view = t[:, c0:c1]
+    if view.stride(0) == 1 and n > 1:  # column-major == feature-major
+        dst[:, :n].copy_(view.t(), non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return
+    if view.stride(1) != 1:
+        view = view.contiguous()
+    if view.is_cuda:
+        call("mbpls_transpose_in_f64", ptr(view), view.stride(0), n, cols, ptr(dst), ld, 0, stream_ptr(device))
+        torch.cuda.current_stream(device).synchronize()  # `view` may be a temporary
+        return
+    rows_per = max(1, min(n, _STAGE_BYTES // max(8 * cols, 1)))
+    stage = torch.empty((rows_per, cols), dtype=F64, device=device)
     for r0 in range(0, n, rows_per):
         r1 = min(n, r0 + rows_per)
-        _upload_rows(dst, ld, src[r0:r1], r0, device, None)
+        stage[:r1 - r0].copy_(view[r0:r1], non_blocking=True)
+        call("mbpls_transpose_in_f64", ptr(stage), cols, r1 - r0, cols, ptr(dst), ld, r0, stream_ptr(device))
     torch.cuda.current_stream(device).synchronize()
+
+
+def try_adopt_feature_major(blocks, n: int):
+    """Zero-copy path: the blocks are consecutive column-major CUDA views into one 128-byte aligned
+    buffer with a common leading dimension -> return that buffer as the p x ld feature-major matrix."""
+    if not blocks or not all(isinstance(b, torch.Tensor) and b.is_cuda and b.dtype == F64 and b.dim() == 2 for b in blocks):
+        return None
+    ld = blocks[0].stride(1)
+    if ld % 16 != 0 or ld < n or blocks[0].data_ptr() % 128 != 0:
+        return None
+    nxt = blocks[0].data_ptr()
+    base_storage = blocks[0].untyped_storage().data_ptr()
+    for b in blocks:
+        if b.shape[0] != n or b.shape[1] < 1 or b.stride(0) != 1 or b.stride(1) != ld or b.data_ptr() != nxt \
+                or b.untyped_storage().data_ptr() != base_storage:
+            return None
+        nxt += b.shape[1] * ld * 8
+    p = sum(int(b.shape[1]) for b in blocks)
+    Xt = blocks[0].as_strided((p, ld), (ld, 1))
+    if ld > n:
+        Xt[:, n:].zero_()
+    return Xt
 
 
 def alloc_feature_major(p: int, n: int, device) -> torch.Tensor:
@@ -160,13 +172,23 @@ def alloc_feature_major(p: int, n: int, device) -> torch.Tensor:
     return t
 
 
-def ingest_blocks(blocks, n: int, shard: ShardMap, device) -> torch.Tensor:
+def ingest_blocks(blocks, n: int, shard: ShardMap, device, presharded: bool = False, adopt: bool = False) -> torch.Tensor:
+    """blocks: the global blocks (every rank slices its own column range) or, when ``presharded``, this
+    rank's local column ranges of them.  ``adopt`` allows the zero-copy path (caller passed copy=False)."""
+    if adopt and (presharded or shard.world == 1):
+        nonempty = [b for b in blocks if b is not None and b.shape[1] > 0]
+        Xt = try_adopt_feature_major(nonempty, n)
+        if Xt is not None and Xt.shape[0] == shard.p_local:
+            return Xt
     Xt = alloc_feature_major(shard.p_local, n, device)
     for b, blk in enumerate(blocks):
         c0, c1 = shard.local_ranges[b]
         if c1 > c0:
             o0, o1 = shard.block_off[b], shard.block_off[b + 1]
-            ingest_feature_major(blk, n, c0, c1, Xt[o0:o1], device)
+            if presharded:
+                ingest_feature_major(blk, n, 0, c1 - c0, Xt[o0:o1], device)
+            else:
+                ingest_feature_major(blk, n, c0, c1, Xt[o0:o1], device)
     return Xt
 
 
@@ -295,7 +317,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                u0: torch.Tensor, nanmode: bool = False, row_flag: Optional[torch.Tensor] = None,
                ycol_flag: Optional[torch.Tensor] = None, max_tol: float = 1e-14, norm_kind: int = 0,
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
-               trips_per_sync: Optional[int] = None) -> NipalsResult:
+               trips_per_sync: Optional[int] = None, profile: Optional[dict] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -351,6 +373,18 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         est_ms = 2.0 * p * ld * 8 / 5e12 * 1e3
         trips_per_sync = 1 if est_ms > 1.0 else 4
     w_ready = False  # True when w already holds the first weights of the coming component
+    cur = torch.cuda.current_stream(dev)
+
+    def timed(key, fn):
+        """Optionally bracket one launch with CUDA events on the launching stream (bench.py roofline)."""
+        if profile is None:
+            fn()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        fn()
+        e1.record(cur)
+        profile.setdefault(key, []).append((e0, e1))
 
     for k in range(K):
         call("mbpls_nipals_begin_component_f64", ptr(u0), n, ptr(u), ptr(scal), ptr(ctrl), st)
@@ -360,10 +394,10 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 if launched == 0 and w_ready:
                     call("mbpls_block_sumsq_parts_f64", ptr(w), p, ptr(boff), B, ptr(norm_part), done_p, st)
                 else:
-                    call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(scal), ptr(boff), B, ptr(w),
-                         ptr(norm_part), nan, done_p, st)
-                call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit, ptr(Tnum), ptr(Tden),
-                     ld, nan, done_p, st)
+                    timed("xtu", lambda: call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(scal), ptr(boff), B,
+                                              ptr(w), ptr(norm_part), nan, done_p, st))
+                timed("xw", lambda: call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit,
+                                         ptr(Tnum), ptr(Tden), ld, nan, done_p, st))
                 call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
                      nparts, ptr(red), nan, done_p, st)
                 allreduce_(red, group)
@@ -387,8 +421,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         call("mbpls_nipals_record_component_f64", C.byref(rec), st)
         last = (k == K - 1)
         fuse = fuse_next_xtu and not last
-        call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts), ptr(u0) if fuse else None,
-             ptr(u0u0) if fuse else None, ptr(res.P[k]), ptr(w) if fuse else None, ptr(pss), nan, deflate_mode, st)
+        timed("deflate", lambda: call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts), ptr(u0) if fuse else None,
+                                      ptr(u0u0) if fuse else None, ptr(res.P[k]), ptr(w) if fuse else None, ptr(pss),
+                                      nan, deflate_mode, st))
         w_ready = fuse
         if p > 0:
             call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
@@ -441,7 +476,8 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         f0, f1, _ = make_splits(block_off, n, sm_count(dev))
         ns = len(f0)
         part = torch.zeros((ns, Cc * ld), dtype=F64, device=dev)
-        call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(_i32(f0, dev)), ptr(_i32(f1, dev)),
+        sf0, sf1 = _i32(f0, dev), _i32(f1, dev)  # keep alive: ptr() of a temporary would dangle
+        call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(sf0), ptr(sf1),
              ns, ptr(part), ld, stream_ptr(dev))
         call("mbpls_reduce_chunks_f64", ptr(part), ns, Cc * ld, ptr(out), stream_ptr(dev))
     allreduce_(out, group)

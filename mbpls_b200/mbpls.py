@@ -42,6 +42,8 @@ _RUNTIME_DEFAULTS = dict(
     standardize_mode=0,   # idem for the standardisation pass
     trips_per_sync=None,  # NIPALS trips enqueued per convergence-flag readback (None: auto)
     max_iter=1_000_000,   # safety cap on NIPALS trips; the reference loop is unbounded (mbpls.py:841)
+    global_sizes=None,    # multi-GPU: the blocks passed in are this rank's column ranges of blocks of these sizes
+    profile=None,         # dict collecting CUDA-event pairs per kernel (bench.py roofline)
 )
 
 
@@ -55,7 +57,7 @@ def _shape2(a):
     return tuple(np.shape(a))
 
 
-def _as_2d_source(a, what: str):
+def _as_2d_source(a, what: str, allow_empty: bool = False):
     """Array-like -> numpy float64 view / torch tensor with 2 dims (no copy when already float64)."""
     if isinstance(a, torch.Tensor):
         t = a
@@ -68,7 +70,7 @@ def _as_2d_source(a, what: str):
                 raise ValueError(f"could not convert {what} to float64") from exc
     if t.ndim != 2:
         raise ValueError(f"Expected 2D array, got {t.ndim}D array instead ({what}).")
-    if t.shape[0] < 1 or t.shape[1] < 1:
+    if t.shape[0] < 1 or (t.shape[1] < 1 and not allow_empty):
         raise ValueError(f"Found array with {t.shape[0]} sample(s) and {t.shape[1]} feature(s) while a minimum of 1 is required.")
     return t
 
@@ -165,9 +167,10 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         return (np.where(row_has)[0], np.where(col_has)[0], np.where(~row_has)[0], np.where(~col_has)[0])
 
     # ------------------------------------------------------------------ ingest shared by fit / predict / transform
-    def _ingest(self, X, n_expected: Optional[int], shard: Optional[ShardMap], device, what="X"):
+    def _ingest(self, X, n_expected: Optional[int], shard: Optional[ShardMap], device, what="X", adopt=False):
+        gs = self._runtime()["global_sizes"]
         blocks = X if _is_block_list(X) else [X]
-        blocks = [_as_2d_source(b, what) for b in blocks]
+        blocks = [_as_2d_source(b, what, allow_empty=gs is not None) for b in blocks]
         n = blocks[0].shape[0]
         want = n if n_expected is None else int(n_expected)
         for b in blocks:
@@ -175,12 +178,20 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 raise ValueError("Found input variables with inconsistent numbers of samples: %r"
                                  % [int(b.shape[0]), want])
         sizes = [int(b.shape[1]) for b in blocks]
-        if shard is None:
-            _, rank, world = self._group_info()
+        _, rank, world = self._group_info()
+        if gs is not None:  # pre-sharded input
+            want_shard = ShardMap.build(gs, rank, world)
+            local = [c1 - c0 for c0, c1 in want_shard.local_ranges]
+            if sizes != local:
+                raise ValueError("pre-sharded blocks have widths %r, expected %r" % (sizes, local))
+            if shard is not None and list(shard.sizes) != list(gs):
+                raise ValueError("X has %r features per block, but MBPLS was fitted with %r" % (list(gs), list(shard.sizes)))
+            shard = want_shard
+        elif shard is None:
             shard = ShardMap.build(sizes, rank, world)
         elif list(shard.sizes) != sizes:
             raise ValueError("X has %r features per block, but MBPLS was fitted with %r" % (sizes, list(shard.sizes)))
-        Xt = E.ingest_blocks(blocks, n, shard, device)
+        Xt = E.ingest_blocks(blocks, n, shard, device, presharded=gs is not None, adopt=adopt)
         return Xt, n, shard
 
     # ------------------------------------------------------------------ fit (mbpls.py:273-1050)
@@ -207,7 +218,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             Ysrc = _as_2d_source(Ysrc, "Y")
             n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
             # ---- X blocks (mbpls.py:299-347)
-            Xt, n_x, shard = self._ingest(X, n, None, device)
+            Xt, n_x, shard = self._ingest(X, n, None, device, adopt=not self.copy)
             B = len(shard.sizes)
             ld = Xt.shape[1]
             Yt = E.alloc_feature_major(q, n, device)
@@ -327,7 +338,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         res = E.nipals_fit(Xt, Yt, n, shard.block_off, K, u0=u0, nanmode=sparse, row_flag=row_flag, ycol_flag=ycol_flag,
                            max_tol=self.max_tol, norm_kind=E.norm_kind_of(self.nipals_convergence_norm),
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
-                           deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"])
+                           deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"])
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")

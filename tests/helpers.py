@@ -83,3 +83,17 @@ def compare(ours, ref, tol, what, skip=()):
             worst, worst_key = e, key
         assert e <= tol, f"{what}: {key} rel err {e:.3e} > {tol:g}"
     return worst, worst_key
+
+
+def assert_trips(ours, oracle_trips, oracle_traces, tol, what=""):
+    """NIPALS trip counts: exact wherever the oracle's diff_t crosses `tol` with margin (factor 3 on both
+    sides of the threshold); where the trajectory grazes the fp64 noise floor (hard
+    part 1) a different summation order may legitimately move the exit by a trip or two."""
+    assert len(ours) == len(oracle_trips), (what, ours, oracle_trips)
+    for k, (a, b) in enumerate(zip(ours, oracle_trips)):
+        tr = oracle_traces[k] if oracle_traces is not None else None
+        margin = tr is not None and len(tr) >= 1 and tr[-1] <= tol / 3 and (len(tr) < 2 or tr[-2] >= 3 * tol)
+        if margin or tr is None:
+            assert a == b, f"{what}: component {k}: {a} trips vs oracle {b}"
+        else:
+            assert abs(a - b) <= 2, f"{what}: component {k}: {a} trips vs oracle {b} (grazing exit)"

@@ -9,12 +9,12 @@ import warnings
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, compare, live_cases, load_live, rel_err, snapshot_model
+from helpers import GOLDEN, assert_trips, compare, live_cases, load_live, rel_err, snapshot_model
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-8
-NIPALS_CASES = [c for c in live_cases() if "nipals" in c]
+NIPALS_CASES = [c for c in live_cases() if "nipals" in c and "unipals" not in c]
 
 
 def _fit(kwargs, X, Y, **rt):
@@ -79,7 +79,7 @@ def test_nipals_matches_live_oracle(n, sizes, q, nan_frac):
     m = _fit(kw, X, Y)
     ours = snapshot_model(m, Xt, Yt)
     compare(ours, ref, TOL, f"live n={n}")
-    assert list(m.n_iter_) == list(o.n_iter_)
+    assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, 1e-14, f"live n={n}")
 
 
 @pytest.mark.parametrize("rt", [dict(deflate_mode=1, standardize_mode=1), dict(fuse_next_xtu=False),
@@ -129,7 +129,7 @@ def test_ingest_layouts_and_roundtrip():
     A = rng.standard_normal((45, 70))
     want = A.T
     for src in (A, np.asfortranarray(A), A[:, ::1], torch.from_numpy(A), torch.from_numpy(A).to(dev),
-                torch.from_numpy(np.ascontiguousarray(A.T)).to(dev).t(), A.astype(np.float32).astype(np.float64)):
+                torch.from_numpy(np.ascontiguousarray(A.T)).to(dev).t(), A.tolist()):
         Xt = E.alloc_feature_major(70, 45, dev)
         E.ingest_feature_major(src, 45, 0, 70, Xt, dev)
         assert np.array_equal(Xt[:, :45].cpu().numpy(), want)
