@@ -36,8 +36,9 @@ __device__ __forceinline__ int warp_or(int v) {
   return v;
 }
 
-// Deterministic block-wide sum of `NV` values per thread.  `scratch` must hold 32*NV doubles.
-// Every thread gets the result.  Two __syncthreads per call.
+// Deterministic block-wide sum of `NV` values per thread (blockDim <= 1024).  `scratch` must hold
+// 32*NV doubles.  Every thread gets the result: warp shuffles, one smem exchange, and the same
+// shuffle tree over the per-warp partials in every warp -> bitwise reproducible.  Two __syncthreads.
 template <int NV>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -46,15 +47,11 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   __syncthreads();  // protect scratch from a previous call's readers
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) scratch[warp * NV + k] = v[k];
+    for (int k = 0; k < NV; ++k) scratch[k * 32 + warp] = v[k];
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double s = 0.0;
-    for (int w = 0; w < nw; ++w) s += scratch[w * NV + k];  // fixed order -> bitwise reproducible
-    v[k] = s;
-  }
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? scratch[k * 32 + lane] : 0.0);
 }
 
 __device__ __forceinline__ double block_sum1(double x, double* scratch) {

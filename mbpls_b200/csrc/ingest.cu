@@ -167,6 +167,76 @@ __global__ void __launch_bounds__(256) standardize_fused_kernel(double* __restri
   stream_feature_slabs<true>(Xt, sh, op);
 }
 
+// Long features: 1024-thread CTA, each thread keeps its EPT samples of the resident feature in
+// registers across the three reductions (one shared-memory read + one write per element).
+template <int EPT>
+struct StandardizeWideOp {
+  int n;
+  long ld;
+  ScalerOut out;
+  double* scratch;
+  __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    for (int f = 0; f < nf; ++f) {
+      double* x = slab + static_cast<size_t>(f) * ld;
+      double xr[EPT];
+      double v[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        xr[k] = i < n ? x[i] : NAN;  // out-of-range lanes behave like missing values
+        if (!isnan(xr[k])) {
+          v[0] += 1.0;
+          v[1] += xr[k];
+        }
+      }
+      block_sum<2>(v, scratch);
+      const double cnt = v[0], mean = v[1] / v[0];
+      double c[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        xr[k] = xr[k] - mean;
+        if (!isnan(xr[k])) {
+          c[0] += xr[k];
+          c[1] = fma(xr[k], xr[k], c[1]);
+        }
+      }
+      block_sum<2>(c, scratch);
+      double var;
+      const double scale = scale_from(cnt, mean, c[0], c[1], var);
+      double z[1] = {0.0};
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        const double zi = xr[k] / scale;
+        if (i < n) x[i] = zi;
+        if (!isnan(zi)) z[0] = fma(zi, zi, z[0]);
+      }
+      block_sum<1>(z, scratch);
+      if (threadIdx.x == 0) {
+        out.mean[f0 + f] = mean;
+        out.var[f0 + f] = var;
+        out.scale[f0 + f] = scale;
+        out.seen[f0 + f] = static_cast<long long>(cnt);
+        out.zss[f0 + f] = z[0];
+      }
+    }
+  }
+};
+
+template <int EPT>
+__global__ void __launch_bounds__(1024, 1) standardize_wide_kernel(double* __restrict__ Xt, StreamShape sh, int n, ScalerOut out) {
+  __shared__ double scratch[64];
+  StandardizeWideOp<EPT> op{n, sh.ld, out, scratch};
+  stream_feature_slabs<true>(Xt, sh, op);
+}
+
+template <int EPT>
+static void launch_standardize_wide(double* Xt, const StreamShape& sh, int n, const ScalerOut& out, int grid, size_t smem,
+                                    cudaStream_t st) {
+  cudaFuncSetAttribute(standardize_wide_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  standardize_wide_kernel<EPT><<<grid, 1024, smem, st>>>(Xt, sh, n, out);
+}
+
 // Fallback for features too long for shared memory: one CTA per feature straight from global
 // memory (3 reads + 1 write instead of 1 + 1).
 __global__ void __launch_bounds__(256) standardize_global_kernel(double* __restrict__ Xt, long ld, int n, int p, ScalerOut out) {
@@ -284,7 +354,14 @@ int mbpls_standardize_fit_f64(double* Xt, long ld, int n, int p, double* mean, d
   if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
-    if (cta_wide) {
+    if (cta_wide && n <= 16384) {
+      const int ept = (n + 1023) / 1024;
+      if (ept <= 4) launch_standardize_wide<4>(Xt, sh, n, out, grid, smem, st);
+      else if (ept <= 8) launch_standardize_wide<8>(Xt, sh, n, out, grid, smem, st);
+      else if (ept <= 10) launch_standardize_wide<10>(Xt, sh, n, out, grid, smem, st);
+      else if (ept <= 12) launch_standardize_wide<12>(Xt, sh, n, out, grid, smem, st);
+      else launch_standardize_wide<16>(Xt, sh, n, out, grid, smem, st);
+    } else if (cta_wide) {
       cudaFuncSetAttribute(standardize_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       standardize_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, n, out);
     } else {

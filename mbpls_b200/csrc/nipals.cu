@@ -540,6 +540,96 @@ __global__ void __launch_bounds__(256) loadings_deflate_fused_kernel(double* __r
   stream_feature_slabs<true>(Xt, sh, op);
 }
 
+// Long features (n > 1024): one 1024-thread CTA per resident feature.  Every thread keeps its EPT
+// samples of ts in registers for the whole kernel and its EPT samples of the resident feature between
+// the loading reduction and the update, so a feature costs one shared-memory read and one write per
+// element; u0 (fused next-XtU only) is streamed from L2 with EPT independent loads in flight.
+template <int EPT>
+struct DeflateWideOp {
+  DeflateParams P;
+  double* scratch;
+  double ts_r[EPT];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const int i = threadIdx.x + k * 1024;
+      ts_r[k] = i < P.n ? P.ts[i] : 0.0;
+    }
+  }
+  __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    for (int f = 0; f < nf; ++f) {
+      double* x = slab + static_cast<size_t>(f) * P.ld;
+      double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        const double xv = i < P.n ? x[i] : 0.0;
+        if (P.nanmode) {
+          if (!isnan(xv)) {
+            v[0] = fma(xv, ts_r[k], v[0]);
+            v[1] = fma(ts_r[k], ts_r[k], v[1]);
+          } else {
+            v[2] = 1.0;
+          }
+        } else {
+          v[0] = fma(xv, ts_r[k], v[0]);
+        }
+      }
+      block_sum<3>(v, scratch);
+      const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
+      double w[3] = {0.0, 0.0, 0.0};
+      double u_r[EPT];
+      if (P.u0) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          const int i = threadIdx.x + k * 1024;
+          u_r[k] = i < P.n ? __ldg(P.u0 + i) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 1024;
+        const double xi = __dsub_rn(i < P.n ? x[i] : 0.0, __dmul_rn(ts_r[k], pj));
+        if (i < P.n) x[i] = xi;
+        if (P.u0) {
+          if (P.nanmode) {
+            if (!isnan(xi)) {
+              w[0] = fma(xi, u_r[k], w[0]);
+              w[1] = fma(u_r[k], u_r[k], w[1]);
+            } else {
+              w[2] = 1.0;
+            }
+          } else {
+            w[0] = fma(xi, u_r[k], w[0]);
+          }
+        }
+      }
+      if (P.u0) block_sum<3>(w, scratch);
+      if (threadIdx.x == 0) {
+        P.P_k[f0 + f] = pj;
+        P.pss[f0 + f] = pj * pj;
+        if (P.u0) P.w_next[f0 + f] = (P.nanmode && w[2] > 0.0) ? w[0] / w[1] : w[0] / *P.u0u0;
+      }
+    }
+  }
+};
+
+template <int EPT>
+__global__ void __launch_bounds__(1024, 1) loadings_deflate_wide_kernel(double* __restrict__ Xt, StreamShape sh, DeflateParams P) {
+  __shared__ double scratch[96];
+  DeflateWideOp<EPT> op;
+  op.P = P;
+  op.scratch = scratch;
+  op.init();
+  stream_feature_slabs<true>(Xt, sh, op);
+}
+
+template <int EPT>
+static void launch_deflate_wide(double* Xt, const StreamShape& sh, const DeflateParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(loadings_deflate_wide_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  loadings_deflate_wide_kernel<EPT><<<grid, 1024, smem, st>>>(Xt, sh, P);
+}
+
 // global-memory fallback (feature too long for shared memory): 2 reads + 1 write
 __global__ void __launch_bounds__(256) loadings_deflate_global_kernel(double* __restrict__ Xt, int p, DeflateParams P) {
   __shared__ double scratch[96];
@@ -670,7 +760,14 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
   if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
-    if (cta_wide) {
+    if (cta_wide && n <= 16384) {
+      const int ept = (n + 1023) / 1024;
+      if (ept <= 4) launch_deflate_wide<4>(Xt, sh, P, grid, smem, st);
+      else if (ept <= 8) launch_deflate_wide<8>(Xt, sh, P, grid, smem, st);
+      else if (ept <= 10) launch_deflate_wide<10>(Xt, sh, P, grid, smem, st);
+      else if (ept <= 12) launch_deflate_wide<12>(Xt, sh, P, grid, smem, st);
+      else launch_deflate_wide<16>(Xt, sh, P, grid, smem, st);
+    } else if (cta_wide) {
       cudaFuncSetAttribute(loadings_deflate_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       loadings_deflate_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, P);
     } else {
