@@ -76,6 +76,7 @@ int mbpls_segsum_f64(const double* v, const int* off, int nseg, double* out, voi
 /* ---- NIPALS inner loop (mbpls.py:841-914) -------------------------------------------------------- */
 int mbpls_xtu_feats_per_cta(int p);
 int mbpls_xtu_num_ctas(int p); /* rows of norm_part */
+int mbpls_xw_ctas_per_sm(void); /* resident CTAs per SM of the sample-owning kernels: size grids to one wave */
 
 /* w[j] = x_j . u / u'u (mbpls.py:847,856); NaN mode: masked ratio for features with NaN (:848-852).
  * uu == NULL: no division for fully observed features (the loadings of :920,:928).

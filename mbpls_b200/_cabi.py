@@ -59,6 +59,7 @@ SIGNATURES = {
     "mbpls_segsum_f64": [_p, _p, _i, _p, _p],
     "mbpls_xtu_feats_per_cta": [_i],
     "mbpls_xtu_num_ctas": [_i],
+    "mbpls_xw_ctas_per_sm": [],
     "mbpls_nipals_xtu_f64": [_p, _l, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p, _p],
     "mbpls_block_sumsq_parts_f64": [_p, _i, _p, _i, _p, _p, _p],
     "mbpls_nipals_xw_f64": [_p, _l, _i, _p, _p, _p, _i, _p, _p, _l, _i, _p, _p],
@@ -78,7 +79,8 @@ SIGNATURES = {
 }
 
 # functions whose int return value is a plain number, not a status
-_PLAIN = {"mbpls_abi_version", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks"}
+_PLAIN = {"mbpls_abi_version", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
+          "mbpls_xw_ctas_per_sm"}
 
 
 class MbplsCudaError(RuntimeError):

@@ -54,6 +54,23 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? scratch[k * 32 + lane] : 0.0);
 }
 
+// Same reduction among the consumer warps of a warp-specialised CTA (threads [0, nthreads), nthreads a
+// multiple of 32): named barrier 1 instead of __syncthreads so the producer warp is not involved.
+template <int NV>
+__device__ __forceinline__ void block_sum_consumers(double (&v)[NV], double* scratch, int nthreads) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[k * 32 + warp] = v[k];
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? scratch[k * 32 + lane] : 0.0);
+}
+
 __device__ __forceinline__ double block_sum1(double x, double* scratch) {
   double v[1] = {x};
   block_sum<1>(v, scratch);
@@ -76,6 +93,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

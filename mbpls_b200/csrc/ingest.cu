@@ -144,31 +144,25 @@ __device__ __forceinline__ void standardize_resident(double* x, int n, int j, co
   }
 }
 
-template <bool CTA_WIDE>
-struct StandardizeOp {
+// Short features: one consumer warp per resident feature (8 consumer warps + the producer warp).
+struct StandardizeWarpOp {
   int n;
   long ld;
   ScalerOut out;
-  double* scratch;
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
-    if (CTA_WIDE) {
-      for (int f = 0; f < nf; ++f) standardize_resident<true>(slab + static_cast<size_t>(f) * ld, n, f0 + f, out, scratch);
-    } else {
-      const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-      for (int f = warp; f < nf; f += nw) standardize_resident<false>(slab + static_cast<size_t>(f) * ld, n, f0 + f, out, nullptr);
-    }
+    const int warp = threadIdx.x >> 5, nw = (blockDim.x >> 5) - 1;
+    for (int f = warp; f < nf; f += nw) standardize_resident<false>(slab + static_cast<size_t>(f) * ld, n, f0 + f, out, nullptr);
   }
 };
 
-template <bool CTA_WIDE>
-__global__ void __launch_bounds__(256) standardize_fused_kernel(double* __restrict__ Xt, StreamShape sh, int n, ScalerOut out) {
-  __shared__ double scratch[64];
-  StandardizeOp<CTA_WIDE> op{n, sh.ld, out, scratch};
+__global__ void __launch_bounds__(288) standardize_warp_kernel(double* __restrict__ Xt, StreamShape sh, int n, ScalerOut out) {
+  StandardizeWarpOp op{n, sh.ld, out};
   stream_feature_slabs<true>(Xt, sh, op);
 }
 
-// Long features: 1024-thread CTA, each thread keeps its EPT samples of the resident feature in
-// registers across the three reductions (one shared-memory read + one write per element).
+// Long features: 1024-thread CTA (31 consumer warps + the producer warp); each consumer keeps its EPT
+// samples of the resident feature in registers across the three reductions (one shared-memory read
+// and one write per element).
 template <int EPT>
 struct StandardizeWideOp {
   int n;
@@ -176,20 +170,21 @@ struct StandardizeWideOp {
   ScalerOut out;
   double* scratch;
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    const int nt = blockDim.x - 32;
     for (int f = 0; f < nf; ++f) {
       double* x = slab + static_cast<size_t>(f) * ld;
       double xr[EPT];
       double v[2] = {0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
-        const int i = threadIdx.x + k * 1024;
+        const int i = threadIdx.x + k * nt;
         xr[k] = i < n ? x[i] : NAN;  // out-of-range lanes behave like missing values
         if (!isnan(xr[k])) {
           v[0] += 1.0;
           v[1] += xr[k];
         }
       }
-      block_sum<2>(v, scratch);
+      block_sum_consumers<2>(v, scratch, nt);
       const double cnt = v[0], mean = v[1] / v[0];
       double c[2] = {0.0, 0.0};
 #pragma unroll
@@ -200,18 +195,18 @@ struct StandardizeWideOp {
           c[1] = fma(xr[k], xr[k], c[1]);
         }
       }
-      block_sum<2>(c, scratch);
+      block_sum_consumers<2>(c, scratch, nt);
       double var;
       const double scale = scale_from(cnt, mean, c[0], c[1], var);
       double z[1] = {0.0};
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
-        const int i = threadIdx.x + k * 1024;
+        const int i = threadIdx.x + k * nt;
         const double zi = xr[k] / scale;
         if (i < n) x[i] = zi;
         if (!isnan(zi)) z[0] = fma(zi, zi, z[0]);
       }
-      block_sum<1>(z, scratch);
+      block_sum_consumers<1>(z, scratch, nt);
       if (threadIdx.x == 0) {
         out.mean[f0 + f] = mean;
         out.var[f0 + f] = var;
@@ -354,19 +349,15 @@ int mbpls_standardize_fit_f64(double* Xt, long ld, int n, int p, double* mean, d
   if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
-    if (cta_wide && n <= 16384) {
-      const int ept = (n + 1023) / 1024;
+    if (cta_wide) {
+      const int ept = (n + 991) / 992;  // 31 consumer warps
       if (ept <= 4) launch_standardize_wide<4>(Xt, sh, n, out, grid, smem, st);
       else if (ept <= 8) launch_standardize_wide<8>(Xt, sh, n, out, grid, smem, st);
-      else if (ept <= 10) launch_standardize_wide<10>(Xt, sh, n, out, grid, smem, st);
       else if (ept <= 12) launch_standardize_wide<12>(Xt, sh, n, out, grid, smem, st);
       else launch_standardize_wide<16>(Xt, sh, n, out, grid, smem, st);
-    } else if (cta_wide) {
-      cudaFuncSetAttribute(standardize_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      standardize_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, n, out);
     } else {
-      cudaFuncSetAttribute(standardize_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      standardize_fused_kernel<false><<<grid, 256, smem, st>>>(Xt, sh, n, out);
+      cudaFuncSetAttribute(standardize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      standardize_warp_kernel<<<grid, 288, smem, st>>>(Xt, sh, n, out);
     }
   } else {
     int grid = p < num_sms() * 8 ? p : num_sms() * 8;

@@ -136,7 +136,7 @@ xtu_kernel(const double* __restrict__ Xt, long ld, int n, int p, int feats_per_c
 // grid = (sample chunks of 512, splits); partials go to Tnum[split][ld] (and Tden).
 // ------------------------------------------------------------------------------------------
 template <bool NANMODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 xw_kernel(const double* __restrict__ Xt, long ld, int n, const double* __restrict__ w,
           const int* __restrict__ split_f0, const int* __restrict__ split_f1, double* __restrict__ Tnum,
           double* __restrict__ Tden, long ldt, const int* __restrict__ done) {
@@ -519,41 +519,45 @@ __device__ __forceinline__ void deflate_resident(double* x, int j, const Deflate
   }
 }
 
-template <bool CTA_WIDE>
-struct DeflateOp {
+// Short features: one consumer warp per resident feature (8 consumer warps + the producer warp).
+struct DeflateWarpOp {
   DeflateParams P;
-  double* scratch;
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
-    if (CTA_WIDE) {
-      for (int f = 0; f < nf; ++f) deflate_resident<true>(slab + static_cast<size_t>(f) * P.ld, f0 + f, P, scratch);
-    } else {
-      const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-      for (int f = warp; f < nf; f += nw) deflate_resident<false>(slab + static_cast<size_t>(f) * P.ld, f0 + f, P, nullptr);
-    }
+    const int warp = threadIdx.x >> 5, nw = (blockDim.x >> 5) - 1;
+    for (int f = warp; f < nf; f += nw) deflate_resident<false>(slab + static_cast<size_t>(f) * P.ld, f0 + f, P, nullptr);
   }
 };
 
-template <bool CTA_WIDE>
-__global__ void __launch_bounds__(256) loadings_deflate_fused_kernel(double* __restrict__ Xt, StreamShape sh, DeflateParams P) {
-  __shared__ double scratch[96];
-  DeflateOp<CTA_WIDE> op{P, scratch};
+__global__ void __launch_bounds__(288) loadings_deflate_warp_kernel(double* __restrict__ Xt, StreamShape sh, DeflateParams P) {
+  DeflateWarpOp op{P};
   stream_feature_slabs<true>(Xt, sh, op);
 }
 
-// Long features (n > 1024): one 1024-thread CTA per resident feature.  Every thread keeps its EPT
-// samples of ts in registers for the whole kernel and its EPT samples of the resident feature between
-// the loading reduction and the update, so a feature costs one shared-memory read and one write per
-// element; u0 (fused next-XtU only) is streamed from L2 with EPT independent loads in flight.
+// Long features (n > 1024): one 1024-thread CTA (31 consumer warps + the producer warp) per resident
+// feature.  Every consumer keeps its EPT samples of ts in registers for the whole kernel, so a feature
+// costs two shared-memory reads and one write per element; u0 (fused next-XtU only) is streamed from
+// L2 with EPT independent loads in flight.
 template <int EPT>
 struct DeflateWideOp {
   DeflateParams P;
   double* scratch;
+  int nt;  // consumer threads
   double ts_r[EPT];
   __device__ __forceinline__ void init() {
+    nt = blockDim.x - 32;
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
-      const int i = threadIdx.x + k * 1024;
-      ts_r[k] = i < P.n ? P.ts[i] : 0.0;
+      const int i = threadIdx.x + k * nt;
+      ts_r[k] = (threadIdx.x < nt && i < P.n) ? P.ts[i] : 0.0;
+    }
+  }
+  __device__ __forceinline__ void reduce3(double (&v)[3]) {
+    if (P.nanmode) {
+      block_sum_consumers<3>(v, scratch, nt);
+    } else {
+      double one[1] = {v[0]};
+      block_sum_consumers<1>(one, scratch, nt);
+      v[0] = one[0];
     }
   }
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
@@ -562,7 +566,7 @@ struct DeflateWideOp {
       double v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
-        const int i = threadIdx.x + k * 1024;
+        const int i = threadIdx.x + k * nt;
         const double xv = i < P.n ? x[i] : 0.0;
         if (P.nanmode) {
           if (!isnan(xv)) {
@@ -575,21 +579,21 @@ struct DeflateWideOp {
           v[0] = fma(xv, ts_r[k], v[0]);
         }
       }
-      block_sum<3>(v, scratch);
+      reduce3(v);
       const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
       double w[3] = {0.0, 0.0, 0.0};
       double u_r[EPT];
       if (P.u0) {
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
-          const int i = threadIdx.x + k * 1024;
+          const int i = threadIdx.x + k * nt;
           u_r[k] = i < P.n ? __ldg(P.u0 + i) : 0.0;
         }
       }
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
-        const int i = threadIdx.x + k * 1024;
-        const double xi = __dsub_rn(i < P.n ? x[i] : 0.0, __dmul_rn(ts_r[k], pj));
+        const int i = threadIdx.x + k * nt;
+        const double xi = __dsub_rn(i < P.n ? x[i] : 0.0, __dmul_rn(ts_r[k], pj));  // reference rounds ts*p first (:969)
         if (i < P.n) x[i] = xi;
         if (P.u0) {
           if (P.nanmode) {
@@ -604,7 +608,7 @@ struct DeflateWideOp {
           }
         }
       }
-      if (P.u0) block_sum<3>(w, scratch);
+      if (P.u0) reduce3(w);
       if (threadIdx.x == 0) {
         P.P_k[f0 + f] = pj;
         P.pss[f0 + f] = pj * pj;
@@ -670,6 +674,16 @@ int mbpls_xtu_feats_per_cta(int p) {
   if (f < 16) f = 16;
   if (f > 4096) f = 4096;
   return static_cast<int>(f);
+}
+
+int mbpls_xw_ctas_per_sm(void) {
+  static int v = -1;
+  if (v < 0) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, xw_kernel<false>, 256, 0) != cudaSuccess || b < 1) b = 4;
+    v = b;
+  }
+  return v;
 }
 
 int mbpls_xtu_num_ctas(int p) {
@@ -760,19 +774,15 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
   if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
-    if (cta_wide && n <= 16384) {
-      const int ept = (n + 1023) / 1024;
+    if (cta_wide) {
+      const int ept = (n + 991) / 992;  // 31 consumer warps
       if (ept <= 4) launch_deflate_wide<4>(Xt, sh, P, grid, smem, st);
       else if (ept <= 8) launch_deflate_wide<8>(Xt, sh, P, grid, smem, st);
-      else if (ept <= 10) launch_deflate_wide<10>(Xt, sh, P, grid, smem, st);
       else if (ept <= 12) launch_deflate_wide<12>(Xt, sh, P, grid, smem, st);
       else launch_deflate_wide<16>(Xt, sh, P, grid, smem, st);
-    } else if (cta_wide) {
-      cudaFuncSetAttribute(loadings_deflate_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      loadings_deflate_fused_kernel<true><<<grid, 256, smem, st>>>(Xt, sh, P);
     } else {
-      cudaFuncSetAttribute(loadings_deflate_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      loadings_deflate_fused_kernel<false><<<grid, 256, smem, st>>>(Xt, sh, P);
+      cudaFuncSetAttribute(loadings_deflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      loadings_deflate_warp_kernel<<<grid, 288, smem, st>>>(Xt, sh, P);
     }
   } else {
     int grid = p < num_sms() * 8 ? p : num_sms() * 8;

@@ -247,25 +247,38 @@ def nan_census(Xt: torch.Tensor, n: int, block_off_dev: torch.Tensor, B: int):
 # --------------------------------------------------------------------------------------------- #
 # split table for the sample-owning kernels (xw, skinny_gemm)
 # --------------------------------------------------------------------------------------------- #
-def make_splits(block_off: Sequence[int], n: int, sm_count: int, ctas_per_sm: int = 8, min_feats: int = 64):
-    """Cut every block's local feature range into pieces so that (row chunks x splits) fills the GPU."""
+def make_splits(block_off: Sequence[int], n: int, sm_count: int, ctas_per_sm: Optional[int] = None, min_feats: int = 32):
+    """Cut every block's local feature range into pieces so that (row chunks x splits) is at most ONE
+    wave of resident CTAs (a partial second wave would run alone at the end of the kernel), with the
+    pieces as equal as possible (largest-remainder apportionment over the blocks)."""
+    if ctas_per_sm is None:
+        ctas_per_sm = call("mbpls_xw_ctas_per_sm")
     B = len(block_off) - 1
-    p = block_off[-1]
+    sizes = [block_off[b + 1] - block_off[b] for b in range(B)]
+    p = sum(sizes)
     row_chunks = max(1, -(-n // 512))
-    target = max(1, (sm_count * ctas_per_sm) // row_chunks)
+    total = max(1, (sm_count * ctas_per_sm) // row_chunks)
+    total = max(1, min(total, max(1, p // min_feats)))
+    nonempty = [b for b in range(B) if sizes[b] > 0]
+    counts = [0] * B
+    if nonempty:
+        total = max(total, len(nonempty))
+        quota = [sizes[b] * total / p for b in range(B)]
+        for b in nonempty:
+            counts[b] = max(1, int(quota[b]))
+        while sum(counts) > total and any(counts[b] > 1 for b in nonempty):
+            b = max((b for b in nonempty if counts[b] > 1), key=lambda b: counts[b] - quota[b])
+            counts[b] -= 1
+        while sum(counts) < total:
+            b = max(nonempty, key=lambda b: quota[b] - counts[b])
+            counts[b] += 1
     f0, f1, bso = [], [], [0]
     for b in range(B):
         a, e = block_off[b], block_off[b + 1]
-        pb = e - a
-        if pb > 0:
-            nb = max(1, min(int(round(target * pb / max(p, 1))) or 1, max(1, pb // min_feats)))
-            step = -(-pb // nb)
-            step = -(-step // 8) * 8
-            s = a
-            while s < e:
-                f0.append(s)
-                f1.append(min(e, s + step))
-                s += step
+        nb = min(counts[b], max(1, e - a)) if e > a else 0
+        for k in range(nb):
+            f0.append(a + (e - a) * k // nb)
+            f1.append(a + (e - a) * (k + 1) // nb)
         bso.append(len(f0))
     return f0, f1, bso
 
