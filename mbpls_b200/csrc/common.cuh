@@ -142,6 +142,11 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return r;
 }
 
+// streaming 16-byte store (written once, not re-read by this kernel)
+__device__ __forceinline__ void st_stream(double2* p, const double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // block index of local feature j given B+1 ascending offsets (B is small)
 __device__ __forceinline__ int block_of(const int* __restrict__ off, int B, int j) {
   int b = 0;

@@ -232,6 +232,68 @@ static void launch_standardize_wide(double* Xt, const StreamShape& sh, int n, co
   standardize_wide_kernel<EPT><<<grid, 1024, smem, st>>>(Xt, sh, n, out);
 }
 
+// Mid-length features (1024 < n <= 16384): register-resident variant (see loadings_deflate_regs_kernel):
+// a 256-thread CTA holds one whole feature in registers across the three reductions.
+template <int EPT2>
+__global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __restrict__ Xt, long ld, int n, int p, ScalerOut out) {
+  __shared__ double scratch[64];
+  const int n2 = (n + 1) >> 1;
+  const bool odd = (n & 1) != 0;
+  for (int j = blockIdx.x; j < p; j += gridDim.x) {
+    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * ld);
+    double2 xr[EPT2];
+    double v[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      xr[k] = i < n2 ? ld_stream(x2 + i) : make_double2(NAN, NAN);  // out of range == missing
+      if (odd && i == n2 - 1) xr[k].y = NAN;                         // the padding element is not a sample
+      if (!isnan(xr[k].x)) { v[0] += 1.0; v[1] += xr[k].x; }
+      if (!isnan(xr[k].y)) { v[0] += 1.0; v[1] += xr[k].y; }
+    }
+    block_sum<2>(v, scratch);
+    const double cnt = v[0], mean = v[1] / v[0];
+    double c[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      xr[k].x -= mean;
+      xr[k].y -= mean;
+      if (!isnan(xr[k].x)) { c[0] += xr[k].x; c[1] = fma(xr[k].x, xr[k].x, c[1]); }
+      if (!isnan(xr[k].y)) { c[0] += xr[k].y; c[1] = fma(xr[k].y, xr[k].y, c[1]); }
+    }
+    block_sum<2>(c, scratch);
+    double var;
+    const double scale = scale_from(cnt, mean, c[0], c[1], var);
+    double z[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n2) {
+        double2 zi = make_double2(xr[k].x / scale, xr[k].y / scale);
+        if (!isnan(zi.x)) z[0] = fma(zi.x, zi.x, z[0]);
+        if (!isnan(zi.y)) z[0] = fma(zi.y, zi.y, z[0]);
+        if (odd && i == n2 - 1) zi.y = 0.0;  // keep the padding element zero
+        st_stream(x2 + i, zi);
+      }
+    }
+    block_sum<1>(z, scratch);
+    if (threadIdx.x == 0) {
+      out.mean[j] = mean;
+      out.var[j] = var;
+      out.scale[j] = scale;
+      out.seen[j] = static_cast<long long>(cnt);
+      out.zss[j] = z[0];
+    }
+  }
+}
+
+template <int EPT2>
+static void launch_standardize_regs(double* Xt, long ld, int n, int p, const ScalerOut& out, cudaStream_t st) {
+  int grid = num_sms() * 2;
+  if (grid > p) grid = p;
+  standardize_regs_kernel<EPT2><<<grid, 256, 0, st>>>(Xt, ld, n, p, out);
+}
+
 // Fallback for features too long for shared memory: one CTA per feature straight from global
 // memory (3 reads + 1 write instead of 1 + 1).
 __global__ void __launch_bounds__(256) standardize_global_kernel(double* __restrict__ Xt, long ld, int n, int p, ScalerOut out) {
@@ -346,7 +408,16 @@ int mbpls_standardize_fit_f64(double* Xt, long ld, int n, int p, double* mean, d
   ScalerOut out{mean, var, scale, seen, zss};
   StreamShape sh;
   bool cta_wide = false;
-  if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
+  if (mode == 0 && n > 1024 && n <= 16384) {  // register-resident
+    const int e = (((n + 1) >> 1) + 255) / 256;
+    if (e <= 4) launch_standardize_regs<4>(Xt, ld, n, p, out, st);
+    else if (e <= 8) launch_standardize_regs<8>(Xt, ld, n, p, out, st);
+    else if (e <= 12) launch_standardize_regs<12>(Xt, ld, n, p, out, st);
+    else if (e <= 16) launch_standardize_regs<16>(Xt, ld, n, p, out, st);
+    else if (e <= 20) launch_standardize_regs<20>(Xt, ld, n, p, out, st);
+    else if (e <= 24) launch_standardize_regs<24>(Xt, ld, n, p, out, st);
+    else launch_standardize_regs<32>(Xt, ld, n, p, out, st);
+  } else if ((mode == 0 || mode == 2) && pick_stream_shape(ld, p, &sh, &cta_wide)) {  // mode 2: force the smem pipeline
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
     if (cta_wide) {

@@ -1,5 +1,6 @@
 // Host-side launch helpers shared by the .cu files (device properties, slab-shape choice).
 #pragma once
+#include <stdlib.h>
 #include "stream.cuh"
 
 namespace mbpls {
@@ -19,6 +20,19 @@ inline int num_sms() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return v;
+}
+
+// Bytes per bulk-copy op (multiple of 16).  One 80 KB op streams at only ~13 GB/s per SM (measured,
+// profiles/), several smaller ops in flight are needed to reach the HBM rate.  MBPLS_BULK_CHUNK overrides.
+inline int bulk_chunk_bytes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MBPLS_BULK_CHUNK");
+    long c = e ? atol(e) : 8192;
+    if (c < 512) c = 512;
+    v = static_cast<int>((c / 16) * 16);
   }
   return v;
 }
@@ -47,6 +61,7 @@ inline bool pick_stream_shape(long ld, int p, StreamShape* sh, bool* cta_wide) {
   sh->p = p;
   sh->G = G;
   sh->stages = stages;
+  sh->chunk = bulk_chunk_bytes();
   return true;
 }
 

@@ -466,6 +466,7 @@ struct DeflateParams {
   double* P_k;            // p_local loadings out
   double* w_next;         // p_local next w~ out (if u0)
   double* pss;            // p_local: p_j^2 (for explained variance), always written
+  int debug;              // profiling experiments only (MBPLS_DEFLATE_DEBUG): 1 = consumers skip the arithmetic
 };
 
 template <bool CTA_WIDE>
@@ -561,6 +562,7 @@ struct DeflateWideOp {
     }
   }
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
+    if (P.debug == 1) return;
     for (int f = 0; f < nf; ++f) {
       double* x = slab + static_cast<size_t>(f) * P.ld;
       double v[3] = {0.0, 0.0, 0.0};
@@ -632,6 +634,93 @@ template <int EPT>
 static void launch_deflate_wide(double* Xt, const StreamShape& sh, const DeflateParams& P, int grid, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(loadings_deflate_wide_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   loadings_deflate_wide_kernel<EPT><<<grid, 1024, smem, st>>>(Xt, sh, P);
+}
+
+// Mid-length features (1024 < n <= 16384): REGISTER-resident variant.  A 256-thread CTA loads one whole
+// feature into registers (EPT2 16-byte loads in flight per thread), reduces the loading, updates the
+// registers and streams them back: exactly 1 read + 1 write of X, no shared-memory staging, and the
+// n-vectors ts / u0 stay L1-resident.  Two CTAs per SM overlap one CTA's reductions with the other's
+// loads (the single-CTA shared-memory pipeline above is latency-chain-bound for long features:
+// measured 3.3 TB/s vs 6.0 TB/s for its copy skeleton, profiles/r1_notes.md).
+template <int EPT2>
+__global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* __restrict__ Xt, int p, DeflateParams P) {
+  __shared__ double scratch[96];
+  const int n2 = (P.n + 1) >> 1;  // 16-byte units; an odd tail pairs with the zero padding element
+  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(P.ts);
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(P.u0);
+  for (int j = blockIdx.x; j < p; j += gridDim.x) {
+    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * P.ld);
+    double2 xr[EPT2];
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      xr[k] = i < n2 ? ld_stream(x2 + i) : make_double2(0.0, 0.0);
+    }
+    double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const double2 t = i < n2 ? ts2[i] : make_double2(0.0, 0.0);
+      if (P.nanmode) {
+        if (!isnan(xr[k].x)) { v[0] = fma(xr[k].x, t.x, v[0]); v[1] = fma(t.x, t.x, v[1]); } else v[2] = 1.0;
+        if (!isnan(xr[k].y)) { v[0] = fma(xr[k].y, t.y, v[0]); v[1] = fma(t.y, t.y, v[1]); } else v[2] = 1.0;
+      } else {
+        v[0] = fma(xr[k].x, t.x, v[0]);
+        v[0] = fma(xr[k].y, t.y, v[0]);
+      }
+    }
+    if (P.nanmode) {
+      block_sum<3>(v, scratch);
+    } else {
+      double one[1] = {v[0]};
+      block_sum<1>(one, scratch);
+      v[0] = one[0];
+    }
+    const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
+    double w[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n2) {
+        const double2 t = ts2[i];
+        double2 xi;
+        xi.x = __dsub_rn(xr[k].x, __dmul_rn(t.x, pj));  // the reference rounds ts*p before subtracting (:969)
+        xi.y = __dsub_rn(xr[k].y, __dmul_rn(t.y, pj));
+        st_stream(x2 + i, xi);
+        if (P.u0) {
+          const double2 uv = u2[i];
+          if (P.nanmode) {
+            if (!isnan(xi.x)) { w[0] = fma(xi.x, uv.x, w[0]); w[1] = fma(uv.x, uv.x, w[1]); } else w[2] = 1.0;
+            if (!isnan(xi.y)) { w[0] = fma(xi.y, uv.y, w[0]); w[1] = fma(uv.y, uv.y, w[1]); } else w[2] = 1.0;
+          } else {
+            w[0] = fma(xi.x, uv.x, w[0]);
+            w[0] = fma(xi.y, uv.y, w[0]);
+          }
+        }
+      }
+    }
+    if (P.u0) {
+      if (P.nanmode) {
+        block_sum<3>(w, scratch);
+      } else {
+        double one[1] = {w[0]};
+        block_sum<1>(one, scratch);
+        w[0] = one[0];
+      }
+    }
+    if (threadIdx.x == 0) {
+      P.P_k[j] = pj;
+      P.pss[j] = pj * pj;
+      if (P.u0) P.w_next[j] = (P.nanmode && w[2] > 0.0) ? w[0] / w[1] : w[0] / *P.u0u0;
+    }
+  }
+}
+
+template <int EPT2>
+static void launch_deflate_regs(double* Xt, int p, const DeflateParams& P, cudaStream_t st) {
+  int grid = num_sms() * 2;
+  if (grid > p) grid = p;
+  loadings_deflate_regs_kernel<EPT2><<<grid, 256, 0, st>>>(Xt, p, P);
 }
 
 // global-memory fallback (feature too long for shared memory): 2 reads + 1 write
@@ -768,10 +857,21 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
   if (!Xt || !ts || !P_k || !pss || (u0 && (!u0u0 || !w_next)) || ld < n || (ld % 16) != 0) return MBPLS_ERR_ARG;
   if (p == 0) return MBPLS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MBPLS_DEFLATE_DEBUG"); dbg = e ? atoi(e) : 0; }
+  DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss, dbg};
   StreamShape sh;
   bool cta_wide = false;
-  if (mode == 0 && pick_stream_shape(ld, p, &sh, &cta_wide)) {
+  if (mode == 0 && n > 1024 && n <= 16384) {  // register-resident
+    const int e = (((n + 1) >> 1) + 255) / 256;
+    if (e <= 4) launch_deflate_regs<4>(Xt, p, P, st);
+    else if (e <= 8) launch_deflate_regs<8>(Xt, p, P, st);
+    else if (e <= 12) launch_deflate_regs<12>(Xt, p, P, st);
+    else if (e <= 16) launch_deflate_regs<16>(Xt, p, P, st);
+    else if (e <= 20) launch_deflate_regs<20>(Xt, p, P, st);
+    else if (e <= 24) launch_deflate_regs<24>(Xt, p, P, st);
+    else launch_deflate_regs<32>(Xt, p, P, st);
+  } else if ((mode == 0 || mode == 2) && pick_stream_shape(ld, p, &sh, &cta_wide)) {  // mode 2: force the smem pipeline
     const size_t smem = stream_smem_bytes(sh);
     const int grid = stream_grid(sh, smem);
     if (cta_wide) {

@@ -14,6 +14,7 @@ struct StreamShape {
   int p;         // features in this (local) matrix
   int G;         // features per slab
   int stages;    // ring depth (>= 2)
+  int chunk;     // bytes per bulk-copy op (a slab moves as ceil(bytes/chunk) ops so several are in flight)
 };
 
 // smem: [stages][G*ld] doubles, then 2*stages mbarriers (full, done; 8 B each)
@@ -60,7 +61,9 @@ __device__ __forceinline__ void stream_feature_slabs(double* __restrict__ Xt, co
         const uint32_t bytes = static_cast<uint32_t>(static_cast<size_t>(nf) * sh.ld * sizeof(double));
         const int s = k % sh.stages;
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(slab0 + static_cast<size_t>(s) * slab_elems, Xt + static_cast<size_t>(g) * sh.G * sh.ld, bytes, &full[s]);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(slab0 + static_cast<size_t>(s) * slab_elems);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(Xt + static_cast<size_t>(g) * sh.G * sh.ld);
+        for (uint32_t o = 0; o < bytes; o += sh.chunk) bulk_g2s(dst + o, src + o, min(static_cast<uint32_t>(sh.chunk), bytes - o), &full[s]);
       };
       const int pre = min(sh.stages, nmine);
       for (int k = 0; k < pre; ++k) issue_load(k);
@@ -73,8 +76,10 @@ __device__ __forceinline__ void stream_feature_slabs(double* __restrict__ Xt, co
         if (WRITEBACK) {
           const int g = first + k * step;
           const int nf = min(sh.G, sh.p - g * sh.G);
-          bulk_s2g(Xt + static_cast<size_t>(g) * sh.G * sh.ld, slab0 + static_cast<size_t>(s) * slab_elems,
-                   static_cast<uint32_t>(static_cast<size_t>(nf) * sh.ld * sizeof(double)));
+          const uint32_t bytes = static_cast<uint32_t>(static_cast<size_t>(nf) * sh.ld * sizeof(double));
+          unsigned char* dst = reinterpret_cast<unsigned char*>(Xt + static_cast<size_t>(g) * sh.G * sh.ld);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(slab0 + static_cast<size_t>(s) * slab_elems);
+          for (uint32_t o = 0; o < bytes; o += sh.chunk) bulk_s2g(dst + o, src + o, min(static_cast<uint32_t>(sh.chunk), bytes - o));
           bulk_commit();
         }
         if (kn < nmine) {

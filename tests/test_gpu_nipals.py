@@ -97,17 +97,31 @@ def test_runtime_variants_agree(rt):
         assert rel_err(a, b) < 1e-12
 
 
+@pytest.mark.parametrize("n", [1500, 2501, 9000])
+def test_long_feature_kernel_variants_agree(n):
+    """1024 < n <= 16384: register-resident (mode 0), global fallback (mode 1) and the warp-specialised
+    shared-memory bulk-copy pipeline (mode 2) must produce the same model; odd n exercises the padding."""
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(n, (150, 90), 2, 3, seed=n)
+    fits = [_fit(dict(n_components=3), X, Y, deflate_mode=m, standardize_mode=m) for m in (0, 1, 2)]
+    for other in fits[1:]:
+        assert list(other.n_iter_) == list(fits[0].n_iter_)
+        assert rel_err(other.beta_, fits[0].beta_) < 1e-11
+        assert rel_err(other.Ts_, fits[0].Ts_) < 1e-11
+        assert rel_err(other.x_scalers_[0].scale_, fits[0].x_scalers_[0].scale_) < 1e-13
+
+
 def test_standardize_kernel_matches_sklearn_semantics():
     import torch
     from mbpls_b200 import engine as E
     from oracle import OracleScaler
     rng = np.random.default_rng(1)
-    for n in (57, 1500):
+    for n in (57, 1500, 2049):
         X = rng.standard_normal((n, 40)) * rng.uniform(0.1, 30, 40) + rng.uniform(-4, 4, 40)
         X[:, 5] = 1.25
         X[rng.random(X.shape) < 0.07] = np.nan
         ref = OracleScaler().fit(X)
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             dev = torch.device("cuda:0")
             Xt = E.alloc_feature_major(40, n, dev)
             E.ingest_feature_major(X, n, 0, 40, Xt, dev)
