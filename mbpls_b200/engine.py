@@ -358,6 +358,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     Tden = buf(nsplit, ld, zero=True) if nan else None
     nred = (2 if nan else 1) * B * ld + B
     red = buf(nred, zero=True)
+    # multi-GPU: partials are reduced into red_local and *copied* into red before the all-reduce, so that
+    # the no-op trips enqueued after convergence re-create the same global sums instead of re-adding them
+    red_local = buf(nred, zero=True) if group is not None else red
     T = buf(B, ld, zero=True)
     u, ts, ts_old = buf(ld, zero=True), buf(ld, zero=True), buf(ld, zero=True)
     a, v = buf(B), buf(q)
@@ -412,8 +415,10 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 timed("xw", lambda: call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit,
                                          ptr(Tnum), ptr(Tden), ld, nan, done_p, st))
                 call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
-                     nparts, ptr(red), nan, done_p, st)
-                allreduce_(red, group)
+                     nparts, ptr(red_local), nan, done_p, st)
+                if group is not None:
+                    red.copy_(red_local)
+                    allreduce_(red, group)
                 call("mbpls_nipals_epilogue_f64", C.byref(epi), st)
                 launched += 1
             ctrl_h.copy_(ctrl, non_blocking=True)

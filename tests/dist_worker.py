@@ -1,0 +1,81 @@
+"""Worker for the multi-process tests: launched by torch.distributed.run (see test_gpu_multi.py /
+test_dist_host_logic.py).  argv[1] = 'nccl' (one GPU per rank) or 'gloo' (CPU, host logic only)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def gpu_checks(group, rank, world, dev):
+    from helpers import assert_trips, compare, snapshot_model
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    from oracle.cases import latent_blocks
+    for nan_frac, n in ((0.0, 400), (0.08, 260), (0.0, 2300)):
+        sizes = (300, 50, 450)  # uneven: shard boundaries cut through blocks, some ranks miss a block
+        X, Y = latent_blocks(n, sizes, 3, 4, seed=5 + n, nan_frac=nan_frac)
+        Xt, Yt = latent_blocks(13, sizes, 3, 4, seed=6, nan_frac=nan_frac)
+        kw = dict(n_components=4, sparse_data=nan_frac > 0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = OracleMBPLS(**kw).fit([x.copy() for x in X], Y.copy())
+            m = MBPLS(**kw).set_runtime(group=group, device=dev)
+            m.fit([x.copy() for x in X], Y.copy())
+        ref, ours = snapshot_model(o, Xt, Yt), snapshot_model(m, Xt, Yt)
+        worst = compare(ours, ref, 1e-8, f"rank {rank} nan={nan_frac} n={n}")
+        assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, 1e-14, f"rank {rank}")
+        # pre-sharded input: every rank passes only its own column ranges
+        from mbpls_b200.engine import ShardMap
+        sh = ShardMap.build(sizes, rank, world)
+        local = [X[b][:, c0:c1].copy() for b, (c0, c1) in enumerate(sh.local_ranges)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m2 = MBPLS(**kw).set_runtime(group=group, device=dev, global_sizes=list(sizes))
+            m2.fit(local, Y.copy())
+        assert np.allclose(m2.beta_, m.beta_, rtol=1e-11, atol=1e-14), "pre-sharded fit differs"
+        print(f"rank {rank}: world={world} nan={nan_frac} n={n} trips={m.n_iter_} worst={worst}", flush=True)
+
+
+def host_checks(group, rank, world):
+    from mbpls_b200.engine import ShardMap
+    from mbpls_b200.mbpls import MBPLS
+    sizes = [7, 1, 12, 5]
+    sh = ShardMap.build(sizes, rank, world)
+    # every global feature is owned exactly once
+    own = torch.zeros(sum(sizes), dtype=torch.int32)
+    own[sh.lo:sh.hi] += 1
+    dist.all_reduce(own, group=group)
+    assert bool((own == 1).all())
+    assert sh.block_off[-1] == sh.hi - sh.lo
+    # gather of a K x p_local tensor reproduces the global matrix on every rank
+    full = torch.arange(3 * sum(sizes), dtype=torch.float64).view(3, -1)
+    m = MBPLS().set_runtime(group=group)
+    got = m._gather_features(full[:, sh.lo:sh.hi].contiguous(), sh)
+    assert np.array_equal(got, full.numpy())
+    print(f"rank {rank}: host logic ok", flush=True)
+
+
+def main():
+    backend = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        gpu_checks(dist.group.WORLD, rank, world, dev)
+    else:
+        dist.init_process_group("gloo")
+        host_checks(dist.group.WORLD, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
