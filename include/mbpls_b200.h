@@ -158,6 +158,32 @@ int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, 
 int mbpls_rows_sumsq_f64(const double* M, long ld, int rows, int n, double* out, void* stream);
 int mbpls_rows_scale_f64(double* M, long ld, int rows, int n, const double* scale, int divide, void* stream);
 
+/* ---- SIMPLS / UNIPALS / KERNEL building blocks (mbpls.py:384-807, :995-1048) ------------------------ */
+/* out[c][j] = sum_i nan0(Xt[j][i]) * M[c][i]: X'Y (:396,:587,:998), X'U (:731), X'Ts (:734) */
+int mbpls_xt_multi_f64(const double* Xt, long ld, int n, int p, const double* M, long ldm, int C, double* out, long ldo,
+                       void* stream);
+/* out[j] = base[j] - sum_k V[k][j]*coef[k]: SIMPLS orthogonalisation (:1016-1017) */
+int mbpls_lincomb_sub_f64(double* out, const double* base, const double* V, long ldv, int K, const double* coef, int len,
+                          void* stream);
+/* t <- t - mean(t) (if center); *nrm_out = ||t||; t <- t/||t|| (if normalize)  (:1007-1009, :417, :424) */
+int mbpls_center_normalize_f64(double* t, int n, int center, int normalize, double* nrm_out, void* stream);
+/* out[b] = ||w_b||^2 and out[j] = w[j]/sqrt(a[block(j)]): block weights / importances (:405-408, :605-609, :746-750) */
+int mbpls_block_sumsq_f64(const double* w, const int* off, int B, double* out, void* stream);
+int mbpls_scale_by_block_f64(const double* w, const int* off, int B, const double* a, double* out, int p, void* stream);
+/* FP64 tensor-core (DMMA m8n8k4) cross product with deterministic split-K:
+ * kmajor=1: C = A B' (A: M x Kdim, B: N x Kdim)  -> X'X from the feature-major matrix (:586)
+ * kmajor=0: C = A' B (A: Kdim x M, B: Kdim x N)  -> X X' from the feature-major matrix (:704)
+ * Cpart: splits x M x ldc partials (splits = mbpls_crossprod_splits); sum them with mbpls_reduce_chunks_f64. */
+int mbpls_crossprod_splits(int M, int N, long Kdim);
+int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, int M, int N, long Kdim, int kmajor, int splits,
+                        double* Cpart, long ldc, void* stream);
+/* y = A x for a dense m x ncols matrix (VAR w :595,:599; AS_Y ts :718) */
+int mbpls_dense_gemv_f64(const double* A, long lda, int m, int ncols, const double* x, double* y, void* stream);
+/* A += al*x y' + be*y x' + ga*x x' with al,be (ga) optionally multiplied by scal[alpha_from] (scal[gamma_from]):
+ * the rank-1/2 forms of the sandwich deflations D'VAR D (:632) and D AS_X D (:723) */
+int mbpls_dense_rank2_f64(double* A, long lda, int m, int ncols, const double* x, const double* y, const double* scal,
+                          double alpha, double beta, double gamma, int alpha_from, int gamma_from, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

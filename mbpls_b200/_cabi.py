@@ -76,11 +76,20 @@ SIGNATURES = {
     "mbpls_rank1_update_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_rows_sumsq_f64": [_p, _l, _i, _i, _p, _p],
     "mbpls_rows_scale_f64": [_p, _l, _i, _i, _p, _i, _p],
+    "mbpls_xt_multi_f64": [_p, _l, _i, _i, _p, _l, _i, _p, _l, _p],
+    "mbpls_lincomb_sub_f64": [_p, _p, _p, _l, _i, _p, _i, _p],
+    "mbpls_center_normalize_f64": [_p, _i, _i, _i, _p, _p],
+    "mbpls_block_sumsq_f64": [_p, _p, _i, _p, _p],
+    "mbpls_scale_by_block_f64": [_p, _p, _i, _p, _p, _i, _p],
+    "mbpls_crossprod_splits": [_i, _i, _l],
+    "mbpls_crossprod_f64": [_p, _l, _p, _l, _i, _i, _l, _i, _i, _p, _l, _p],
+    "mbpls_dense_gemv_f64": [_p, _l, _i, _i, _p, _p, _p],
+    "mbpls_dense_rank2_f64": [_p, _l, _i, _i, _p, _p, _p, _d, _d, _d, _i, _i, _p],
 }
 
 # functions whose int return value is a plain number, not a status
 _PLAIN = {"mbpls_abi_version", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
-          "mbpls_xw_ctas_per_sm"}
+          "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits"}
 
 
 class MbplsCudaError(RuntimeError):

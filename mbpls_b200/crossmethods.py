@@ -1,6 +1,448 @@
-"""KERNEL / UNIPALS / SIMPLS fit bodies (mbpls/mbpls.py:384-807, :995-1048) -- filled in below."""
+"""SIMPLS / UNIPALS / KERNEL fit bodies (reference: mbpls/mbpls.py:995-1048, :384-574, :576-807) on the
+feature-major device matrix.
+
+Algebra that replaces the reference's dense p x p / n x n work:
+* ``S = X'YY'X = C C'`` with ``C = X'Y`` (p x q): its top left singular vector is ``C c / |C c|`` with ``c`` the top
+  eigenvector of the q x q matrix ``C'C``  (:396-400, :584-592).
+* ``S = XX'YY' = A Y'`` with ``A = X (X'Y)`` (n x q): the top left singular vector of ``A Y'`` is ``A c / |A c|`` with
+  ``c = L z``, ``Y'Y = L L'``, ``z`` the top eigenvector of ``L' (A'A) L``  (:489-493, :704-715).
+* KERNEL sandwich deflations (:630-633, :722-725) are rank-1 / rank-2 updates because ``w'VAR = den * p`` and
+  ``D = I - ts ts'`` is symmetric.
+Only q x q / K x K problems are solved on the host; every O(n p) or larger step is a kernel.
+"""
 from __future__ import annotations
 
+import ctypes as C
+import warnings
 
+import numpy as np
+import torch
+
+from . import engine as E
+from .engine import F64, call, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers
+# ------------------------------------------------------------------------------------------------
+def xt_multi(Xt, n, M):
+    """(C x ld) right-hand sides -> C x p_local with out[c][j] = x_j . M[c]."""
+    p, ld = Xt.shape
+    Cc = M.shape[0]
+    out = torch.zeros((Cc, max(p, 1)), dtype=F64, device=Xt.device)
+    if p > 0:
+        call("mbpls_xt_multi_f64", ptr(Xt), ld, n, p, ptr(M), M.stride(0), Cc, ptr(out), out.stride(0), stream_ptr(Xt.device))
+    return out[:, :p]
+
+
+def xt_vec(Xt, n, u, boff_dev, B, uu=None):
+    """x_j . u (/ uu) for every local feature -> p_local vector (the NIPALS xtu kernel)."""
+    p, ld = Xt.shape
+    w = torch.zeros(max(p, 1), dtype=F64, device=Xt.device)
+    call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(uu), ptr(boff_dev), B, ptr(w), None, 0, None,
+         stream_ptr(Xt.device))
+    return w[:p]
+
+
+def lincomb_sub(base, V, K, coef, length):
+    out = base.clone()
+    call("mbpls_lincomb_sub_f64", ptr(out), ptr(base), ptr(V), V.stride(0) if K > 0 else 0, K, ptr(coef), length,
+         stream_ptr(base.device))
+    return out
+
+
+def normalize_(t, n, center=False):
+    nrm = torch.zeros(1, dtype=F64, device=t.device)
+    call("mbpls_center_normalize_f64", ptr(t), n, 1 if center else 0, 1, ptr(nrm), stream_ptr(t.device))
+    return nrm
+
+
+def scale_rows_(M, n, scale, divide):
+    rows = M.shape[0] if M.dim() == 2 else 1
+    call("mbpls_rows_scale_f64", ptr(M), M.stride(0) if M.dim() == 2 else n, rows, n, ptr(scale), 1 if divide else 0,
+         stream_ptr(M.device))
+
+
+def normalize_over_features_(w, p, group):
+    """w <- w / |w| with the norm taken over the *global* feature axis."""
+    nrm = torch.sqrt(E.rows_sumsq(w.view(1, -1), p, group))
+    if p > 0:
+        scale_rows_(w.view(1, -1), p, nrm, True)
+    return nrm
+
+
+def block_sumsq(w, boff_dev, B, group):
+    out = torch.zeros(B, dtype=F64, device=w.device)
+    call("mbpls_block_sumsq_f64", ptr(w), ptr(boff_dev), B, ptr(out), stream_ptr(w.device))
+    E.allreduce_(out, group)
+    return out
+
+
+def scale_by_block(w, boff_dev, B, a, p):
+    out = torch.empty_like(w)
+    call("mbpls_scale_by_block_f64", ptr(w), ptr(boff_dev), B, ptr(a), ptr(out), p, stream_ptr(w.device))
+    return out
+
+
+def rank1_update_(Xt, n, ts, pvec):
+    p, ld = Xt.shape
+    call("mbpls_rank1_update_f64", ptr(Xt), ld, n, p, ptr(ts), ptr(pvec), stream_ptr(Xt.device))
+
+
+class BlockProducts:
+    """red[b][i] = sum_{j in block b} w[j] x_ij for all blocks in one pass (the NIPALS xw + reduce kernels)."""
+
+    def __init__(self, Xt, n, block_off, group):
+        dev = Xt.device
+        self.Xt, self.n, self.group = Xt, n, group
+        self.B = len(block_off) - 1
+        f0, f1, bso = E.make_splits(block_off, n, E.sm_count(dev))
+        self.ns = len(f0)
+        self.sf0, self.sf1, self.sbso = E._i32(f0, dev), E._i32(f1, dev), E._i32(bso, dev)
+        ld = Xt.shape[1]
+        self.Tnum = torch.zeros((max(self.ns, 1), ld), dtype=F64, device=dev)
+        self.dummy = torch.zeros(max(self.B, 1), dtype=F64, device=dev)
+
+    def __call__(self, w):
+        Xt, n, B = self.Xt, self.n, self.B
+        ld = Xt.shape[1]
+        st = stream_ptr(Xt.device)
+        red = torch.zeros(B * ld + B, dtype=F64, device=Xt.device)
+        call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(self.sf0), ptr(self.sf1), self.ns, ptr(self.Tnum), None, ld, 0,
+             None, st)
+        call("mbpls_nipals_reduce_partials_f64", ptr(self.Tnum), None, ld, n, B, ptr(self.sbso), ptr(self.dummy), 0, ptr(red),
+             0, None, st)
+        E.allreduce_(red, self.group)
+        return red[:B * ld].view(B, ld)
+
+
+def sum_rows(M, length):
+    """out[i] = sum_b M[b][i] (fixed order)."""
+    out = torch.zeros(M.shape[1], dtype=F64, device=M.device)
+    Mc = M.contiguous()
+    call("mbpls_reduce_chunks_f64", ptr(Mc), Mc.shape[0], Mc.shape[1], ptr(out), stream_ptr(M.device))
+    return out
+
+
+def top_eigvec(M: np.ndarray) -> np.ndarray:
+    M = 0.5 * (M + M.T)
+    w, V = np.linalg.eigh(M)
+    return V[:, -1]
+
+
+def top_left_sv_of_product(G: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """c such that A c is the top left singular vector of A B' given G = B'B and H = A'A (both q x q)."""
+    G = 0.5 * (G + G.T)
+    lam, Q = np.linalg.eigh(G)
+    lam = np.clip(lam, 0.0, None)
+    L = Q * np.sqrt(lam)  # G = L L'
+    z = top_eigvec(L.T @ H @ L)
+    return L @ z
+
+
+def dev_from(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+def _bip_corrected(a, sizes):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    if a.size == 1:
+        return np.array([1.0])
+    sizes = np.asarray(sizes, dtype=np.float64)
+    corrected = a * (1.0 - sizes / sizes.sum())
+    return corrected / corrected.sum()
+
+
+def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=None):
+    """Register lazily materialised attributes shared by the three methods."""
+    B = len(shard.sizes)
+    bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
+
+    def split_T(full):
+        return [np.ascontiguousarray(full[:, bounds[b]:bounds[b + 1]].T) for b in range(B)]
+
+    lazy = {
+        "Ts_": lambda: np.ascontiguousarray(Ts[:, :n].cpu().numpy().T),
+        "U_": lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T) if U is not None else np.empty((n, 0)),
+        "V_": lambda: np.ascontiguousarray(V.cpu().numpy().T),
+        "P_": lambda: split_T(model._gather_features(P, shard)),
+        "R_": lambda: np.ascontiguousarray(model._gather_features(R, shard).T),
+        "beta_": lambda: np.ascontiguousarray(model._gather_features(beta, shard).T),
+    }
+    if Wb is not None:
+        lazy["W_"] = lambda: split_T(model._gather_features(Wb, shard))
+    if Tb is not None:
+        lazy["T_"] = lambda: [np.ascontiguousarray(Tb[b, :, :n].cpu().numpy().T) for b in range(B)]
+    if lazy_extra:
+        lazy.update(lazy_extra)
+    model.__dict__["_lazy"] = lazy
+    model.__dict__["_dev"] = dict(shard=shard, R=R, beta=beta, P=P, V=V, **({"W": Wb} if Wb is not None else {}))
+
+
+# ------------------------------------------------------------------------------------------------
 def fit(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
-    raise NotImplementedError(f"method {model.method!r} is not implemented yet in mbpls_b200")
+    method = model.method
+    if method == 'SIMPLS':
+        return _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device)
+    if method == 'UNIPALS':
+        return _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
+    if method == 'KERNEL':
+        return _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
+    raise NameError('Method you called is unknown')
+
+
+# ---- SIMPLS (mbpls.py:995-1048) ------------------------------------------------------------------
+def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
+    warnings.warn("Method 'SIMPLS' does not calculate A_ and T_!")  # :996
+    K, B = int(model.n_components), len(shard.sizes)
+    p, ld = Xt.shape
+    St = xt_multi(Xt, n, Yt).contiguous()  # q x p : S = X'Y (:998)
+    if p == 0:
+        St = torch.zeros((q, 1), dtype=F64, device=device)[:, :0]
+    R, Tm, P, Q, U, V, W = (torch.zeros((K, max(p, 1)), dtype=F64, device=device), torch.zeros((K, ld), dtype=F64, device=device),
+                           torch.zeros((K, max(p, 1)), dtype=F64, device=device), torch.zeros((K, q), dtype=F64, device=device),
+                           torch.zeros((K, ld), dtype=F64, device=device), torch.zeros((K, max(p, 1)), dtype=F64, device=device),
+                           torch.zeros((K, max(p, 1)), dtype=F64, device=device))
+    ldS = St.stride(0) if p > 0 else 1
+    for k in range(K):
+        StS = E.gram(St, St, p, group).cpu().numpy()  # S'S, q x q (:1001)
+        qv = top_eigvec(StS)
+        r = E.right_multiply(St, p, None, dev_from(qv.reshape(q, 1), device))[0].contiguous()  # r = S q (:1004)
+        W[k, :p] = r
+        t = E.skinny_gemm(Xt, n, r.view(1, -1), shard.block_off, group)[0].contiguous()  # t = X r (:1006)
+        normt = normalize_(t, n, center=True)  # :1007-1009
+        if p > 0:
+            scale_rows_(r.view(1, -1), p, normt, True)  # :1010
+        pv = xt_vec(Xt, n, t, boff_dev, B)  # p = X't (:1011)
+        qk = E.gram(Yt, t.view(1, -1), n)[:, 0].contiguous()  # q = Y't (:1012)
+        u = E.skinny_gemm(Yt, n, qk.view(1, -1), [0, q])[0].contiguous()  # u = Y q (:1013)
+        v = pv.clone() if p > 0 else pv
+        if k > 0:  # :1015-1017
+            cv = E.gram(V[:k, :p], pv.view(1, -1), p, group)[:, 0].contiguous()
+            if p > 0:
+                v = lincomb_sub(pv.contiguous(), V, k, cv, p)
+            cu = E.gram(Tm[:k], u.view(1, -1), n)[:, 0].contiguous()
+            u = lincomb_sub(u, Tm, k, cu, n)
+        normalize_over_features_(v, p, group)  # :1018
+        vS = E.gram(St, v.view(1, -1), p, group)[:, 0].contiguous()  # v'S (q)
+        if p > 0:
+            call("mbpls_rank1_update_f64", ptr(St), ldS, p, q, ptr(v), ptr(vS), stream_ptr(device))  # S -= v v'S (:1019)
+        normalize_(u, n)
+        R[k, :p], Tm[k], P[k, :p], Q[k], U[k], V[k, :p] = r, t, pv, qk, u, v
+    R, P, W = R[:, :p], P[:, :p], W[:, :p]
+    beta = E.right_multiply(R, p, None, Q.contiguous())  # beta = R Q' (:1044)
+    model.explained_var_x_, model.explained_var_y_ = [], []
+    model.explained_var_xblocks_ = np.empty((B, 0))
+    model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
+    model.W_concat_ = np.empty((shard.p_global, 0))
+    _finish_common(model, shard, n, q, R, beta, P, Tm, U, Q, None, None,
+                   {"W_": lambda: np.ascontiguousarray(model._gather_features(W, shard).T)})
+
+
+# ---- UNIPALS (mbpls.py:384-574) ------------------------------------------------------------------
+def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
+    K, B = int(model.n_components), len(shard.sizes)
+    p, ld = Xt.shape
+    pg = shard.p_global
+    blockprod = BlockProducts(Xt, n, shard.block_off, group)
+    if zss is None:
+        zss = E.feature_sumsq(Xt, n)
+    varxb = model._block_sums(zss, boff_dev, B, group)
+    vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
+    Wc = torch.zeros((K, max(p, 1)), dtype=F64, device=device)   # eigenv columns ("weights")
+    Wb = torch.zeros((K, max(p, 1)), dtype=F64, device=device)   # block-normalised
+    P = torch.zeros((K, max(p, 1)), dtype=F64, device=device)
+    Ts, U = torch.zeros((K, ld), dtype=F64, device=device), torch.zeros((K, ld), dtype=F64, device=device)
+    V = torch.zeros((K, q), dtype=F64, device=device)
+    Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
+    A = np.zeros((B, K))
+    evx, evy, evxb = [], [], np.zeros((B, K))
+    GY = E.gram(Yt, Yt, n).cpu().numpy()
+    for k in range(K):
+        Ct = xt_multi(Xt, n, Yt).contiguous()  # (X'Y)' from the *deflated* X (:396 / :489)
+        if n >= pg:  # :388-424
+            c = top_eigvec(E.gram(Ct, Ct, p, group).cpu().numpy())
+            w = E.right_multiply(Ct, p, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            normalize_over_features_(w, p, group)
+            raw = blockprod(w)  # X_b w (un-normalised block part)
+            ts = sum_rows(raw, ld)  # X w (:416)
+            normalize_(ts, n)
+            tt = E.rows_sumsq(ts.view(1, -1), n)
+            v = E.gram(Yt, ts.view(1, -1), n)[:, 0].contiguous()
+            scale_rows_(v.view(1, -1), q, tt, True)  # v = Y'ts / ts'ts (:420)
+            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # :423-424
+            normalize_(u, n)
+        else:  # :481-517
+            At = E.skinny_gemm(Xt, n, Ct, shard.block_off, group)  # (X X'Y)' : q x ld
+            H = E.gram(At, At, n).cpu().numpy()
+            c = top_left_sv_of_product(GY, H)
+            ts = E.right_multiply(At, ld, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            normalize_(ts, n)
+            tt = E.rows_sumsq(ts.view(1, -1), n)
+            v = E.gram(Yt, ts.view(1, -1), n)[:, 0].contiguous()
+            scale_rows_(v.view(1, -1), q, tt, True)
+            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()
+            normalize_(u, n)
+            w = xt_vec(Xt, n, u, boff_dev, B).contiguous()  # :503-504
+            normalize_over_features_(w, p, group)
+            raw = blockprod(w)
+        a = block_sumsq(w, boff_dev, B, group)  # :405-408
+        wb = scale_by_block(w, boff_dev, B, a, p)
+        tb = raw.clone()
+        scale_rows_(tb, n, torch.sqrt(a), True)  # t_b = X_b w_b (:410-413)
+        pv = xt_vec(Xt, n, ts, boff_dev, B, uu=tt)  # p = X'ts / ts'ts (:427)
+        pssb = block_sumsq(pv, boff_dev, B, group).cpu().numpy()
+        ttf = float(tt.item())
+        evx.append(ttf * pssb.sum() / varxb.sum())
+        evxb[:, k] = ttf * pssb / varxb
+        evy.append(ttf * float((v * v).sum().item()) / vary)
+        rank1_update_(Xt, n, ts, pv)  # X <- X - ts p' (:443)
+        A[:, k] = a.cpu().numpy()
+        Wc[k, :p], Wb[k, :p], P[k, :p], Ts[k], U[k], V[k] = w, wb, pv, ts, u, v
+        Tb[:, k, :] = tb
+    Wc, Wb, P = Wc[:, :p], Wb[:, :p], P[:, :p]
+    PtW = E.gram(P, Wc, p, group)
+    M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+    R = E.right_multiply(Wc, p, None, M)  # :476
+    beta = E.right_multiply(R, p, None, V.contiguous())  # :477
+    model.A_ = A
+    model.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
+    model.explained_var_x_, model.explained_var_y_, model.explained_var_xblocks_ = evx, evy, evxb
+    model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
+    model.W_concat_ = np.empty((pg, 0))
+    _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb)
+
+
+# ---- KERNEL (mbpls.py:576-807) -------------------------------------------------------------------
+def crossprod(A, Bm, M, N, Kdim, kmajor, ldc):
+    dev = A.device
+    splits = call("mbpls_crossprod_splits", M, N, Kdim)
+    part = torch.zeros((splits, M * ldc), dtype=F64, device=dev)
+    call("mbpls_crossprod_f64", ptr(A), A.stride(0), ptr(Bm), Bm.stride(0), M, N, Kdim, 1 if kmajor else 0, splits, ptr(part),
+         ldc, stream_ptr(dev))
+    out = torch.zeros((M, ldc), dtype=F64, device=dev)
+    call("mbpls_reduce_chunks_f64", ptr(part), splits, M * ldc, ptr(out), stream_ptr(dev))
+    return out
+
+
+def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
+    if group is not None:
+        raise NotImplementedError("method='KERNEL' is single-GPU in this round (row-sharded variant: SURVEY.md 8e)")
+    K, B = int(model.n_components), len(shard.sizes)
+    p, ld = Xt.shape
+    st = stream_ptr(device)
+    calc_all = bool(model.calc_all)
+    V = torch.zeros((K, q), dtype=F64, device=device)
+    P = torch.zeros((K, p), dtype=F64, device=device)
+    Wc = torch.zeros((K, p), dtype=F64, device=device)
+    Wb = torch.zeros((K, p), dtype=F64, device=device)
+    U = torch.zeros((K, ld), dtype=F64, device=device)
+    A = np.zeros((B, K))
+    if n >= p:  # Lindgren kernel (:580-650)
+        COVt = xt_multi(Xt, n, Yt).contiguous()  # COVAR' : q x p (:587)
+        ldv = (p + 15) // 16 * 16
+        VAR = crossprod(Xt, Xt, p, p, n, True, ldv)  # X'X on the FP64 tensor cores (:586)
+        scal = torch.zeros(4, dtype=F64, device=device)
+        for k in range(K):
+            c = top_eigvec(E.gram(COVt, COVt, p).cpu().numpy())  # S = COVAR COVAR' (:584, :631)
+            w = E.right_multiply(COVt, p, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            normalize_over_features_(w, p, None)
+            Vw = torch.zeros(p, dtype=F64, device=device)
+            call("mbpls_dense_gemv_f64", ptr(VAR), ldv, p, p, ptr(w), ptr(Vw), st)
+            den = E.gram(w.view(1, -1), Vw.view(1, -1), p)  # w'VAR w (:595)
+            scal[0:1] = den.view(-1)
+            wC = E.gram(COVt, w.view(1, -1), p)[:, 0].contiguous()  # w'COVAR  (= den * v)
+            v, pv = wC.clone(), Vw.clone()
+            scale_rows_(v.view(1, -1), q, scal, True)  # v = w'COVAR / den (:596)
+            scale_rows_(pv.view(1, -1), p, scal, True)  # p = w'VAR / den (:599)
+            if calc_all:  # :601-627
+                a = block_sumsq(w, boff_dev, B, None)
+                Wb[k] = scale_by_block(w, boff_dev, B, a, p)
+                A[:, k] = a.cpu().numpy()
+                vv = float((v * v).sum().item())
+                u = E.skinny_gemm(Yt, n, (v / vv).contiguous().view(1, -1), [0, q])[0].contiguous()
+                normalize_(u, n)
+                U[k] = u
+            # COVAR <- D'COVAR, VAR <- D'VAR D = VAR - den p'p  (:630-633)
+            call("mbpls_rank1_update_f64", ptr(COVt), COVt.stride(0), p, q, ptr(pv), ptr(wC), st)
+            call("mbpls_dense_rank2_f64", ptr(VAR), ldv, p, p, ptr(pv), ptr(pv), ptr(scal), 0.0, 0.0, -1.0, -1, 0, st)
+            V[k], P[k], Wc[k] = v, pv, w
+        PtW = E.gram(P, Wc, p)
+        M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+        R = E.right_multiply(Wc, p, None, M)  # :642
+        beta = E.right_multiply(R, p, None, V.contiguous())  # :643
+        Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # Ts = X R (:644)
+        nrm = torch.sqrt(E.rows_sumsq(Ts, n))  # :646-650
+        scale_rows_(V, q, nrm, False)
+        scale_rows_(P, p, nrm, False)
+        scale_rows_(Ts, n, nrm, True)
+    else:  # Rannar kernel (:694-738)
+        AX = crossprod(Xt, Xt, n, n, p, False, ld)  # X X' on the FP64 tensor cores (:704)
+        Yc = Yt.clone()
+        Ts = torch.zeros((K, ld), dtype=F64, device=device)
+        scal = torch.zeros(4, dtype=F64, device=device)
+        for k in range(K):
+            At = E.skinny_gemm(AX[:, :], n, Yc, [0, n])  # (AS_X Y)' : q x ld;  S = AS_X AS_Y = (AS_X Y) Y' (:707, :725)
+            G = E.gram(Yc, Yc, n).cpu().numpy()
+            H = E.gram(At, At, n).cpu().numpy()
+            c = top_left_sv_of_product(G, H)
+            ts = E.right_multiply(At, ld, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            ts[n:] = 0.0
+            normalize_(ts, n)  # :713
+            yt = E.gram(Yc, ts.view(1, -1), n)[:, 0].contiguous()  # Y'ts
+            u = E.skinny_gemm(Yc, n, yt.view(1, -1), [0, q])[0].contiguous()  # AS_Y ts (:718)
+            normalize_(u, n)
+            kv = torch.zeros(ld, dtype=F64, device=device)
+            call("mbpls_dense_gemv_f64", ptr(AX), ld, n, n, ptr(ts), ptr(kv), st)
+            scal[0:1] = E.gram(ts.view(1, -1), kv.view(1, -1), n).view(-1)  # ts' AS_X ts
+            # AS_X <- D AS_X D,  Y <- D Y  with D = I - ts ts' (:722-724)
+            call("mbpls_dense_rank2_f64", ptr(AX), ld, n, n, ptr(ts), ptr(kv), ptr(scal), -1.0, -1.0, 1.0, -1, 0, st)
+            call("mbpls_rank1_update_f64", ptr(Yc), ld, n, q, ptr(ts), ptr(yt), st)
+            U[k], Ts[k] = u, ts
+        Wc = xt_multi(Xt, n, U).contiguous()  # X'U (:731)
+        wn = torch.sqrt(E.rows_sumsq(Wc, p))
+        scale_rows_(Wc, p, wn, True)  # :733
+        Gt = np.linalg.pinv(E.gram(Ts, Ts, n).cpu().numpy())
+        XtTs = xt_multi(Xt, n, Ts).contiguous()
+        P = E.right_multiply(XtTs, p, None, dev_from(Gt, device)).contiguous()  # :734
+        V = dev_from((E.gram(Yt, Ts, n).cpu().numpy() @ Gt).T, device)  # :735  (K x q)
+        PtW = E.gram(P, Wc, p)
+        M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+        R = E.right_multiply(Wc, p, None, M)  # :737
+        beta = E.right_multiply(R, p, None, V.contiguous())  # :738
+    Tb = None
+    evx, evy, evxb = [], [], np.empty((B, 0))
+    if calc_all:  # :653-689 / :740-802
+        if zss is None:
+            zss = E.feature_sumsq(Xt, n)
+        varxb = model._block_sums(zss, boff_dev, B, None)
+        vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
+        blockprod = BlockProducts(Xt, n, shard.block_off, None)
+        Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
+        evxb = np.zeros((B, K))
+        for k in range(K):
+            if n < p:
+                a = block_sumsq(Wc[k].contiguous(), boff_dev, B, None)
+                Wb[k] = scale_by_block(Wc[k].contiguous(), boff_dev, B, a, p)
+                A[:, k] = a.cpu().numpy()
+            Tb[:, k, :] = blockprod(Wb[k].contiguous())
+            tt = float(E.rows_sumsq(Ts[k:k + 1], n).item())
+            pssb = block_sumsq(P[k].contiguous(), boff_dev, B, None).cpu().numpy()
+            evx.append(tt * pssb.sum() / varxb.sum())
+            evxb[:, k] = tt * pssb / varxb
+            evy.append(tt * float((V[k] * V[k]).sum().item()) / vary)
+            rank1_update_(Xt, n, Ts[k].contiguous(), P[k].contiguous())
+        model.A_ = A
+        model.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
+    else:
+        model.A_ = np.empty((B, 0))
+        model.A_corrected_ = np.empty((B, 0))
+    model.explained_var_x_, model.explained_var_y_, model.explained_var_xblocks_ = evx, evy, evxb
+    model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
+    Wc_keep = Wc
+    extra = {"W_concat_": lambda: np.ascontiguousarray(model._gather_features(Wc_keep, shard).T)}
+    if not calc_all:
+        extra["W_"] = lambda: [np.empty((s, 0)) for s in shard.sizes]
+        extra["T_"] = lambda: [np.empty((n, 0)) for _ in shard.sizes]
+        extra["U_"] = (lambda: np.empty((n, 0))) if n >= p else (lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T))
+    _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb if calc_all else None, Tb, extra)

@@ -1,0 +1,373 @@
+// Building blocks of the SIMPLS / UNIPALS / KERNEL fit bodies (mbpls/mbpls.py:384-807, :995-1048) on the
+// feature-major layout: multi-right-hand-side X'M, small vector algebra with fixed-order reductions, and
+// the FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) cross-product kernel for X'X / XX'.
+#include "launch.cuh"
+#include "../../include/mbpls_b200.h"
+
+using namespace mbpls;
+
+// ------------------------------------------------------------------------------------------
+// C[c][j] = sum_i Xt[j][i] * M[c][i]     (X'Y :998,:587; X'U :731; X'Ts :734; per-component X'Y of UNIPALS :396)
+// One warp owns F=4 features and NC<=8 right-hand sides at a time: per step 4 X loads + NC M loads feed
+// 8*NC FMAs, so the M traffic through L1 is at most 2x the HBM stream.  NaN entries of X count as zero.
+// ------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256)
+xt_multi_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ M, long ldm, int c0, int C,
+                double* __restrict__ out, long ldo) {
+  constexpr int F = 4;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nc = min(NC, C - c0);
+  const int n2 = n >> 1;
+  for (int j0 = gw * F; j0 < p; j0 += nwarps * F) {
+    double acc[F][NC];
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[f][c] = 0.0;
+    const double2* xr[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) xr[f] = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(min(j0 + f, p - 1)) * ld);
+    for (int i = lane; i < n2; i += 32) {
+      double2 x[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        x[f] = ld_stream(xr[f] + i);
+        if (isnan(x[f].x)) x[f].x = 0.0;
+        if (isnan(x[f].y)) x[f].y = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (c < nc) {
+          const double2 m = *reinterpret_cast<const double2*>(M + static_cast<size_t>(c0 + c) * ldm + 2 * i);
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            acc[f][c] = fma(x[f].x, m.x, acc[f][c]);
+            acc[f][c] = fma(x[f].y, m.y, acc[f][c]);
+          }
+        }
+      }
+    }
+    if ((n & 1) && lane == 0) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        double xv = Xt[static_cast<size_t>(min(j0 + f, p - 1)) * ld + n - 1];
+        if (isnan(xv)) xv = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c < nc) acc[f][c] = fma(xv, M[static_cast<size_t>(c0 + c) * ldm + n - 1], acc[f][c]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double s = warp_sum(acc[f][c]);
+        if (lane == 0 && c < nc && j0 + f < p) out[static_cast<size_t>(c0 + c) * ldo + j0 + f] = s;
+      }
+  }
+}
+
+// out[j] = base[j] - sum_k V[k][j] * coef[k]      (SIMPLS Gram-Schmidt steps, :1016-1017)
+__global__ void __launch_bounds__(256)
+lincomb_sub_kernel(double* __restrict__ out, const double* __restrict__ base, const double* __restrict__ V, long ldv, int K,
+                   const double* __restrict__ coef, int len) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s = fma(V[static_cast<size_t>(k) * ldv + j], coef[k], s);
+    out[j] = base[j] - s;
+  }
+}
+
+// t <- t - mean(t) (optional); nrm = ||t||; t <- t / nrm (optional).  Single CTA, fixed-order sums.  (:1007-1009)
+__global__ void __launch_bounds__(1024)
+center_normalize_kernel(double* __restrict__ t, int n, int center, int normalize, double* __restrict__ nrm_out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  if (center) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += t[i];
+    s = block_sum1(s, scratch);
+  }
+  const double mean = center ? s / n : 0.0;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = t[i] - mean;
+    t[i] = v;
+    q = fma(v, v, q);
+  }
+  q = block_sum1(q, scratch);
+  const double nrm = sqrt(q);
+  if (normalize)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] = t[i] / nrm;
+  if (threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
+}
+
+// out[b] = sum_{j in block b} w[j]^2   (a_b = ||w_b||^2, :408,:512,:609,:750); one CTA per block
+__global__ void __launch_bounds__(256)
+block_sumsq_kernel(const double* __restrict__ w, const int* __restrict__ off, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int a = off[blockIdx.x], b = off[blockIdx.x + 1];
+  double s = 0.0;
+  for (int j = a + threadIdx.x; j < b; j += blockDim.x) s = fma(w[j], w[j], s);
+  s = block_sum1(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// out[j] = w[j] / sqrt(a[block(j)])   (w_b = partialloading / ||partialloading||, :407,:511,:607,:748)
+__global__ void __launch_bounds__(256)
+scale_by_block_kernel(const double* __restrict__ w, const int* __restrict__ off, int B, const double* __restrict__ a,
+                      double* __restrict__ out, int p) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x)
+    out[j] = w[j] / sqrt(a[block_of(off, B, j)]);
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 tensor-core cross product  C = op(A) . op(B)'  over the long dimension:
+//   KMAJOR = true : C[i][j] = sum_k A[i*lda + k] * B[j*ldb + k]   (X'X from the feature-major matrix, :586)
+//   KMAJOR = false: C[i][j] = sum_k A[k*lda + i] * B[k*ldb + j]   (XX' from the feature-major matrix, :704)
+// 128x128 CTA tile, 16-deep k slabs double-buffered through shared memory, 8 warps (2x4), each warp 64x32 =
+// 8x4 mma.sync.aligned.m8n8k4.f64 tiles (64 accumulator doubles per lane).  Split-K over gridDim.z with
+// per-split partial tiles reduced in fixed order by mbpls_reduce_chunks_f64 (deterministic).
+// ------------------------------------------------------------------------------------------
+#define XP_BM 128
+#define XP_BN 128
+#define XP_BK 16
+#define XP_LD 20  // padded k-stride of a smem row (20 = 4 mod 16 -> conflict-free 64-bit fragment loads)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool KMAJOR>
+__global__ void __launch_bounds__(256)
+crossprod_kernel(const double* __restrict__ A, long lda, const double* __restrict__ B, long ldb, int M, int N, long Kdim,
+                 long k_per_split, double* __restrict__ Cpart, long ldc) {
+  extern __shared__ __align__(16) double xp_smem[];
+  double (*As)[XP_BM * XP_LD] = reinterpret_cast<double (*)[XP_BM * XP_LD]>(xp_smem);
+  double (*Bs)[XP_BN * XP_LD] = reinterpret_cast<double (*)[XP_BN * XP_LD]>(xp_smem + 2 * XP_BM * XP_LD);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int m0 = blockIdx.y * XP_BM, n0 = blockIdx.x * XP_BN;
+  const long kb = static_cast<long>(blockIdx.z) * k_per_split;
+  const long ke = min(Kdim, kb + k_per_split);
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_tile = [&](int buf, long k0) {
+    // 128 rows x 16 k of A and of B -> smem [row][k] (k-stride XP_LD).  2048 elements each, 8 per thread.
+    if (KMAJOR) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {  // 16-byte loads along k
+        const int idx = tid + e * 256;       // 0..1023 double2 slots
+        const int row = idx >> 3, kk = (idx & 7) * 2;
+        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+        const long k = k0 + kk;
+        if (m0 + row < M) {
+          const double* pa = A + static_cast<size_t>(m0 + row) * lda + k;
+          if (k + 1 < ke) va = *reinterpret_cast<const double2*>(pa);
+          else if (k < ke) va.x = pa[0];
+        }
+        if (n0 + row < N) {
+          const double* pb = B + static_cast<size_t>(n0 + row) * ldb + k;
+          if (k + 1 < ke) vb = *reinterpret_cast<const double2*>(pb);
+          else if (k < ke) vb.x = pb[0];
+        }
+        As[buf][row * XP_LD + kk] = va.x;
+        As[buf][row * XP_LD + kk + 1] = va.y;
+        Bs[buf][row * XP_LD + kk] = vb.x;
+        Bs[buf][row * XP_LD + kk + 1] = vb.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // coalesced along the row (m / n) index
+        const int idx = tid + e * 256;       // 0..2047
+        const int kk = idx >> 7, row = idx & 127;
+        const long k = k0 + kk;
+        double va = 0.0, vb = 0.0;
+        if (k < ke) {
+          if (m0 + row < M) va = A[static_cast<size_t>(k) * lda + m0 + row];
+          if (n0 + row < N) vb = B[static_cast<size_t>(k) * ldb + n0 + row];
+        }
+        As[buf][row * XP_LD + kk] = va;
+        Bs[buf][row * XP_LD + kk] = vb;
+      }
+    }
+  };
+
+  int buf = 0;
+  if (kb < ke) load_tile(0, kb);
+  __syncthreads();
+  for (long k0 = kb; k0 < ke; k0 += XP_BK) {
+    if (k0 + XP_BK < ke) load_tile(buf ^ 1, k0 + XP_BK);
+    const double* as = As[buf] + (wm * 64 + (lane >> 2)) * XP_LD + (lane & 3);
+    const double* bs = Bs[buf] + (wn * 32 + (lane >> 2)) * XP_LD + (lane & 3);
+#pragma unroll
+    for (int ks = 0; ks < XP_BK; ks += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = as[i * 8 * XP_LD + ks];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[j * 8 * XP_LD + ks];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  double* Cp = Cpart + static_cast<size_t>(blockIdx.z) * M * ldc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm * 64 + i * 8 + (lane >> 2);
+      const int c = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+      if (r < M) {
+        if (c < N) Cp[static_cast<size_t>(r) * ldc + c] = acc[i][j][0];
+        if (c + 1 < N) Cp[static_cast<size_t>(r) * ldc + c + 1] = acc[i][j][1];
+      }
+    }
+}
+
+// y[i] = sum_j A[i*lda + j] * x[j]  for a dense (symmetric) m x m matrix: one warp per row  (VAR w, AS_X ts)
+__global__ void __launch_bounds__(256) dense_gemv_kernel(const double* __restrict__ A, long lda, int m, int ncols,
+                                                         const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = gw; i < m; i += nwarps) {
+    const double* a = A + static_cast<size_t>(i) * lda;
+    double s = 0.0;
+    for (int j = lane; j < ncols; j += 32) s = fma(a[j], x[j], s);
+    s = warp_sum(s);
+    if (lane == 0) y[i] = s;
+  }
+}
+
+// A[i][j] += alpha * x[i]*y[j] + beta * y[i]*x[j] + gamma * x[i]*x[j]   (rank-1 / rank-2 forms of the sandwich
+// deflations D'SD, D'VAR D (:630-633) and D AS D (:722-724))
+__global__ void __launch_bounds__(256)
+dense_rank2_kernel(double* __restrict__ A, long lda, int row0, int m, int ncols, const double* __restrict__ x,
+                   const double* __restrict__ y, const double* __restrict__ scal, double alpha, double beta, double gamma,
+                   int alpha_from, int gamma_from) {
+  const int i = row0 + blockIdx.y;
+  if (i >= m) return;
+  // coefficients may be multiplied by a device scalar (e.g. -den or ts'K ts)
+  const double al = alpha_from >= 0 ? alpha * scal[alpha_from] : alpha;
+  const double be = alpha_from >= 0 ? beta * scal[alpha_from] : beta;
+  const double ga = gamma_from >= 0 ? gamma * scal[gamma_from] : gamma;
+  const double xi = x[i], yi = y[i];
+  double* a = A + static_cast<size_t>(i) * lda;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x)
+    a[j] += al * xi * y[j] + be * yi * x[j] + ga * xi * x[j];
+}
+
+extern "C" {
+
+int mbpls_xt_multi_f64(const double* Xt, long ld, int n, int p, const double* M, long ldm, int C, double* out, long ldo,
+                       void* stream) {
+  if (!Xt || !M || !out || C < 1 || (ld % 2) != 0 || (ldm % 2) != 0) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  int grid = (p + 31) / 32;  // 8 warps x 4 features
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    const int nc = C - c0;
+    if (nc > 4) xt_multi_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
+    else if (nc > 2) xt_multi_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
+    else if (nc > 1) xt_multi_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
+    else xt_multi_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_lincomb_sub_f64(double* out, const double* base, const double* V, long ldv, int K, const double* coef, int len,
+                          void* stream) {
+  if (!out || !base || (K > 0 && (!V || !coef))) return MBPLS_ERR_ARG;
+  if (len <= 0) return MBPLS_OK;
+  int grid = (len + 255) / 256;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  lincomb_sub_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, base, V, ldv, K, coef, len);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_center_normalize_f64(double* t, int n, int center, int normalize, double* nrm_out, void* stream) {
+  if (!t || n < 1) return MBPLS_ERR_ARG;
+  center_normalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(t, n, center, normalize, nrm_out);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_block_sumsq_f64(const double* w, const int* off, int B, double* out, void* stream) {
+  if (!w || !off || !out || B < 1) return MBPLS_ERR_ARG;
+  block_sumsq_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, off, out);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_scale_by_block_f64(const double* w, const int* off, int B, const double* a, double* out, int p, void* stream) {
+  if (!w || !off || !a || !out || B < 1) return MBPLS_ERR_ARG;
+  if (p <= 0) return MBPLS_OK;
+  int grid = (p + 255) / 256;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  scale_by_block_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, off, B, a, out, p);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_crossprod_splits(int M, int N, long Kdim) {
+  const long tiles = static_cast<long>((M + XP_BM - 1) / XP_BM) * ((N + XP_BN - 1) / XP_BN);
+  long want = (2L * num_sms() + tiles - 1) / tiles;  // ~2 waves of CTAs
+  const long maxs = (Kdim + 4 * XP_BK - 1) / (4 * XP_BK);
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  return static_cast<int>(want);
+}
+
+// kmajor = 1: C = A B' with A (M x Kdim, lda), B (N x Kdim, ldb); kmajor = 0: C = A' B with A (Kdim x M), B (Kdim x N).
+// Cpart holds `splits` partial M x ldc matrices (splits = mbpls_crossprod_splits); reduce with mbpls_reduce_chunks_f64.
+int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, int M, int N, long Kdim, int kmajor, int splits,
+                        double* Cpart, long ldc, void* stream) {
+  if (!A || !B || !Cpart || M < 1 || N < 1 || Kdim < 0 || splits < 1 || ldc < N) return MBPLS_ERR_ARG;
+  if (kmajor && ((lda % 2) != 0 || (ldb % 2) != 0)) return MBPLS_ERR_ARG;
+  long kps = (Kdim + splits - 1) / splits;
+  kps = ((kps + XP_BK - 1) / XP_BK) * XP_BK;
+  if (kps < XP_BK) kps = XP_BK;
+  dim3 grid((N + XP_BN - 1) / XP_BN, (M + XP_BM - 1) / XP_BM, splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem = 2 * (XP_BM + XP_BN) * XP_LD * static_cast<int>(sizeof(double));
+  if (kmajor) {
+    cudaFuncSetAttribute(crossprod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    crossprod_kernel<true><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc);
+  } else {
+    cudaFuncSetAttribute(crossprod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    crossprod_kernel<false><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_dense_gemv_f64(const double* A, long lda, int m, int ncols, const double* x, double* y, void* stream) {
+  if (!A || !x || !y || m < 1) return MBPLS_ERR_ARG;
+  int grid = (m + 7) / 8;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  dense_gemv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, m, ncols, x, y);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_dense_rank2_f64(double* A, long lda, int m, int ncols, const double* x, const double* y, const double* scal,
+                          double alpha, double beta, double gamma, int alpha_from, int gamma_from, void* stream) {
+  if (!A || !x || !y || m < 1) return MBPLS_ERR_ARG;
+  int gx = (ncols + 255) / 256;
+  if (gx > 32) gx = 32;
+  for (int i0 = 0; i0 < m; i0 += 65535) {
+    const int mi = (m - i0) < 65535 ? (m - i0) : 65535;
+    dim3 grid(gx, mi);
+    dense_rank2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, i0, m, ncols, x, y, scal, alpha, beta,
+                                                                           gamma, alpha_from, gamma_from);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"
