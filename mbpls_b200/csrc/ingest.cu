@@ -239,15 +239,22 @@ __global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __rest
   __shared__ double scratch[64];
   const int n2 = (n + 1) >> 1;
   const bool odd = (n & 1) != 0;
-  for (int j = blockIdx.x; j < p; j += gridDim.x) {
-    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * ld);
-    double2 xr[EPT2];
-    double v[2] = {0.0, 0.0};
+  double2 xr[EPT2];
+  int j = blockIdx.x;
+  if (j < p) {
+    const double2* x2 = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(j) * ld);
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
       const int i = threadIdx.x + k * 256;
       xr[k] = i < n2 ? ld_stream(x2 + i) : make_double2(NAN, NAN);  // out of range == missing
-      if (odd && i == n2 - 1) xr[k].y = NAN;                         // the padding element is not a sample
+    }
+  }
+  while (j < p) {
+    double v[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (odd && i == n2 - 1) xr[k].y = NAN;  // the padding element is not a sample
       if (!isnan(xr[k].x)) { v[0] += 1.0; v[1] += xr[k].x; }
       if (!isnan(xr[k].y)) { v[0] += 1.0; v[1] += xr[k].y; }
     }
@@ -264,6 +271,9 @@ __global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __rest
     block_sum<2>(c, scratch);
     double var;
     const double scale = scale_from(cnt, mean, c[0], c[1], var);
+    const int jn = j + gridDim.x;
+    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * ld);
+    const double2* xn = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(jn < p ? jn : j) * ld);
     double z[1] = {0.0};
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
@@ -276,6 +286,13 @@ __global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __rest
         st_stream(x2 + i, zi);
       }
     }
+    if (jn < p) {  // registers are drained: the next feature's loads fly during the reduction below
+#pragma unroll
+      for (int k = 0; k < EPT2; ++k) {
+        const int i = threadIdx.x + k * 256;
+        xr[k] = i < n2 ? ld_stream(xn + i) : make_double2(NAN, NAN);
+      }
+    }
     block_sum<1>(z, scratch);
     if (threadIdx.x == 0) {
       out.mean[j] = mean;
@@ -284,6 +301,7 @@ __global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __rest
       out.seen[j] = static_cast<long long>(cnt);
       out.zss[j] = z[0];
     }
+    j = jn;
   }
 }
 

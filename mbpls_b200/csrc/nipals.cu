@@ -648,14 +648,17 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
   const int n2 = (P.n + 1) >> 1;  // 16-byte units; an odd tail pairs with the zero padding element
   const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(P.ts);
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(P.u0);
-  for (int j = blockIdx.x; j < p; j += gridDim.x) {
-    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * P.ld);
-    double2 xr[EPT2];
+  double2 xr[EPT2];
+  int j = blockIdx.x;
+  if (j < p) {
+    const double2* x2 = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(j) * P.ld);
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
       const int i = threadIdx.x + k * 256;
       xr[k] = i < n2 ? ld_stream(x2 + i) : make_double2(0.0, 0.0);
     }
+  }
+  while (j < p) {
     double v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
@@ -677,6 +680,10 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
       v[0] = one[0];
     }
     const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
+    // update + store this feature
+    const int jn = j + gridDim.x;
+    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * P.ld);
+    const double2* xn = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(jn < p ? jn : j) * P.ld);
     double w[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
@@ -699,6 +706,15 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
         }
       }
     }
+    // all registers are drained: issue the next feature's loads now, so they fly during the reduction below
+    // (issued as one batch -- interleaving them with the L1 loads above serialises on the scoreboard)
+    if (jn < p) {
+#pragma unroll
+      for (int k = 0; k < EPT2; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < n2) xr[k] = ld_stream(xn + i);
+      }
+    }
     if (P.u0) {
       if (P.nanmode) {
         block_sum<3>(w, scratch);
@@ -713,6 +729,7 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
       P.pss[j] = pj * pj;
       if (P.u0) P.w_next[j] = (P.nanmode && w[2] > 0.0) ? w[0] / w[1] : w[0] / *P.u0u0;
     }
+    j = jn;
   }
 }
 
