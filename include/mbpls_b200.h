@@ -149,9 +149,13 @@ int mbpls_reduce_chunks_f64(const double* Cpart, int nchunks, int len, double* C
 /* out[c][j] = sum_k (in[k][j] * rowscale[k]) * M[k*C + c]   (R_ = W pinv(P'W), beta_ = R_ V_') */
 int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const double* rowscale, const double* M, int C,
                              double* out, long ldout, void* stream);
-/* out_part[s][c][i] = sum_{j in split s} nan0(Xt[j][i]) * Bm[c][j]   (X.dot(beta_), X.dot(R_), X_b.dot(W_b)) */
+/* out_part[s][c][i] = sum_{j in split s} nan0(z_ij) * Bm[c][j]   (X.dot(beta_), X.dot(R_), X_b.dot(W_b));
+ * z_ij = Xt[j][i], or (Xt[j][i] - mean[j]) / scale[j] when mean/scale are given (x_scalers_[b].transform fused
+ * into the product, mbpls.py:1097,:1369, so predict reads new data exactly once).  nonfinite_flag (optional) is
+ * set to 1 if any raw element is NaN or inf (check_array's finiteness test, :1368, without an extra pass). */
 int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
-                          const int* split_f1, int nsplit, double* out_part, long ldo, void* stream);
+                          const int* split_f1, int nsplit, double* out_part, long ldo, const double* mean,
+                          const double* scale, int* nonfinite_flag, void* stream);
 /* X_b <- X_b - ts p_b' for new data (transform, mbpls.py:1145,1204); NaNs stay NaN */
 int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, const double* pvec, void* stream);
 /* column norms / scaling of a C x ld feature-major array over n samples */

@@ -84,12 +84,14 @@ template <int NC>
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* __restrict__ Bm, long ldb, int C, int c0,
                    const int* __restrict__ split_f0, const int* __restrict__ split_f1, double* __restrict__ out_part,
-                   long ldo) {
+                   long ldo, const double* __restrict__ mean, const double* __restrict__ scale, int* __restrict__ flag) {
   const int s = blockIdx.y;
   const int f0 = split_f0[s], f1 = split_f1[s];
   const int r = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (r >= n) return;
   const int nc = min(NC, C - c0);
+  const bool last_is_pad = (r + 1 >= n);  // odd n: the second lane element is the zero padding, not a sample
+  int bad = 0;
   double ax[NC], ay[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) ax[c] = ay[c] = 0.0;
@@ -100,6 +102,12 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       x[k] = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j + k) * ld));
+      bad |= !isfinite(x[k].x) | !isfinite(x[k].y);
+      if (mean) {  // StandardScaler.transform fused into the product (mbpls.py:1097,:1369): z = (x - mean) / scale
+        const double m = __ldg(mean + j + k), sc = __ldg(scale + j + k);
+        x[k].x = (x[k].x - m) / sc;
+        x[k].y = (x[k].y - m) / sc;
+      }
       if (isnan(x[k].x)) x[k].x = 0.0;
       if (isnan(x[k].y)) x[k].y = 0.0;
     }
@@ -117,6 +125,12 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
   }
   for (; j < f1; ++j) {
     double2 x = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j) * ld));
+    bad |= !isfinite(x.x) | !isfinite(x.y);
+    if (mean) {
+      const double m = __ldg(mean + j), sc = __ldg(scale + j);
+      x.x = (x.x - m) / sc;
+      x.y = (x.y - m) / sc;
+    }
     if (isnan(x.x)) x.x = 0.0;
     if (isnan(x.y)) x.y = 0.0;
 #pragma unroll
@@ -132,9 +146,10 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
   for (int c = 0; c < NC; ++c) {
     if (c < nc) {
       double* o = out_part + (static_cast<size_t>(s) * C + c0 + c) * ldo + r;
-      *reinterpret_cast<double2*>(o) = make_double2(ax[c], ay[c]);
+      *reinterpret_cast<double2*>(o) = make_double2(ax[c], last_is_pad ? 0.0 : ay[c]);
     }
   }
+  if (flag && bad) *flag = 1;  // idempotent: lets the caller reject NaN/inf input without an extra pass
 }
 
 __global__ void __launch_bounds__(256)
@@ -201,7 +216,9 @@ int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const do
 }
 
 int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
-                          const int* split_f1, int nsplit, double* out_part, long ldo, void* stream) {
+                          const int* split_f1, int nsplit, double* out_part, long ldo, const double* mean,
+                          const double* scale, int* nonfinite_flag, void* stream) {
+  if ((mean == nullptr) != (scale == nullptr)) return MBPLS_ERR_ARG;
   if (!Xt || !Bm || !split_f0 || !split_f1 || !out_part || C < 1 || (ld % 2) != 0 || (ldo % 2) != 0) return MBPLS_ERR_ARG;
   if (nsplit == 0 || n == 0) return MBPLS_OK;
   if (nsplit > 65535) return MBPLS_ERR_SIZE;
@@ -209,11 +226,11 @@ int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, lo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int c0 = 0; c0 < C; c0 += 16) {
     const int nc = C - c0;
-    if (nc >= 16 || nc > 8) skinny_gemm_kernel<16><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
-    else if (nc > 4) skinny_gemm_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
-    else if (nc > 2) skinny_gemm_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
-    else if (nc > 1) skinny_gemm_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
-    else skinny_gemm_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo);
+    if (nc >= 16 || nc > 8) skinny_gemm_kernel<16><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 4) skinny_gemm_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 2) skinny_gemm_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 1) skinny_gemm_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else skinny_gemm_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
   }
   MBPLS_RETURN_LAST();
 }

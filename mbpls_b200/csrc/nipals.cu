@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(1024) nipals_epilogue_kernel(mbpls_epilogue_ar
   int* ctrl = a.ctrl;
   if (ctrl[MBPLS_CTRL_DONE]) return;
   __shared__ double scratch[32 * 4];
-  __shared__ double s_norm[EPI_MAXB], s_a[EPI_MAXB], s_v[EPI_MAXQ], s_vnum[EPI_MAXQ], s_vden[EPI_MAXQ];
+  __shared__ double s_norm[EPI_MAXB], s_a[EPI_MAXB], s_v[EPI_MAXQ];
   __shared__ double s_sc[8];
   const int n = a.n, B = a.B, q = a.q;
   const long ldt = a.ldt;

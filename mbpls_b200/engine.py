@@ -330,7 +330,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                u0: torch.Tensor, nanmode: bool = False, row_flag: Optional[torch.Tensor] = None,
                ycol_flag: Optional[torch.Tensor] = None, max_tol: float = 1e-14, norm_kind: int = 0,
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
-               trips_per_sync: Optional[int] = None, profile: Optional[dict] = None) -> NipalsResult:
+               trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
+               deflate_last: bool = False) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -439,12 +440,20 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         call("mbpls_nipals_record_component_f64", C.byref(rec), st)
         last = (k == K - 1)
         fuse = fuse_next_xtu and not last
-        timed("deflate", lambda: call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts), ptr(u0) if fuse else None,
-                                      ptr(u0u0) if fuse else None, ptr(res.P[k]), ptr(w) if fuse else None, ptr(pss),
-                                      nan, deflate_mode, st))
+        if last and not deflate_last:
+            # the deflated X of the last component is never read (mbpls.py:968-969 is followed by the end of the
+            # loop), so only the loadings are computed: one read instead of read + write
+            timed("loadings", lambda: call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(ts), None, ptr(boff), B,
+                                           ptr(res.P[k]), None, nan, None, st))
+            if p > 0:
+                call("mbpls_block_sumsq_f64", ptr(res.P[k]), ptr(boff), B, ptr(res.pssb[k]), st)
+        else:
+            timed("deflate", lambda: call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts),
+                                          ptr(u0) if fuse else None, ptr(u0u0) if fuse else None, ptr(res.P[k]),
+                                          ptr(w) if fuse else None, ptr(pss), nan, deflate_mode, st))
+            if p > 0:
+                call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
         w_ready = fuse
-        if p > 0:
-            call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
     return res
 
 
@@ -484,8 +493,11 @@ def right_multiply(inp: torch.Tensor, p: int, rowscale: Optional[torch.Tensor], 
     return out[:, :p]
 
 
-def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[int], group=None) -> torch.Tensor:
-    """out[c][i] = sum_j nan0(Xt[j][i]) * Bm[c][j]  ->  C x ld (feature-major result)."""
+def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[int], group=None,
+                mean: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+                flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c][i] = sum_j nan0(z_ij) * Bm[c][j]  ->  C x ld (feature-major result); z = Xt, or the standardised
+    value (Xt - mean_j) / scale_j computed on the fly when mean/scale are given."""
     dev = Xt.device
     p, ld = Xt.shape
     Cc = Bm.shape[0]
@@ -496,7 +508,7 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         part = torch.zeros((ns, Cc * ld), dtype=F64, device=dev)
         sf0, sf1 = _i32(f0, dev), _i32(f1, dev)  # keep alive: ptr() of a temporary would dangle
         call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(sf0), ptr(sf1),
-             ns, ptr(part), ld, stream_ptr(dev))
+             ns, ptr(part), ld, ptr(mean), ptr(scale), ptr(flag), stream_ptr(dev))
         call("mbpls_reduce_chunks_f64", ptr(part), ns, Cc * ld, ptr(out), stream_ptr(dev))
     allreduce_(out, group)
     return out

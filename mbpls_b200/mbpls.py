@@ -44,6 +44,7 @@ _RUNTIME_DEFAULTS = dict(
     max_iter=1_000_000,   # safety cap on NIPALS trips; the reference loop is unbounded (mbpls.py:841)
     global_sizes=None,    # multi-GPU: the blocks passed in are this rank's column ranges of blocks of these sizes
     profile=None,         # dict collecting CUDA-event pairs per kernel (bench.py roofline)
+    deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
 )
 
 
@@ -153,10 +154,15 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
 
     # ------------------------------------------------------------------ NaN census (mbpls.py:255-271)
     def check_sparsity_level(self, data):
-        """Reference-compatible census of one host array; the fit path uses the device census kernel."""
-        data = np.asarray(data, dtype=np.float64)
-        nanmask = np.isnan(data)
-        return self._census_from_flags(nanmask.any(axis=1), nanmask.any(axis=0))
+        """Reference-compatible census of one array (mbpls.py:255-271), computed by the device census kernel."""
+        device = E.require_cuda(self._runtime()["device"])
+        src = _as_2d_source(data, "data")
+        n, p = int(src.shape[0]), int(src.shape[1])
+        with torch.cuda.device(device):
+            Xt = E.alloc_feature_major(p, n, device)
+            E.ingest_feature_major(src, n, 0, p, Xt, device)
+            col_nan, row_flag = E.nan_census(Xt, n, E._i32([0, p], device), 1)
+            return self._census_from_flags(row_flag[0, :n].cpu().numpy().astype(bool), (col_nan > 0).cpu().numpy())
 
     @staticmethod
     def _census_from_flags(row_has: np.ndarray, col_has: np.ndarray):
@@ -338,7 +344,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         res = E.nipals_fit(Xt, Yt, n, shard.block_off, K, u0=u0, nanmode=sparse, row_flag=row_flag, ycol_flag=ycol_flag,
                            max_tol=self.max_tol, norm_kind=E.norm_kind_of(self.nipals_convergence_norm),
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
-                           deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"])
+                           deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
+                           deflate_last=rt["deflate_last"])
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
@@ -425,29 +432,39 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_dev_scalers"] = sc
         return sc
 
-    def _prepare_new_X(self, X, device):
+    def _prepare_new_X(self, X, device, scaled_copy: bool):
+        """Ingest new data.  scaled_copy=False: X is left untouched (device views are adopted zero-copy) and the
+        scaler statistics are returned for on-the-fly standardisation inside the product kernel;
+        scaled_copy=True: a private, standardised copy (needed by the sequential block-score deflation)."""
         dev = self._device_model(device)
         shard = dev["shard"]
-        Xt, m, _ = self._ingest(X, None, shard, device)
-        if not self.sparse_data:
-            self._require_finite(Xt, Xt[:0])
-        elif bool(torch.isinf(Xt).any()):
-            raise ValueError("Input contains infinity or a value too large for dtype('float64').")
+        Xt, m, _ = self._ingest(X, None, shard, device, adopt=not scaled_copy)
+        mean = scale = None
         if self.standardize:
             mean, scale, _, _ = self._device_scalers(shard, device)
-            E.standardize_apply(Xt, m, mean, scale)
-        return dev, shard, Xt, m
+            if scaled_copy:
+                E.standardize_apply(Xt, m, mean, scale)
+                mean = scale = None
+        return dev, shard, Xt, m, mean, scale
+
+    def _check_flag(self, flag, group):
+        bad = bool(flag.item())
+        if self.sparse_data:
+            return
+        self._raise_if_any_rank(bad, "Input contains NaN or infinity.", group)
 
     def predict(self, X, copy=True):
         """y_hat = inverse_scale(scale(X) . beta_)  (mbpls.py:1337-1410); NaN entries count as zero after
-        scaling (:1379-1383)."""
+        scaling (:1379-1383).  One pass over X: standardisation and the finiteness check are fused into the product."""
         self._check_is_fitted()
         device = E.require_cuda(self._runtime()["device"])
         group, _, _ = self._group_info()
         with torch.cuda.device(device):
-            dev, shard, Xt, m = self._prepare_new_X(X, device)
+            dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=False)
             q = dev["beta"].shape[0]
-            Yh = E.skinny_gemm(Xt, m, dev["beta"], shard.block_off, group)
+            flag = torch.zeros(1, dtype=torch.int32, device=device)
+            Yh = E.skinny_gemm(Xt, m, dev["beta"], shard.block_off, group, mean, scale, flag)
+            self._check_flag(flag, group)
             if self.standardize:
                 _, _, ymean, yscale = self._device_scalers(shard, device)
                 call("mbpls_scaler_inverse_f64", ptr(Yh), Yh.shape[1], m, q, ptr(ymean), ptr(yscale), stream_ptr(device))
@@ -459,12 +476,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         device = E.require_cuda(self._runtime()["device"])
         group, _, _ = self._group_info()
         with torch.cuda.device(device):
-            dev, shard, Xt, m = self._prepare_new_X(X, device)
+            want_blocks = self.method != 'SIMPLS' and return_block_scores
+            dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=want_blocks)
+            if want_blocks and "W" not in dev:
+                raise AttributeError("block scores need W_ (fit with calc_all=True)")
             K = dev["R"].shape[0]
-            Ts_dev = E.skinny_gemm(Xt, m, dev["R"], shard.block_off, group)  # K x ld   (:1110-1117)
+            flag = torch.zeros(1, dtype=torch.int32, device=device)
+            Ts_dev = E.skinny_gemm(Xt, m, dev["R"], shard.block_off, group, mean, scale, flag)  # K x ld   (:1110-1117)
+            self._check_flag(flag, group)
             Ts = np.ascontiguousarray(Ts_dev[:, :m].cpu().numpy().T)
             out = [Ts]
-            if self.method != 'SIMPLS' and return_block_scores:  # :1126-1155
+            if want_blocks:  # :1126-1155
                 B = len(shard.sizes)
                 T = []
                 for b in range(B):
@@ -487,12 +509,12 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 q = int(Ysrc.shape[1])
                 Yt = E.alloc_feature_major(q, m, device)
                 E.ingest_feature_major(Ysrc, m, 0, q, Yt, device)
-                if not self.sparse_data:
-                    self._require_finite(Yt, Yt[:0])
+                ymean = yscale = None
                 if self.standardize:
                     _, _, ymean, yscale = self._device_scalers(shard, device)
-                    E.standardize_apply(Yt, m, ymean, yscale)
-                Ur = E.skinny_gemm(Yt, m, dev["V"], [0, q], None)  # K x ld
+                yflag = torch.zeros(1, dtype=torch.int32, device=device)
+                Ur = E.skinny_gemm(Yt, m, dev["V"], [0, q], None, ymean, yscale, yflag)  # K x ld
+                self._check_flag(yflag, None)
                 nrm = torch.sqrt(E.rows_sumsq(Ur, m))
                 call("mbpls_rows_scale_f64", ptr(Ur), Ur.shape[1], K, m, ptr(nrm), 1, stream_ptr(device))
                 out.append(np.ascontiguousarray(Ur[:, :m].cpu().numpy().T))

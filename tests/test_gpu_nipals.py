@@ -190,3 +190,55 @@ def test_sklearn_surface():
     assert 0.5 < m.score(X, Y.ravel()) <= 1.0
     assert np.isclose(m.r2_score(X, Y.ravel()), m.score(X, Y.ravel()))
     assert m.x_scalers_[0].inverse_transform(m.P_[0].T).shape == (2, 30)
+
+
+def test_large_shape_invariants_and_device_inputs():
+    """Size-independent properties at a shape the oracle cannot hold comfortably (n=10,000, p=60,000, device-generated,
+    adopted zero-copy): orthonormal superscores, unit block weights, A_ columns sum to 1, beta_ = R_ V_', predict ==
+    inverse_scale(Ts V_'), predict leaves a device input untouched, trips == 2 for PLS1."""
+    import torch
+    from mbpls_b200 import MBPLS, synth, engine as E
+    dev = torch.device("cuda:0")
+    n, sizes, K = 10_000, (10_000, 20_000, 30_000), 6
+    p = sum(sizes)
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    Xbuf = torch.empty((p, E.round_ld(n)), dtype=torch.float64, device=dev)
+
+    def blocks():
+        synth.fill_feature_major(Xbuf, n, 0, p, K, 77, noise=0.02, decay=0.85)
+        return [Xbuf[off[b]:off[b + 1], :n].t() for b in range(len(sizes))]
+
+    Y = synth.response(n, 1, K, dev, 77, decay=0.85)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = MBPLS(n_components=K, copy=False).fit(blocks(), Y)
+    assert m.n_iter_ == [2] * K
+    G = m.Ts_.T @ m.Ts_
+    assert np.allclose(G, np.eye(K), atol=1e-10)
+    for Wb in m.W_:
+        assert np.allclose(np.linalg.norm(Wb, axis=0), 1.0, rtol=1e-12)
+    assert np.allclose(m.A_.sum(axis=0), 1.0, rtol=1e-12)
+    assert np.allclose(m.beta_, m.R_ @ m.V_.T, rtol=1e-10, atol=1e-14)
+    assert 0 < sum(m.explained_var_x_) <= 1 + 1e-9 and np.all(np.diff(np.cumsum(m.explained_var_y_)) >= -1e-12)
+    Xnew = blocks()
+    before = Xbuf[:, :n].clone()
+    yh = m.predict(Xnew)
+    assert torch.equal(Xbuf[:, :n], before), "predict must not modify a device input"
+    Ts_new = m.transform(Xnew)
+    yh2 = m.y_scaler_.inverse_transform(Ts_new @ m.V_.T)
+    assert np.allclose(yh, yh2, rtol=1e-9, atol=1e-11)
+    # the training data reproduce the training superscores
+    assert np.allclose(np.abs(Ts_new / np.linalg.norm(Ts_new, axis=0)), np.abs(m.Ts_), rtol=1e-8, atol=1e-10)
+    assert m.score(Xnew, Y.cpu().numpy()) > 0.9
+
+
+def test_check_sparsity_level_matches_reference_semantics():
+    from mbpls_b200 import MBPLS
+    from oracle import nan_census
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((37, 53))
+    A[rng.random(A.shape) < 0.03] = np.nan
+    got = MBPLS().check_sparsity_level(A)
+    want = nan_census(A)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
