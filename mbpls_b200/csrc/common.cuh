@@ -71,6 +71,29 @@ __device__ __forceinline__ void block_sum_consumers(double (&v)[NV], double* scr
   for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? scratch[k * 32 + lane] : 0.0);
 }
 
+// Reduction inside one 256-thread *group* of a CTA (group g uses named barrier 1+g and its own scratch):
+// lets two independent feature pipelines share one CTA (and its shared-memory copies of ts / u0).
+template <int NV>
+__device__ __forceinline__ void group_sum256(double (&v)[NV], double* scratch, int group) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x & 255) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[k * 8 + warp] = v[k];
+  }
+  asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = lane < 8 ? scratch[k * 8 + lane] : 0.0;
+    t += __shfl_xor_sync(MBPLS_FULL_MASK, t, 4);
+    t += __shfl_xor_sync(MBPLS_FULL_MASK, t, 2);
+    t += __shfl_xor_sync(MBPLS_FULL_MASK, t, 1);
+    v[k] = __shfl_sync(MBPLS_FULL_MASK, t, 0);
+  }
+}
+
 __device__ __forceinline__ double block_sum1(double x, double* scratch) {
   double v[1] = {x};
   block_sum<1>(v, scratch);
@@ -139,6 +162,13 @@ __device__ __forceinline__ void bulk_wait_all() {
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
   double2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// 16-byte load of a small vector that every CTA re-reads (ts, u0): keep it in L1 against the streaming traffic
+__device__ __forceinline__ double2 ld_keep(const double2* p) {
+  double2 r;
+  asm("ld.global.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
 }
 

@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
       const int i = threadIdx.x + k * 256;
-      const double2 t = i < n2 ? ts2[i] : make_double2(0.0, 0.0);
+      const double2 t = i < n2 ? ld_keep(ts2 + i) : make_double2(0.0, 0.0);
       if (P.nanmode) {
         if (!isnan(xr[k].x)) { v[0] = fma(xr[k].x, t.x, v[0]); v[1] = fma(t.x, t.x, v[1]); } else v[2] = 1.0;
         if (!isnan(xr[k].y)) { v[0] = fma(xr[k].y, t.y, v[0]); v[1] = fma(t.y, t.y, v[1]); } else v[2] = 1.0;
@@ -689,13 +689,13 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
     for (int k = 0; k < EPT2; ++k) {
       const int i = threadIdx.x + k * 256;
       if (i < n2) {
-        const double2 t = ts2[i];
+        const double2 t = ld_keep(ts2 + i);
         double2 xi;
         xi.x = __dsub_rn(xr[k].x, __dmul_rn(t.x, pj));  // the reference rounds ts*p before subtracting (:969)
         xi.y = __dsub_rn(xr[k].y, __dmul_rn(t.y, pj));
         st_stream(x2 + i, xi);
         if (P.u0) {
-          const double2 uv = u2[i];
+          const double2 uv = ld_keep(u2 + i);
           if (P.nanmode) {
             if (!isnan(xi.x)) { w[0] = fma(xi.x, uv.x, w[0]); w[1] = fma(uv.x, uv.x, w[1]); } else w[2] = 1.0;
             if (!isnan(xi.y)) { w[0] = fma(xi.y, uv.y, w[0]); w[1] = fma(uv.y, uv.y, w[1]); } else w[2] = 1.0;
@@ -733,10 +733,124 @@ __global__ void __launch_bounds__(256, 2) loadings_deflate_regs_kernel(double* _
   }
 }
 
+// Same algorithm with ts and u0 staged ONCE per CTA in shared memory: a 512-thread CTA runs two independent
+// 256-thread feature pipelines (named barriers 1 and 2) that share the 2 x 8n-byte copies, so phase B no longer
+// depends on L1 hit rates (ncu: 20 % of the ts/u0 sectors missed L1 in the 2-CTA variant and every miss sat
+// on the update's critical path, profiles/r1_notes.md).
+template <int EPT2>
+__global__ void __launch_bounds__(512, 1) loadings_deflate_regs2_kernel(double* __restrict__ Xt, int p, DeflateParams P) {
+  extern __shared__ __align__(16) double vecs[];  // ts[ld] | u0[ld]
+  __shared__ double scratch2[2][24];
+  const int n2 = (P.n + 1) >> 1;
+  const int g = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  double* s_ts = vecs;
+  double* s_u = vecs + P.ld;
+  for (int i = threadIdx.x; i < P.ld; i += 512) {
+    s_ts[i] = i < P.n ? P.ts[i] : 0.0;
+    if (P.u0) s_u[i] = i < P.n ? P.u0[i] : 0.0;
+  }
+  __syncthreads();
+  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(s_ts);
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(s_u);
+  double* scratch = scratch2[g];
+  const int stride = 2 * gridDim.x;
+  double2 xr[EPT2];
+  int j = 2 * blockIdx.x + g;
+  if (j < p) {
+    const double2* x2 = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(j) * P.ld);
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = tid + k * 256;
+      xr[k] = i < n2 ? ld_stream(x2 + i) : make_double2(0.0, 0.0);
+    }
+  }
+  while (j < p) {
+    double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = tid + k * 256;
+      const double2 t = i < n2 ? ts2[i] : make_double2(0.0, 0.0);
+      if (P.nanmode) {
+        if (!isnan(xr[k].x)) { v[0] = fma(xr[k].x, t.x, v[0]); v[1] = fma(t.x, t.x, v[1]); } else v[2] = 1.0;
+        if (!isnan(xr[k].y)) { v[0] = fma(xr[k].y, t.y, v[0]); v[1] = fma(t.y, t.y, v[1]); } else v[2] = 1.0;
+      } else {
+        v[0] = fma(xr[k].x, t.x, v[0]);
+        v[0] = fma(xr[k].y, t.y, v[0]);
+      }
+    }
+    if (P.nanmode) {
+      group_sum256<3>(v, scratch, g);
+    } else {
+      double one[1] = {v[0]};
+      group_sum256<1>(one, scratch, g);
+      v[0] = one[0];
+    }
+    const double pj = (P.nanmode && v[2] > 0.0) ? v[0] / v[1] : v[0];
+    const int jn = j + stride;
+    double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * P.ld);
+    const double2* xn = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(jn < p ? jn : j) * P.ld);
+    double w[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EPT2; ++k) {
+      const int i = tid + k * 256;
+      if (i < n2) {
+        const double2 t = ts2[i];
+        double2 xi;
+        xi.x = __dsub_rn(xr[k].x, __dmul_rn(t.x, pj));  // the reference rounds ts*p before subtracting (:969)
+        xi.y = __dsub_rn(xr[k].y, __dmul_rn(t.y, pj));
+        st_stream(x2 + i, xi);
+        if (P.u0) {
+          const double2 uv = u2[i];
+          if (P.nanmode) {
+            if (!isnan(xi.x)) { w[0] = fma(xi.x, uv.x, w[0]); w[1] = fma(uv.x, uv.x, w[1]); } else w[2] = 1.0;
+            if (!isnan(xi.y)) { w[0] = fma(xi.y, uv.y, w[0]); w[1] = fma(uv.y, uv.y, w[1]); } else w[2] = 1.0;
+          } else {
+            w[0] = fma(xi.x, uv.x, w[0]);
+            w[0] = fma(xi.y, uv.y, w[0]);
+          }
+        }
+      }
+    }
+    if (jn < p) {  // registers are drained: the next feature's loads fly during the reduction below
+#pragma unroll
+      for (int k = 0; k < EPT2; ++k) {
+        const int i = tid + k * 256;
+        if (i < n2) xr[k] = ld_stream(xn + i);
+      }
+    }
+    if (P.u0) {
+      if (P.nanmode) {
+        group_sum256<3>(w, scratch, g);
+      } else {
+        double one[1] = {w[0]};
+        group_sum256<1>(one, scratch, g);
+        w[0] = one[0];
+      }
+    }
+    if (tid == 0) {
+      P.P_k[j] = pj;
+      P.pss[j] = pj * pj;
+      if (P.u0) P.w_next[j] = (P.nanmode && w[2] > 0.0) ? w[0] / w[1] : w[0] / *P.u0u0;
+    }
+    j = jn;
+  }
+}
+
+template <int EPT2>
+static void launch_deflate_regs2(double* Xt, int p, const DeflateParams& P, cudaStream_t st) {
+  int grid = num_sms();
+  if (grid > (p + 1) / 2) grid = (p + 1) / 2;
+  const size_t smem = 2 * static_cast<size_t>(P.ld) * sizeof(double);
+  cudaFuncSetAttribute(loadings_deflate_regs2_kernel<EPT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  loadings_deflate_regs2_kernel<EPT2><<<grid, 512, smem, st>>>(Xt, p, P);
+}
+
 template <int EPT2>
 static void launch_deflate_regs(double* Xt, int p, const DeflateParams& P, cudaStream_t st) {
   int grid = num_sms() * 2;
   if (grid > p) grid = p;
+  // ts and u0 (2 x 8n bytes) must stay L1-resident: give the unified L1/shared array entirely to L1
+  cudaFuncSetAttribute(loadings_deflate_regs_kernel<EPT2>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   loadings_deflate_regs_kernel<EPT2><<<grid, 256, 0, st>>>(Xt, p, P);
 }
 
@@ -879,7 +993,21 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
   DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss, dbg};
   StreamShape sh;
   bool cta_wide = false;
-  if (mode == 0 && n > 1024 && n <= 16384) {  // register-resident
+  if ((mode == 0 || mode == 3) && n > 1024 && n <= 16384 &&
+      2 * static_cast<size_t>(ld) * sizeof(double) + 1024 <= static_cast<size_t>(smem_optin())) {
+    // register-resident features, ts/u0 shared-memory resident (two 256-thread pipelines per CTA)
+    const int e = (((n + 1) >> 1) + 255) / 256;
+    if (mode == 3) {  // experiment switch: the 2-CTA/SM variant that reads ts/u0 through L1
+      if (e <= 20) launch_deflate_regs<20>(Xt, p, P, st);
+      else launch_deflate_regs<32>(Xt, p, P, st);
+    } else if (e <= 4) launch_deflate_regs2<4>(Xt, p, P, st);
+    else if (e <= 8) launch_deflate_regs2<8>(Xt, p, P, st);
+    else if (e <= 12) launch_deflate_regs2<12>(Xt, p, P, st);
+    else if (e <= 16) launch_deflate_regs2<16>(Xt, p, P, st);
+    else if (e <= 20) launch_deflate_regs2<20>(Xt, p, P, st);
+    else if (e <= 24) launch_deflate_regs2<24>(Xt, p, P, st);
+    else launch_deflate_regs2<32>(Xt, p, P, st);
+  } else if (mode == 0 && n > 1024 && n <= 16384) {  // register-resident, vectors through L1 (n too long for smem copies)
     const int e = (((n + 1) >> 1) + 255) / 256;
     if (e <= 4) launch_deflate_regs<4>(Xt, p, P, st);
     else if (e <= 8) launch_deflate_regs<8>(Xt, p, P, st);
