@@ -292,16 +292,19 @@ def run_ours(args):
 
     x_bytes_local = 8.0 * n * shard.p_local
     kern = {}
-    for key, mult in (("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0)):
+    for key, mult in (("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0), ("loadings", 1.0), ("standardize", 2.0)):
         t = mean_ms(key)
         if t:
             kern[key] = {"ms": t, "launches": len(profile[key]), "algorithmic_bytes": mult * x_bytes_local,
                          "gbs": mult * x_bytes_local / (t / 1e3) / 1e9}
     dominant = "xw" if "xw" in kern else None
     traffic = None
-    try:
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one xw launch from the committed ncu --set full capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        traffic = prof.get("xw", {}).get("dram_bytes_per_launch")
+        entry = prof.get("xw", {})
+        if dominant and entry.get("algorithmic_bytes_per_launch"):
+            # the capture may have been taken on a different shard size: scale by the algorithmic bytes
+            traffic = entry["dram_bytes_per_launch"] * kern[dominant]["algorithmic_bytes"] / entry["algorithmic_bytes_per_launch"]
     except Exception:
         pass
     roofline = None

@@ -387,8 +387,10 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     done_p = ptr(ctrl)  # ctrl[MBPLS_CTRL_DONE] is element 0
 
     if trips_per_sync is None:
+        # trips enqueued per readback of the convergence flag; trips launched after convergence are no-ops
+        # (a few microseconds each), so batching only removes host round-trips from the critical path
         est_ms = 2.0 * p * ld * 8 / 5e12 * 1e3
-        trips_per_sync = 1 if est_ms > 1.0 else 4
+        trips_per_sync = 2 if est_ms > 1.0 else 4
     w_ready = False  # True when w already holds the first weights of the coming component
     cur = torch.cuda.current_stream(dev)
 

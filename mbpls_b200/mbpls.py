@@ -240,7 +240,14 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             # ---- standardisation (mbpls.py:299-326)
             zss = None
             if self.standardize:
+                prof = rt["profile"]
+                if prof is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record(torch.cuda.current_stream(device))
                 xs = E.standardize_fit(Xt, n, rt["standardize_mode"])
+                if prof is not None:
+                    ev[1].record(torch.cuda.current_stream(device))
+                    prof.setdefault("standardize", []).append(ev)
                 ys = E.standardize_fit(Yt, n, rt["standardize_mode"])
                 if not sparse:
                     ok = bool((xs.seen[:shard.p_local] == n).all()) and bool(torch.isfinite(xs.zss[:shard.p_local]).all()) \
