@@ -466,7 +466,6 @@ struct DeflateParams {
   double* P_k;            // p_local loadings out
   double* w_next;         // p_local next w~ out (if u0)
   double* pss;            // p_local: p_j^2 (for explained variance), always written
-  int debug;              // profiling experiments only (MBPLS_DEFLATE_DEBUG): 1 = consumers skip the arithmetic
 };
 
 template <bool CTA_WIDE>
@@ -562,7 +561,6 @@ struct DeflateWideOp {
     }
   }
   __device__ __forceinline__ void operator()(double* slab, int f0, int nf) {
-    if (P.debug == 1) return;
     for (int f = 0; f < nf; ++f) {
       double* x = slab + static_cast<size_t>(f) * P.ld;
       double v[3] = {0.0, 0.0, 0.0};
@@ -988,9 +986,7 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
   if (!Xt || !ts || !P_k || !pss || (u0 && (!u0u0 || !w_next)) || ld < n || (ld % 16) != 0) return MBPLS_ERR_ARG;
   if (p == 0) return MBPLS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("MBPLS_DEFLATE_DEBUG"); dbg = e ? atoi(e) : 0; }
-  DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss, dbg};
+  DeflateParams P{n, ld, nanmode, ts, u0, u0u0, P_k, w_next, pss};
   StreamShape sh;
   bool cta_wide = false;
   if ((mode == 0 || mode == 3) && n > 1024 && n <= 16384 &&

@@ -1,0 +1,118 @@
+"""GPU: edge cases of the fit path against the live oracle -- ragged / tiny shapes, single-feature blocks, one
+component, constant columns (scale 1 rule), K equal to the rank budget, many blocks, float32 / list inputs,
+NaN mode with a fully observed block, copy=False semantics."""
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import assert_trips, compare, rel_err, snapshot_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _both(kw, X, Y, Xt=None, Yt=None):
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    cp = (lambda a: [np.array(x, dtype=float) for x in a] if isinstance(a, list) else np.array(a, dtype=float))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(**kw).fit(cp(X), np.array(Y, dtype=float))
+        m = MBPLS(**kw).fit(cp(X), np.array(Y, dtype=float))
+    if Xt is None:
+        Xt, Yt = X, Y
+    ref, ours = snapshot_model(o, cp(Xt), np.array(Yt, dtype=float)), snapshot_model(m, cp(Xt), np.array(Yt, dtype=float))
+    compare(ours, ref, TOL, str(kw))
+    if kw.get("method", "NIPALS") == "NIPALS":
+        assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, kw.get("max_tol", 1e-14))
+    return m, o
+
+
+@pytest.mark.parametrize("method", ["NIPALS", "UNIPALS", "KERNEL", "SIMPLS"])
+def test_tiny_and_ragged_shapes(method):
+    rng = np.random.default_rng(1)
+    Z = rng.standard_normal((9, 3))
+    X = [Z @ rng.standard_normal((3, 1)) + 0.1 * rng.standard_normal((9, 1)),      # single-feature block
+         Z @ rng.standard_normal((3, 5)) + 0.1 * rng.standard_normal((9, 5)),
+         Z @ rng.standard_normal((3, 2)) + 0.1 * rng.standard_normal((9, 2))]
+    Y = Z[:, :2] @ rng.standard_normal((2, 2)) + 0.05 * rng.standard_normal((9, 2))
+    _both(dict(n_components=2, method=method, full_svd=True), X, Y)
+
+
+@pytest.mark.parametrize("method", ["NIPALS", "UNIPALS", "KERNEL", "SIMPLS"])
+def test_single_block_single_component(method):
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(33, (17,), 1, 2, seed=3)
+    m, o = _both(dict(n_components=1, method=method, full_svd=True), X[0], Y.ravel())
+    if method != "SIMPLS":
+        assert np.allclose(m.A_corrected_, 1.0) and m.A_corrected_.shape == (1, 1)  # mbpls.py:956-957
+
+
+def test_constant_columns_get_unit_scale():
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(40, (12, 9), 2, 2, seed=4)
+    X[0][:, 3] = 7.5       # constant feature -> scale_ == 1, standardised column == 0
+    X[1][:, 0] = -2.0
+    m, o = _both(dict(n_components=2), X, Y)
+    assert m.x_scalers_[0].scale_[3] == 1.0 and m.x_scalers_[1].scale_[0] == 1.0
+    assert np.all(m.W_[0][3] == 0.0)
+
+
+def test_many_blocks_and_list_float32_inputs():
+    rng = np.random.default_rng(5)
+    Z = rng.standard_normal((50, 6))
+    sizes = [3, 11, 1, 8, 20, 2, 5, 9, 4]
+    X = [(Z @ rng.standard_normal((6, s)) + 0.05 * rng.standard_normal((50, s))).astype(np.float32) for s in sizes]
+    Y = (Z[:, :3] @ rng.standard_normal((3, 3)) + 0.05 * rng.standard_normal((50, 3)))
+    _both(dict(n_components=4), [x.astype(np.float64) for x in X], Y)
+    from mbpls_b200 import MBPLS
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = MBPLS(n_components=3).fit([x.tolist() for x in X][0:1][0], Y[:, 0].tolist())  # nested lists -> single block
+        b = MBPLS(n_components=3).fit(np.asarray(X[0], dtype=np.float64), Y[:, 0])
+    assert rel_err(a.beta_, b.beta_) < 1e-12
+
+
+def test_nan_mode_with_a_fully_observed_block_and_dense_rows():
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(70, (20, 35, 15), 2, 3, seed=6)
+    rng = np.random.default_rng(7)
+    X[1][rng.random(X[1].shape) < 0.05] = np.nan        # block 0 and 2 stay fully observed
+    Xt, Yt = latent_blocks(9, (20, 35, 15), 2, 3, seed=8)
+    Xt[2][0, 4] = np.nan
+    m, o = _both(dict(n_components=3, sparse_data=True), X, Y, Xt, Yt)
+    assert len(m.sparse_X_info_[0][0]) == 0 and len(m.sparse_X_info_[1][0]) > 0
+
+
+def test_max_tol_and_norm_variants_change_trip_counts_like_the_reference():
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(80, (30, 50), 3, 3, seed=9)
+    for kw in (dict(max_tol=1e-6), dict(max_tol=1e-10, nipals_convergence_norm=1), dict(max_tol=1e-9, nipals_convergence_norm=-np.inf),
+               dict(max_tol=1e-8, nipals_convergence_norm="fro")):
+        m, o = _both(dict(n_components=3, **kw), X, Y)
+        assert list(m.n_iter_) == list(o.n_iter_)
+    from mbpls_b200 import MBPLS
+    with pytest.raises(ValueError):
+        MBPLS(nipals_convergence_norm=0).fit(X, Y)
+
+
+def test_copy_false_leaves_host_arrays_usable_and_model_identical():
+    from mbpls_b200 import MBPLS
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(60, (25, 40), 2, 2, seed=10)
+    keep = [x.copy() for x in X]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = MBPLS(n_components=2, copy=True).fit(X, Y)
+        assert all(np.array_equal(x, k) for x, k in zip(X, keep))  # copy=True never touches the inputs (mbpls.py:303)
+        b = MBPLS(n_components=2, copy=False).fit([x.copy() for x in X], Y.copy())
+    assert rel_err(a.beta_, b.beta_) < 1e-13
+
+
+def test_components_up_to_rank_budget():
+    """n_components close to min(n, p): late components are tiny but every attribute must still match."""
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(14, (6, 5), 1, 2, seed=11, noise=0.3)
+    _both(dict(n_components=6, method="SIMPLS", full_svd=True), X, Y.ravel())
+    _both(dict(n_components=6, method="KERNEL", full_svd=True), X, Y.ravel())
