@@ -180,7 +180,10 @@ int mbpls_scale_by_block_f64(const double* w, const int* off, int B, const doubl
  * Cpart: splits x M x ldc partials (splits = mbpls_crossprod_splits); sum them with mbpls_reduce_chunks_f64. */
 int mbpls_crossprod_splits(int M, int N, long Kdim);
 int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, int M, int N, long Kdim, int kmajor, int splits,
-                        double* Cpart, long ldc, void* stream);
+                        double* Cpart, long ldc, int symmetric, void* stream);
+/* symmetric=1 (A == B, M == N): only the tiles on/above the diagonal are computed (SYRK); after the split-K
+ * reduction call mbpls_symmetrize_f64 to mirror them below the diagonal. */
+int mbpls_symmetrize_f64(double* C, long ldc, int M, void* stream);
 /* y = A x for a dense m x ncols matrix (VAR w :595,:599; AS_Y ts :718) */
 int mbpls_dense_gemv_f64(const double* A, long lda, int m, int ncols, const double* x, double* y, void* stream);
 /* A += al*x y' + be*y x' + ga*x x' with al,be (ga) optionally multiplied by scal[alpha_from] (scal[gamma_from]):

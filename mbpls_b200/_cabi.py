@@ -82,7 +82,8 @@ SIGNATURES = {
     "mbpls_block_sumsq_f64": [_p, _p, _i, _p, _p],
     "mbpls_scale_by_block_f64": [_p, _p, _i, _p, _p, _i, _p],
     "mbpls_crossprod_splits": [_i, _i, _l],
-    "mbpls_crossprod_f64": [_p, _l, _p, _l, _i, _i, _l, _i, _i, _p, _l, _p],
+    "mbpls_crossprod_f64": [_p, _l, _p, _l, _i, _i, _l, _i, _i, _p, _l, _i, _p],
+    "mbpls_symmetrize_f64": [_p, _l, _i, _p],
     "mbpls_dense_gemv_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_dense_rank2_f64": [_p, _l, _i, _i, _p, _p, _p, _d, _d, _d, _i, _i, _p],
 }

@@ -315,13 +315,17 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
 
 # ---- KERNEL (mbpls.py:576-807) -------------------------------------------------------------------
 def crossprod(A, Bm, M, N, Kdim, kmajor, ldc):
+    """FP64 tensor-core cross product; A is Bm (X'X / XX') -> SYRK: upper tiles only, then mirrored."""
     dev = A.device
+    sym = 1 if (A.data_ptr() == Bm.data_ptr() and M == N) else 0
     splits = call("mbpls_crossprod_splits", M, N, Kdim)
     part = torch.zeros((splits, M * ldc), dtype=F64, device=dev)
     call("mbpls_crossprod_f64", ptr(A), A.stride(0), ptr(Bm), Bm.stride(0), M, N, Kdim, 1 if kmajor else 0, splits, ptr(part),
-         ldc, stream_ptr(dev))
+         ldc, sym, stream_ptr(dev))
     out = torch.zeros((M, ldc), dtype=F64, device=dev)
     call("mbpls_reduce_chunks_f64", ptr(part), splits, M * ldc, ptr(out), stream_ptr(dev))
+    if sym:
+        call("mbpls_symmetrize_f64", ptr(out), ldc, M, stream_ptr(dev))
     return out
 
 

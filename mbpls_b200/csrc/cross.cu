@@ -126,7 +126,7 @@ scale_by_block_kernel(const double* __restrict__ w, const int* __restrict__ off,
 // FP64 tensor-core cross product  C = op(A) . op(B)'  over the long dimension:
 //   KMAJOR = true : C[i][j] = sum_k A[i*lda + k] * B[j*ldb + k]   (X'X from the feature-major matrix, :586)
 //   KMAJOR = false: C[i][j] = sum_k A[k*lda + i] * B[k*ldb + j]   (XX' from the feature-major matrix, :704)
-// 128x128 CTA tile, 16-deep k slabs double-buffered through shared memory, 8 warps (2x4), each warp 64x32 =
+// 128x128 CTA tile, 16-deep k slabs in a 3-stage cp.async (LDGSTS) ring, 8 warps (2x4), each warp 64x32 =
 // 8x4 mma.sync.aligned.m8n8k4.f64 tiles (64 accumulator doubles per lane).  Split-K over gridDim.z with
 // per-split partial tiles reduced in fixed order by mbpls_reduce_chunks_f64 (deterministic).
 // ------------------------------------------------------------------------------------------
@@ -139,72 +139,81 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+#define XP_STAGES 3
+
+// cp.async (LDGSTS): asynchronous global -> shared copies of 8 / 16 bytes; src_bytes = 0 zero-fills the slot
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <bool KMAJOR>
 __global__ void __launch_bounds__(256)
 crossprod_kernel(const double* __restrict__ A, long lda, const double* __restrict__ B, long ldb, int M, int N, long Kdim,
-                 long k_per_split, double* __restrict__ Cpart, long ldc) {
+                 long k_per_split, double* __restrict__ Cpart, long ldc, int symmetric) {
+  if (symmetric && blockIdx.x < blockIdx.y) return;  // SYRK: only tiles on / above the diagonal (mirrored afterwards)
   extern __shared__ __align__(16) double xp_smem[];
-  double (*As)[XP_BM * XP_LD] = reinterpret_cast<double (*)[XP_BM * XP_LD]>(xp_smem);
-  double (*Bs)[XP_BN * XP_LD] = reinterpret_cast<double (*)[XP_BN * XP_LD]>(xp_smem + 2 * XP_BM * XP_LD);
+  constexpr int TILE = XP_BM * XP_LD;  // doubles per operand tile
+  double* As = xp_smem;                      // [XP_STAGES][TILE]
+  double* Bs = xp_smem + XP_STAGES * TILE;   // [XP_STAGES][TILE]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
   const int m0 = blockIdx.y * XP_BM, n0 = blockIdx.x * XP_BN;
   const long kb = static_cast<long>(blockIdx.z) * k_per_split;
   const long ke = min(Kdim, kb + k_per_split);
+  const int ntiles = kb < ke ? static_cast<int>((ke - kb + XP_BK - 1) / XP_BK) : 0;
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto load_tile = [&](int buf, long k0) {
-    // 128 rows x 16 k of A and of B -> smem [row][k] (k-stride XP_LD).  2048 elements each, 8 per thread.
+  // asynchronous tile load: 128 rows x 16 k of A and of B -> smem [row][k] (k-stride XP_LD)
+  auto issue_tile = [&](int slot, long k0) {
+    double* as = As + slot * TILE;
+    double* bs = Bs + slot * TILE;
     if (KMAJOR) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {  // 16-byte loads along k
-        const int idx = tid + e * 256;       // 0..1023 double2 slots
+      for (int e = 0; e < 4; ++e) {  // 16-byte copies along k (lda, ldb even; k0 even)
+        const int idx = tid + e * 256;
         const int row = idx >> 3, kk = (idx & 7) * 2;
-        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
         const long k = k0 + kk;
-        if (m0 + row < M) {
-          const double* pa = A + static_cast<size_t>(m0 + row) * lda + k;
-          if (k + 1 < ke) va = *reinterpret_cast<const double2*>(pa);
-          else if (k < ke) va.x = pa[0];
-        }
-        if (n0 + row < N) {
-          const double* pb = B + static_cast<size_t>(n0 + row) * ldb + k;
-          if (k + 1 < ke) vb = *reinterpret_cast<const double2*>(pb);
-          else if (k < ke) vb.x = pb[0];
-        }
-        As[buf][row * XP_LD + kk] = va.x;
-        As[buf][row * XP_LD + kk + 1] = va.y;
-        Bs[buf][row * XP_LD + kk] = vb.x;
-        Bs[buf][row * XP_LD + kk + 1] = vb.y;
+        const int kbytes = k + 1 < ke ? 16 : (k < ke ? 8 : 0);
+        const bool oka = (m0 + row < M) && kbytes > 0, okb = (n0 + row < N) && kbytes > 0;
+        cp_async16(as + row * XP_LD + kk, oka ? A + static_cast<size_t>(m0 + row) * lda + k : A, oka ? kbytes : 0);
+        cp_async16(bs + row * XP_LD + kk, okb ? B + static_cast<size_t>(n0 + row) * ldb + k : B, okb ? kbytes : 0);
       }
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {  // coalesced along the row (m / n) index
-        const int idx = tid + e * 256;       // 0..2047
+      for (int e = 0; e < 8; ++e) {  // 8-byte copies, coalesced along the row (m / n) index
+        const int idx = tid + e * 256;
         const int kk = idx >> 7, row = idx & 127;
         const long k = k0 + kk;
-        double va = 0.0, vb = 0.0;
-        if (k < ke) {
-          if (m0 + row < M) va = A[static_cast<size_t>(k) * lda + m0 + row];
-          if (n0 + row < N) vb = B[static_cast<size_t>(k) * ldb + n0 + row];
-        }
-        As[buf][row * XP_LD + kk] = va;
-        Bs[buf][row * XP_LD + kk] = vb;
+        const bool oka = (k < ke) && (m0 + row < M), okb = (k < ke) && (n0 + row < N);
+        cp_async8(as + row * XP_LD + kk, oka ? A + static_cast<size_t>(k) * lda + m0 + row : A, oka ? 8 : 0);
+        cp_async8(bs + row * XP_LD + kk, okb ? B + static_cast<size_t>(k) * ldb + n0 + row : B, okb ? 8 : 0);
       }
     }
   };
 
-  int buf = 0;
-  if (kb < ke) load_tile(0, kb);
-  __syncthreads();
-  for (long k0 = kb; k0 < ke; k0 += XP_BK) {
-    if (k0 + XP_BK < ke) load_tile(buf ^ 1, k0 + XP_BK);
-    const double* as = As[buf] + (wm * 64 + (lane >> 2)) * XP_LD + (lane & 3);
-    const double* bs = Bs[buf] + (wn * 32 + (lane >> 2)) * XP_LD + (lane & 3);
+#pragma unroll
+  for (int s = 0; s < XP_STAGES - 1; ++s) {
+    if (s < ntiles) issue_tile(s, kb + static_cast<long>(s) * XP_BK);
+    cp_async_commit();
+  }
+  for (int t = 0; t < ntiles; ++t) {
+    cp_async_wait<XP_STAGES - 2>();  // tile t has landed (this thread's copies) ...
+    __syncthreads();                 // ... and everybody's; also: everyone is done reading the slot refilled below
+    const int tn = t + XP_STAGES - 1;
+    if (tn < ntiles) issue_tile(tn % XP_STAGES, kb + static_cast<long>(tn) * XP_BK);
+    cp_async_commit();
+    const double* as = As + (t % XP_STAGES) * TILE + (wm * 64 + (lane >> 2)) * XP_LD + (lane & 3);
+    const double* bs = Bs + (t % XP_STAGES) * TILE + (wn * 32 + (lane >> 2)) * XP_LD + (lane & 3);
 #pragma unroll
     for (int ks = 0; ks < XP_BK; ks += 4) {
       double a[8], b[4];
@@ -217,9 +226,8 @@ crossprod_kernel(const double* __restrict__ A, long lda, const double* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();
-    buf ^= 1;
   }
+  cp_async_wait<0>();
   double* Cp = Cpart + static_cast<size_t>(blockIdx.z) * M * ldc;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -230,6 +238,30 @@ crossprod_kernel(const double* __restrict__ A, long lda, const double* __restric
       if (r < M) {
         if (c < N) Cp[static_cast<size_t>(r) * ldc + c] = acc[i][j][0];
         if (c + 1 < N) Cp[static_cast<size_t>(r) * ldc + c + 1] = acc[i][j][1];
+      }
+    }
+}
+
+// C[j][i] = C[i][j] for the 128x128 tiles strictly below the diagonal (completes a symmetric crossprod)
+__global__ void __launch_bounds__(256) symmetrize_kernel(double* __restrict__ C, long ldc, int M) {
+  const int bi = blockIdx.y, bj = blockIdx.x;  // destination tile (row block bi, col block bj), bj < bi
+  if (bj >= bi) return;
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int si = 0; si < XP_BM; si += 32)
+    for (int sj = 0; sj < XP_BN; sj += 32) {
+      // source element (r = bj*128+sj+.., c = bi*128+si+..) -> destination (c, r)
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = bj * XP_BM + sj + ty + 8 * k, c = bi * XP_BN + si + tx;
+        if (r < M && c < M) tile[ty + 8 * k][tx] = C[static_cast<size_t>(r) * ldc + c];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = bi * XP_BN + si + ty + 8 * k, r = bj * XP_BM + sj + tx;
+        if (r < M && c < M) C[static_cast<size_t>(c) * ldc + r] = tile[tx][ty + 8 * k];
       }
     }
 }
@@ -328,8 +360,18 @@ int mbpls_crossprod_splits(int M, int N, long Kdim) {
 
 // kmajor = 1: C = A B' with A (M x Kdim, lda), B (N x Kdim, ldb); kmajor = 0: C = A' B with A (Kdim x M), B (Kdim x N).
 // Cpart holds `splits` partial M x ldc matrices (splits = mbpls_crossprod_splits); reduce with mbpls_reduce_chunks_f64.
+int mbpls_symmetrize_f64(double* C, long ldc, int M, void* stream) {
+  if (!C || M < 1 || ldc < M) return MBPLS_ERR_ARG;
+  const int nb = (M + XP_BM - 1) / XP_BM;
+  if (nb < 2) return MBPLS_OK;
+  dim3 grid(nb, nb);
+  symmetrize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, ldc, M);
+  MBPLS_RETURN_LAST();
+}
+
 int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, int M, int N, long Kdim, int kmajor, int splits,
-                        double* Cpart, long ldc, void* stream) {
+                        double* Cpart, long ldc, int symmetric, void* stream) {
+  if (symmetric && (A != B || M != N)) return MBPLS_ERR_ARG;
   if (!A || !B || !Cpart || M < 1 || N < 1 || Kdim < 0 || splits < 1 || ldc < N) return MBPLS_ERR_ARG;
   if (kmajor && ((lda % 2) != 0 || (ldb % 2) != 0)) return MBPLS_ERR_ARG;
   long kps = (Kdim + splits - 1) / splits;
@@ -337,13 +379,13 @@ int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, in
   if (kps < XP_BK) kps = XP_BK;
   dim3 grid((N + XP_BN - 1) / XP_BN, (M + XP_BM - 1) / XP_BM, splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int smem = 2 * (XP_BM + XP_BN) * XP_LD * static_cast<int>(sizeof(double));
+  const int smem = XP_STAGES * (XP_BM + XP_BN) * XP_LD * static_cast<int>(sizeof(double));
   if (kmajor) {
     cudaFuncSetAttribute(crossprod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    crossprod_kernel<true><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc);
+    crossprod_kernel<true><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc, symmetric);
   } else {
     cudaFuncSetAttribute(crossprod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    crossprod_kernel<false><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc);
+    crossprod_kernel<false><<<grid, 256, smem, st>>>(A, lda, B, ldb, M, N, Kdim, kps, Cpart, ldc, symmetric);
   }
   MBPLS_RETURN_LAST();
 }
