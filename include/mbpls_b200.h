@@ -191,6 +191,15 @@ int mbpls_dense_gemv_f64(const double* A, long lda, int m, int ncols, const doub
 int mbpls_dense_rank2_f64(double* A, long lda, int m, int ncols, const double* x, const double* y, const double* scal,
                           double alpha, double beta, double gamma, int alpha_from, int gamma_from, void* stream);
 
+/* ---- small dense linear algebra of the per-component steps (single CTA, one-sided Jacobi SVD, m <= 64) ---- */
+/* out[0..m) = unit top eigenvector of the symmetric PSD m x m matrix G: np.linalg.svd(S)[0][:, 0:1] for
+ * S = C C' via the q x q matrix C'C (mbpls.py:398,:590,:1001) */
+int mbpls_small_top_eigvec_f64(const double* G, long ld, int m, double* out, void* stream);
+/* out = pinv(M) (m x m), singular values <= rcond * sigma_max dropped: np.linalg.pinv (:476,:569,:642,:734,:737,:988) */
+int mbpls_small_pinv_f64(const double* M, long ld, int m, double rcond, double* out, long ldo, void* stream);
+/* c with A c = top left singular vector of A B', given G = B'B and H = A'A: svd(XX'YY') (:491,:713) */
+int mbpls_small_top_sv_product_f64(const double* G, long ldg, const double* H, long ldh, int m, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,9 @@ SIGNATURES = {
     "mbpls_crossprod_splits": [_i, _i, _l],
     "mbpls_crossprod_f64": [_p, _l, _p, _l, _i, _i, _l, _i, _i, _p, _l, _i, _p],
     "mbpls_symmetrize_f64": [_p, _l, _i, _p],
+    "mbpls_small_top_eigvec_f64": [_p, _l, _i, _p, _p],
+    "mbpls_small_pinv_f64": [_p, _l, _i, _d, _p, _l, _p],
+    "mbpls_small_top_sv_product_f64": [_p, _l, _p, _l, _i, _p, _p],
     "mbpls_dense_gemv_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_dense_rank2_f64": [_p, _l, _i, _i, _p, _p, _p, _d, _d, _d, _i, _i, _p],
 }

@@ -8,7 +8,8 @@ Algebra that replaces the reference's dense p x p / n x n work (SURVEY.md sectio
   ``c = L z``, ``Y'Y = L L'``, ``z`` the top eigenvector of ``L' (A'A) L``  (:489-493, :704-715).
 * KERNEL sandwich deflations (:630-633, :722-725) are rank-1 / rank-2 updates because ``w'VAR = den * p`` and
   ``D = I - ts ts'`` is symmetric.
-Only q x q / K x K problems are solved on the host; every O(n p) or larger step is a kernel.
+The q x q / K x K eigen-problems and pseudo-inverses run on the device too (one-sided Jacobi SVD, csrc/smalllin.cu),
+so a fit enqueues asynchronously without per-component host round-trips.
 """
 from __future__ import annotations
 
@@ -124,26 +125,6 @@ def sum_rows(M, length):
     return out
 
 
-def top_eigvec(M: np.ndarray) -> np.ndarray:
-    M = 0.5 * (M + M.T)
-    w, V = np.linalg.eigh(M)
-    return V[:, -1]
-
-
-def top_left_sv_of_product(G: np.ndarray, H: np.ndarray) -> np.ndarray:
-    """c such that A c is the top left singular vector of A B' given G = B'B and H = A'A (both q x q)."""
-    G = 0.5 * (G + G.T)
-    lam, Q = np.linalg.eigh(G)
-    lam = np.clip(lam, 0.0, None)
-    L = Q * np.sqrt(lam)  # G = L L'
-    z = top_eigvec(L.T @ H @ L)
-    return L @ z
-
-
-def dev_from(a, device):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
-
-
 def _bip_corrected(a, sizes):
     a = np.asarray(a, dtype=np.float64).ravel()
     if a.size == 1:
@@ -205,9 +186,8 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
                            torch.zeros((K, max(p, 1)), dtype=F64, device=device))
     ldS = St.stride(0) if p > 0 else 1
     for k in range(K):
-        StS = E.gram(St, St, p, group).cpu().numpy()  # S'S, q x q (:1001)
-        qv = top_eigvec(StS)
-        r = E.right_multiply(St, p, None, dev_from(qv.reshape(q, 1), device))[0].contiguous()  # r = S q (:1004)
+        qv = E.small_top_eigvec(E.gram(St, St, p, group))  # top singular vector of S'S, q x q (:1001)
+        r = E.right_multiply(St, p, None, qv.view(q, 1))[0].contiguous()  # r = S q (:1004)
         W[k, :p] = r
         t = E.skinny_gemm(Xt, n, r.view(1, -1), shard.block_off, group)[0].contiguous()  # t = X r (:1006)
         normt = normalize_(t, n, center=True)  # :1007-1009
@@ -255,14 +235,17 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     Ts, U = torch.zeros((K, ld), dtype=F64, device=device), torch.zeros((K, ld), dtype=F64, device=device)
     V = torch.zeros((K, q), dtype=F64, device=device)
     Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
-    A = np.zeros((B, K))
     evx, evy, evxb = [], [], np.zeros((B, K))
-    GY = E.gram(Yt, Yt, n).cpu().numpy()
+    GY = E.gram(Yt, Yt, n)
+    A_dev = torch.zeros((K, B), dtype=F64, device=device)
+    pss_dev = torch.zeros((K, B), dtype=F64, device=device)
+    tt_dev = torch.zeros(K, dtype=F64, device=device)
+    vv_dev = torch.zeros(K, dtype=F64, device=device)
     for k in range(K):
         Ct = xt_multi(Xt, n, Yt).contiguous()  # (X'Y)' from the *deflated* X (:396 / :489)
         if n >= pg:  # :388-424
-            c = top_eigvec(E.gram(Ct, Ct, p, group).cpu().numpy())
-            w = E.right_multiply(Ct, p, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            c = E.small_top_eigvec(E.gram(Ct, Ct, p, group))
+            w = E.right_multiply(Ct, p, None, c.view(q, 1))[0].contiguous()
             normalize_over_features_(w, p, group)
             raw = blockprod(w)  # X_b w (un-normalised block part)
             ts = sum_rows(raw, ld)  # X w (:416)
@@ -274,9 +257,8 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
             normalize_(u, n)
         else:  # :481-517
             At = E.skinny_gemm(Xt, n, Ct, shard.block_off, group)  # (X X'Y)' : q x ld
-            H = E.gram(At, At, n).cpu().numpy()
-            c = top_left_sv_of_product(GY, H)
-            ts = E.right_multiply(At, ld, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            c = E.small_top_sv_product(GY, E.gram(At, At, n))
+            ts = E.right_multiply(At, ld, None, c.view(q, 1))[0].contiguous()
             normalize_(ts, n)
             tt = E.rows_sumsq(ts.view(1, -1), n)
             v = E.gram(Yt, ts.view(1, -1), n)[:, 0].contiguous()
@@ -291,18 +273,21 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         tb = raw.clone()
         scale_rows_(tb, n, torch.sqrt(a), True)  # t_b = X_b w_b (:410-413)
         pv = xt_vec(Xt, n, ts, boff_dev, B, uu=tt)  # p = X'ts / ts'ts (:427)
-        pssb = block_sumsq(pv, boff_dev, B, group).cpu().numpy()
-        ttf = float(tt.item())
-        evx.append(ttf * pssb.sum() / varxb.sum())
-        evxb[:, k] = ttf * pssb / varxb
-        evy.append(ttf * float((v * v).sum().item()) / vary)
+        pss_dev[k] = block_sumsq(pv, boff_dev, B, group)
+        tt_dev[k:k + 1] = tt
+        vv_dev[k:k + 1] = E.rows_sumsq(v.view(1, -1), q)
         rank1_update_(Xt, n, ts, pv)  # X <- X - ts p' (:443)
-        A[:, k] = a.cpu().numpy()
+        A_dev[k] = a
         Wc[k, :p], Wb[k, :p], P[k, :p], Ts[k], U[k], V[k] = w, wb, pv, ts, u, v
         Tb[:, k, :] = tb
+    A = A_dev.cpu().numpy().T.copy()
+    pssb_h, tt_h, vv_h = pss_dev.cpu().numpy(), tt_dev.cpu().numpy(), vv_dev.cpu().numpy()
+    for k in range(K):  # explained variances (:429-448): ((ts p')**2).sum() == ts'ts * p'p
+        evx.append(float(tt_h[k] * pssb_h[k].sum() / varxb.sum()))
+        evxb[:, k] = tt_h[k] * pssb_h[k] / varxb
+        evy.append(float(tt_h[k] * vv_h[k] / vary))
     Wc, Wb, P = Wc[:, :p], Wb[:, :p], P[:, :p]
-    PtW = E.gram(P, Wc, p, group)
-    M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+    M = E.small_pinv(E.gram(P, Wc, p, group))
     R = E.right_multiply(Wc, p, None, M)  # :476
     beta = E.right_multiply(R, p, None, V.contiguous())  # :477
     model.A_ = A
@@ -341,15 +326,15 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     Wc = torch.zeros((K, p), dtype=F64, device=device)
     Wb = torch.zeros((K, p), dtype=F64, device=device)
     U = torch.zeros((K, ld), dtype=F64, device=device)
-    A = np.zeros((B, K))
+    A_dev = torch.zeros((K, B), dtype=F64, device=device)
     if n >= p:  # Lindgren kernel (:580-650)
         COVt = xt_multi(Xt, n, Yt).contiguous()  # COVAR' : q x p (:587)
         ldv = (p + 15) // 16 * 16
         VAR = crossprod(Xt, Xt, p, p, n, True, ldv)  # X'X on the FP64 tensor cores (:586)
         scal = torch.zeros(4, dtype=F64, device=device)
         for k in range(K):
-            c = top_eigvec(E.gram(COVt, COVt, p).cpu().numpy())  # S = COVAR COVAR' (:584, :631)
-            w = E.right_multiply(COVt, p, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            c = E.small_top_eigvec(E.gram(COVt, COVt, p))  # S = COVAR COVAR' (:584, :631)
+            w = E.right_multiply(COVt, p, None, c.view(q, 1))[0].contiguous()
             normalize_over_features_(w, p, None)
             Vw = torch.zeros(p, dtype=F64, device=device)
             call("mbpls_dense_gemv_f64", ptr(VAR), ldv, p, p, ptr(w), ptr(Vw), st)
@@ -362,17 +347,15 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
             if calc_all:  # :601-627
                 a = block_sumsq(w, boff_dev, B, None)
                 Wb[k] = scale_by_block(w, boff_dev, B, a, p)
-                A[:, k] = a.cpu().numpy()
-                vv = float((v * v).sum().item())
-                u = E.skinny_gemm(Yt, n, (v / vv).contiguous().view(1, -1), [0, q])[0].contiguous()
-                normalize_(u, n)
+                A_dev[k] = a
+                u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # Y v' / (v v') up to the scale ...
+                normalize_(u, n)  # ... which the normalisation removes (:624-625)
                 U[k] = u
             # COVAR <- D'COVAR, VAR <- D'VAR D = VAR - den p'p  (:630-633)
             call("mbpls_rank1_update_f64", ptr(COVt), COVt.stride(0), p, q, ptr(pv), ptr(wC), st)
             call("mbpls_dense_rank2_f64", ptr(VAR), ldv, p, p, ptr(pv), ptr(pv), ptr(scal), 0.0, 0.0, -1.0, -1, 0, st)
             V[k], P[k], Wc[k] = v, pv, w
-        PtW = E.gram(P, Wc, p)
-        M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+        M = E.small_pinv(E.gram(P, Wc, p))
         R = E.right_multiply(Wc, p, None, M)  # :642
         beta = E.right_multiply(R, p, None, V.contiguous())  # :643
         Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # Ts = X R (:644)
@@ -387,10 +370,8 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         scal = torch.zeros(4, dtype=F64, device=device)
         for k in range(K):
             At = E.skinny_gemm(AX[:, :], n, Yc, [0, n])  # (AS_X Y)' : q x ld;  S = AS_X AS_Y = (AS_X Y) Y' (:707, :725)
-            G = E.gram(Yc, Yc, n).cpu().numpy()
-            H = E.gram(At, At, n).cpu().numpy()
-            c = top_left_sv_of_product(G, H)
-            ts = E.right_multiply(At, ld, None, dev_from(c.reshape(q, 1), device))[0].contiguous()
+            c = E.small_top_sv_product(E.gram(Yc, Yc, n), E.gram(At, At, n))
+            ts = E.right_multiply(At, ld, None, c.view(q, 1))[0].contiguous()
             ts[n:] = 0.0
             normalize_(ts, n)  # :713
             yt = E.gram(Yc, ts.view(1, -1), n)[:, 0].contiguous()  # Y'ts
@@ -406,12 +387,11 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         Wc = xt_multi(Xt, n, U).contiguous()  # X'U (:731)
         wn = torch.sqrt(E.rows_sumsq(Wc, p))
         scale_rows_(Wc, p, wn, True)  # :733
-        Gt = np.linalg.pinv(E.gram(Ts, Ts, n).cpu().numpy())
+        Gt = E.small_pinv(E.gram(Ts, Ts, n))  # (Ts'Ts)^+, K x K
         XtTs = xt_multi(Xt, n, Ts).contiguous()
-        P = E.right_multiply(XtTs, p, None, dev_from(Gt, device)).contiguous()  # :734
-        V = dev_from((E.gram(Yt, Ts, n).cpu().numpy() @ Gt).T, device)  # :735  (K x q)
-        PtW = E.gram(P, Wc, p)
-        M = dev_from(np.linalg.pinv(PtW.cpu().numpy()), device)
+        P = E.right_multiply(XtTs, p, None, Gt).contiguous()  # :734
+        V = E.right_multiply(E.gram(Ts, Yt, n).contiguous(), q, None, Gt).contiguous()  # Y'Ts (Ts'Ts)^+ as K x q (:735)
+        M = E.small_pinv(E.gram(P, Wc, p))
         R = E.right_multiply(Wc, p, None, M)  # :737
         beta = E.right_multiply(R, p, None, V.contiguous())  # :738
     Tb = None
@@ -424,18 +404,23 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         blockprod = BlockProducts(Xt, n, shard.block_off, None)
         Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
         evxb = np.zeros((B, K))
+        pss_dev = torch.zeros((K, B), dtype=F64, device=device)
         for k in range(K):
             if n < p:
                 a = block_sumsq(Wc[k].contiguous(), boff_dev, B, None)
                 Wb[k] = scale_by_block(Wc[k].contiguous(), boff_dev, B, a, p)
-                A[:, k] = a.cpu().numpy()
+                A_dev[k] = a
             Tb[:, k, :] = blockprod(Wb[k].contiguous())
-            tt = float(E.rows_sumsq(Ts[k:k + 1], n).item())
-            pssb = block_sumsq(P[k].contiguous(), boff_dev, B, None).cpu().numpy()
-            evx.append(tt * pssb.sum() / varxb.sum())
-            evxb[:, k] = tt * pssb / varxb
-            evy.append(tt * float((V[k] * V[k]).sum().item()) / vary)
+            pss_dev[k] = block_sumsq(P[k].contiguous(), boff_dev, B, None)
             rank1_update_(Xt, n, Ts[k].contiguous(), P[k].contiguous())
+        tt_h = E.rows_sumsq(Ts, n).cpu().numpy()
+        vv_h = E.rows_sumsq(V.contiguous(), q).cpu().numpy()
+        pssb_h = pss_dev.cpu().numpy()
+        for k in range(K):  # ((Ts_k P_k')**2).sum() == Ts_k'Ts_k * P_k'P_k (:669-689)
+            evx.append(float(tt_h[k] * pssb_h[k].sum() / varxb.sum()))
+            evxb[:, k] = tt_h[k] * pssb_h[k] / varxb
+            evy.append(float(tt_h[k] * vv_h[k] / vary))
+        A = A_dev.cpu().numpy().T.copy()
         model.A_ = A
         model.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
     else:

@@ -514,3 +514,33 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         call("mbpls_reduce_chunks_f64", ptr(part), ns, Cc * ld, ptr(out), stream_ptr(dev))
     allreduce_(out, group)
     return out
+
+
+# --------------------------------------------------------------------------------------------- #
+# small dense linear algebra on the device (csrc/smalllin.cu)
+# --------------------------------------------------------------------------------------------- #
+def small_top_eigvec(G: torch.Tensor) -> torch.Tensor:
+    """Unit top eigenvector of a symmetric PSD m x m matrix (m <= 64)."""
+    m = G.shape[0]
+    G = G.contiguous()
+    out = torch.empty(m, dtype=F64, device=G.device)
+    call("mbpls_small_top_eigvec_f64", ptr(G), G.stride(0), m, ptr(out), stream_ptr(G.device))
+    return out
+
+
+def small_pinv(M: torch.Tensor, rcond: float = 1e-15) -> torch.Tensor:
+    """Moore-Penrose pseudo-inverse of an m x m matrix (numpy.linalg.pinv semantics, m <= 64)."""
+    m = M.shape[0]
+    M = M.contiguous()
+    out = torch.empty((m, m), dtype=F64, device=M.device)
+    call("mbpls_small_pinv_f64", ptr(M), M.stride(0), m, float(rcond), ptr(out), out.stride(0), stream_ptr(M.device))
+    return out
+
+
+def small_top_sv_product(G: torch.Tensor, H: torch.Tensor) -> torch.Tensor:
+    """c such that A c is the top left singular vector of A B', from G = B'B and H = A'A."""
+    m = G.shape[0]
+    G, H = G.contiguous(), H.contiguous()
+    out = torch.empty(m, dtype=F64, device=G.device)
+    call("mbpls_small_top_sv_product_f64", ptr(G), G.stride(0), ptr(H), H.stride(0), m, ptr(out), stream_ptr(G.device))
+    return out

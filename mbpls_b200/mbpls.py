@@ -360,7 +360,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         Wt, P = res.Wt[:, :p_loc], res.P[:, :p_loc]
         colnorm = torch.sqrt(E.rows_sumsq(Wt, p_loc, group))
         PtW = E.gram(P, Wt, p_loc, group) / colnorm.view(1, -1)
-        M = torch.from_numpy(np.linalg.pinv(PtW.cpu().numpy())).to(device)  # K x K control step on the host
+        M = E.small_pinv(PtW)  # pinv(P'W), K x K, one-sided Jacobi SVD on the device (:988)
         R = E.right_multiply(Wt, p_loc, 1.0 / colnorm, M)
         beta = E.right_multiply(R, p_loc, None, res.V[:, :q].contiguous())
         self.__dict__["_dev"] = dict(shard=shard, R=R, beta=beta, W=res.W[:, :p_loc], P=P, V=res.V[:, :q])

@@ -113,3 +113,31 @@ def test_crossprod_dmma_matches_numpy():
         assert rel_err(G, A @ A.T) < 1e-13
         H = CM.crossprod(Xt, Xt, n, n, p, False, Xt.shape[1])[:, :n].cpu().numpy()
         assert rel_err(H, A.T @ A) < 1e-13
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 7, 20, 33, 64])
+def test_small_device_linear_algebra_matches_numpy(m):
+    """One-sided Jacobi kernels (csrc/smalllin.cu) against numpy: top eigenvector of a PSD matrix, pinv of a general
+    (also rank-deficient / ill-conditioned) matrix, top left singular vector of A B' from the two Gram matrices."""
+    import torch
+    from mbpls_b200 import engine as E
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(m)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    C = rng.standard_normal((m + 5, m)) * (0.5 ** np.arange(m))
+    G = C.T @ C
+    v = E.small_top_eigvec(t(G)).cpu().numpy()
+    ref = np.linalg.svd(G)[0][:, 0]
+    assert min(rel_err(v, ref), rel_err(-v, ref)) < 1e-10
+    M = rng.standard_normal((m, m)) + np.triu(np.ones((m, m)))
+    assert rel_err(E.small_pinv(t(M)).cpu().numpy(), np.linalg.pinv(M)) < 1e-9
+    if m > 2:  # rank deficient
+        Md = M.copy()
+        Md[:, -1] = Md[:, 0] + Md[:, 1]
+        assert rel_err(E.small_pinv(t(Md)).cpu().numpy(), np.linalg.pinv(Md)) < 1e-8
+    A, Bm = rng.standard_normal((40 + m, m)), rng.standard_normal((40 + m, m))
+    c = E.small_top_sv_product(t(Bm.T @ Bm), t(A.T @ A)).cpu().numpy()
+    u = A @ c
+    u /= np.linalg.norm(u)
+    uref = np.linalg.svd(A @ Bm.T)[0][:, 0]
+    assert min(rel_err(u, uref), rel_err(-u, uref)) < 1e-9
