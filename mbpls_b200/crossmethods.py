@@ -315,10 +315,12 @@ def crossprod(A, Bm, M, N, Kdim, kmajor, ldc):
 
 
 def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
-    if group is not None:
-        raise NotImplementedError("method='KERNEL' is single-GPU in this round (row-sharded variant: SURVEY.md 8e)")
     K, B = int(model.n_components), len(shard.sizes)
     p, ld = Xt.shape
+    pg = shard.p_global
+    if group is not None and n >= pg:
+        raise NotImplementedError("method='KERNEL' with n >= p needs the row-sharded variant (p x p all-reduce, "
+                                  "SURVEY.md 8e), which is not built yet; feature sharding covers the p > n branch")
     st = stream_ptr(device)
     calc_all = bool(model.calc_all)
     V = torch.zeros((K, q), dtype=F64, device=device)
@@ -327,7 +329,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     Wb = torch.zeros((K, p), dtype=F64, device=device)
     U = torch.zeros((K, ld), dtype=F64, device=device)
     A_dev = torch.zeros((K, B), dtype=F64, device=device)
-    if n >= p:  # Lindgren kernel (:580-650)
+    if n >= pg:  # Lindgren kernel (:580-650)
         COVt = xt_multi(Xt, n, Yt).contiguous()  # COVAR' : q x p (:587)
         ldv = (p + 15) // 16 * 16
         VAR = crossprod(Xt, Xt, p, p, n, True, ldv)  # X'X on the FP64 tensor cores (:586)
@@ -364,7 +366,8 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         scale_rows_(P, p, nrm, False)
         scale_rows_(Ts, n, nrm, True)
     else:  # Rannar kernel (:694-738)
-        AX = crossprod(Xt, Xt, n, n, p, False, ld)  # X X' on the FP64 tensor cores (:704)
+        AX = crossprod(Xt, Xt, n, n, p, False, ld)  # X X' on the FP64 tensor cores (:704); features sharded:
+        E.allreduce_(AX, group)                     # one n x n all-reduce of the partial association matrices
         Yc = Yt.clone()
         Ts = torch.zeros((K, ld), dtype=F64, device=device)
         scal = torch.zeros(4, dtype=F64, device=device)
@@ -385,13 +388,14 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
             call("mbpls_rank1_update_f64", ptr(Yc), ld, n, q, ptr(ts), ptr(yt), st)
             U[k], Ts[k] = u, ts
         Wc = xt_multi(Xt, n, U).contiguous()  # X'U (:731)
-        wn = torch.sqrt(E.rows_sumsq(Wc, p))
-        scale_rows_(Wc, p, wn, True)  # :733
+        wn = torch.sqrt(E.rows_sumsq(Wc, p, group))
+        if p > 0:
+            scale_rows_(Wc, p, wn, True)  # :733
         Gt = E.small_pinv(E.gram(Ts, Ts, n))  # (Ts'Ts)^+, K x K
         XtTs = xt_multi(Xt, n, Ts).contiguous()
         P = E.right_multiply(XtTs, p, None, Gt).contiguous()  # :734
         V = E.right_multiply(E.gram(Ts, Yt, n).contiguous(), q, None, Gt).contiguous()  # Y'Ts (Ts'Ts)^+ as K x q (:735)
-        M = E.small_pinv(E.gram(P, Wc, p))
+        M = E.small_pinv(E.gram(P, Wc, p, group))
         R = E.right_multiply(Wc, p, None, M)  # :737
         beta = E.right_multiply(R, p, None, V.contiguous())  # :738
     Tb = None
@@ -399,19 +403,19 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     if calc_all:  # :653-689 / :740-802
         if zss is None:
             zss = E.feature_sumsq(Xt, n)
-        varxb = model._block_sums(zss, boff_dev, B, None)
+        varxb = model._block_sums(zss, boff_dev, B, group)
         vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
-        blockprod = BlockProducts(Xt, n, shard.block_off, None)
+        blockprod = BlockProducts(Xt, n, shard.block_off, group)
         Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
         evxb = np.zeros((B, K))
         pss_dev = torch.zeros((K, B), dtype=F64, device=device)
         for k in range(K):
-            if n < p:
-                a = block_sumsq(Wc[k].contiguous(), boff_dev, B, None)
+            if n < pg:
+                a = block_sumsq(Wc[k].contiguous(), boff_dev, B, group)
                 Wb[k] = scale_by_block(Wc[k].contiguous(), boff_dev, B, a, p)
                 A_dev[k] = a
             Tb[:, k, :] = blockprod(Wb[k].contiguous())
-            pss_dev[k] = block_sumsq(P[k].contiguous(), boff_dev, B, None)
+            pss_dev[k] = block_sumsq(P[k].contiguous(), boff_dev, B, group)
             rank1_update_(Xt, n, Ts[k].contiguous(), P[k].contiguous())
         tt_h = E.rows_sumsq(Ts, n).cpu().numpy()
         vv_h = E.rows_sumsq(V.contiguous(), q).cpu().numpy()
@@ -433,5 +437,5 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     if not calc_all:
         extra["W_"] = lambda: [np.empty((s, 0)) for s in shard.sizes]
         extra["T_"] = lambda: [np.empty((n, 0)) for _ in shard.sizes]
-        extra["U_"] = (lambda: np.empty((n, 0))) if n >= p else (lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T))
+        extra["U_"] = (lambda: np.empty((n, 0))) if n >= pg else (lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T))
     _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb if calc_all else None, Tb, extra)

@@ -41,6 +41,19 @@ def gpu_checks(group, rank, world, dev):
             m2.fit(local, Y.copy())
         assert np.allclose(m2.beta_, m.beta_, rtol=1e-11, atol=1e-14), "pre-sharded fit differs"
         print(f"rank {rank}: world={world} nan={nan_frac} n={n} trips={m.n_iter_} worst={worst}", flush=True)
+    # the other methods under the same feature sharding (KERNEL: the p > n branch; n >= p needs row sharding)
+    for method, n in (("SIMPLS", 400), ("UNIPALS", 400), ("UNIPALS", 1200), ("KERNEL", 400)):
+        sizes = (300, 50, 450)
+        X, Y = latent_blocks(n, sizes, 3, 4, seed=50 + n)
+        Xt, Yt = latent_blocks(13, sizes, 3, 4, seed=6)
+        kw = dict(n_components=4, method=method, full_svd=True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = OracleMBPLS(**kw).fit([x.copy() for x in X], Y.copy())
+            m = MBPLS(**kw).set_runtime(group=group, device=dev)
+            m.fit([x.copy() for x in X], Y.copy())
+        worst = compare(snapshot_model(m, Xt, Yt), snapshot_model(o, Xt, Yt), 1e-8, f"rank {rank} {method} n={n}")
+        print(f"rank {rank}: world={world} {method} n={n} worst={worst}", flush=True)
 
 
 def host_checks(group, rank, world):
