@@ -70,6 +70,9 @@ int mbpls_standardize_apply_f64(double* Xt, long ld, int n, int p, const double*
 int mbpls_scaler_inverse_f64(double* Zt, long ld, int n, int q, const double* mean, const double* scale, void* stream);
 /* nansum(x_j^2) per feature: (X**2).sum() / np.nansum (mbpls.py:826-830, :943-945) */
 int mbpls_feature_sumsq_f64(const double* Xt, long ld, int n, int p, double* out, void* stream);
+/* row-sharded StandardScaler: var_/scale_ from the all-reduced centred sums sum(x-mean), sum((x-mean)^2) */
+int mbpls_scaler_finish_f64(const double* corr, const double* ssq, const double* mean, double count, double* var, double* scale,
+                            int p, void* stream);
 /* deterministic segmented sum out[s] = sum v[off[s]:off[s+1]] */
 int mbpls_segsum_f64(const double* v, const int* off, int nseg, double* out, void* stream);
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mbpls_standardize_apply_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_scaler_inverse_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_feature_sumsq_f64": [_p, _l, _i, _i, _p, _p],
+    "mbpls_scaler_finish_f64": [_p, _p, _p, _d, _p, _p, _i, _p],
     "mbpls_segsum_f64": [_p, _p, _i, _p, _p],
     "mbpls_xtu_feats_per_cta": [_i],
     "mbpls_xtu_num_ctas": [_i],

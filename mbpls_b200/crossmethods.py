@@ -143,8 +143,8 @@ def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=
         return [np.ascontiguousarray(full[:, bounds[b]:bounds[b + 1]].T) for b in range(B)]
 
     lazy = {
-        "Ts_": lambda: np.ascontiguousarray(Ts[:, :n].cpu().numpy().T),
-        "U_": lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T) if U is not None else np.empty((n, 0)),
+        "Ts_": lambda: model._gather_samples(Ts, n),
+        "U_": lambda: model._gather_samples(U, n) if U is not None else np.empty((n, 0)),
         "V_": lambda: np.ascontiguousarray(V.cpu().numpy().T),
         "P_": lambda: split_T(model._gather_features(P, shard)),
         "R_": lambda: np.ascontiguousarray(model._gather_features(R, shard).T),
@@ -153,7 +153,7 @@ def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=
     if Wb is not None:
         lazy["W_"] = lambda: split_T(model._gather_features(Wb, shard))
     if Tb is not None:
-        lazy["T_"] = lambda: [np.ascontiguousarray(Tb[b, :, :n].cpu().numpy().T) for b in range(B)]
+        lazy["T_"] = lambda: [model._gather_samples(Tb[b], n) for b in range(B)]
     if lazy_extra:
         lazy.update(lazy_extra)
     model.__dict__["_lazy"] = lazy
@@ -314,13 +314,24 @@ def crossprod(A, Bm, M, N, Kdim, kmajor, ldc):
     return out
 
 
-def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
+def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_group=None, n_global=None):
+    """rows_group: the SAMPLE axis is sharded over this group (Xt / Yt hold this rank's n rows of all features);
+    sums over samples are all-reduced (p x p + p x q partial cross-products), everything indexed by
+    features is replicated, everything indexed by samples stays row-local."""
     K, B = int(model.n_components), len(shard.sizes)
     p, ld = Xt.shape
     pg = shard.p_global
-    if group is not None and n >= pg:
-        raise NotImplementedError("method='KERNEL' with n >= p needs the row-sharded variant (p x p all-reduce, "
-                                  "SURVEY.md 8e), which is not built yet; feature sharding covers the p > n branch")
+    rg = rows_group
+    ng = n if n_global is None else n_global
+    if group is not None and rg is None and ng >= pg:
+        raise NotImplementedError("feature-sharded KERNEL covers p > n; n >= p uses the row-sharded path")
+
+    def normalize_rows_(t):  # unit norm over the *global* sample axis
+        if rg is None:
+            return normalize_(t, n)
+        nrm = torch.sqrt(E.rows_sumsq(t.view(1, -1), n, rg))
+        scale_rows_(t.view(1, -1), n, nrm, True)
+        return nrm
     st = stream_ptr(device)
     calc_all = bool(model.calc_all)
     V = torch.zeros((K, q), dtype=F64, device=device)
@@ -329,10 +340,12 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     Wb = torch.zeros((K, p), dtype=F64, device=device)
     U = torch.zeros((K, ld), dtype=F64, device=device)
     A_dev = torch.zeros((K, B), dtype=F64, device=device)
-    if n >= pg:  # Lindgren kernel (:580-650)
+    if ng >= pg:  # Lindgren kernel (:580-650)
         COVt = xt_multi(Xt, n, Yt).contiguous()  # COVAR' : q x p (:587)
         ldv = (p + 15) // 16 * 16
         VAR = crossprod(Xt, Xt, p, p, n, True, ldv)  # X'X on the FP64 tensor cores (:586)
+        E.allreduce_(COVt, rg)  # row-sharded: partial cross-products of this rank's samples
+        E.allreduce_(VAR, rg)
         scal = torch.zeros(4, dtype=F64, device=device)
         for k in range(K):
             c = E.small_top_eigvec(E.gram(COVt, COVt, p))  # S = COVAR COVAR' (:584, :631)
@@ -351,7 +364,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
                 Wb[k] = scale_by_block(w, boff_dev, B, a, p)
                 A_dev[k] = a
                 u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # Y v' / (v v') up to the scale ...
-                normalize_(u, n)  # ... which the normalisation removes (:624-625)
+                normalize_rows_(u)  # ... which the normalisation removes (:624-625)
                 U[k] = u
             # COVAR <- D'COVAR, VAR <- D'VAR D = VAR - den p'p  (:630-633)
             call("mbpls_rank1_update_f64", ptr(COVt), COVt.stride(0), p, q, ptr(pv), ptr(wC), st)
@@ -361,7 +374,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         R = E.right_multiply(Wc, p, None, M)  # :642
         beta = E.right_multiply(R, p, None, V.contiguous())  # :643
         Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # Ts = X R (:644)
-        nrm = torch.sqrt(E.rows_sumsq(Ts, n))  # :646-650
+        nrm = torch.sqrt(E.rows_sumsq(Ts, n, rg))  # :646-650
         scale_rows_(V, q, nrm, False)
         scale_rows_(P, p, nrm, False)
         scale_rows_(Ts, n, nrm, True)
@@ -403,8 +416,10 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     if calc_all:  # :653-689 / :740-802
         if zss is None:
             zss = E.feature_sumsq(Xt, n)
-        varxb = model._block_sums(zss, boff_dev, B, group)
-        vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
+        varxb = model._block_sums(zss, boff_dev, B, group if rg is None else rg)
+        vary_t = E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).clone()
+        E.allreduce_(vary_t, rg)
+        vary = float(vary_t.item())
         blockprod = BlockProducts(Xt, n, shard.block_off, group)
         Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
         evxb = np.zeros((B, K))
@@ -417,7 +432,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
             Tb[:, k, :] = blockprod(Wb[k].contiguous())
             pss_dev[k] = block_sumsq(P[k].contiguous(), boff_dev, B, group)
             rank1_update_(Xt, n, Ts[k].contiguous(), P[k].contiguous())
-        tt_h = E.rows_sumsq(Ts, n).cpu().numpy()
+        tt_h = E.rows_sumsq(Ts, n, rg).cpu().numpy()
         vv_h = E.rows_sumsq(V.contiguous(), q).cpu().numpy()
         pssb_h = pss_dev.cpu().numpy()
         for k in range(K):  # ((Ts_k P_k')**2).sum() == Ts_k'Ts_k * P_k'P_k (:669-689)
@@ -436,6 +451,6 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     extra = {"W_concat_": lambda: np.ascontiguousarray(model._gather_features(Wc_keep, shard).T)}
     if not calc_all:
         extra["W_"] = lambda: [np.empty((s, 0)) for s in shard.sizes]
-        extra["T_"] = lambda: [np.empty((n, 0)) for _ in shard.sizes]
-        extra["U_"] = (lambda: np.empty((n, 0))) if n >= pg else (lambda: np.ascontiguousarray(U[:, :n].cpu().numpy().T))
+        extra["T_"] = lambda: [np.empty((ng, 0)) for _ in shard.sizes]
+        extra["U_"] = (lambda: np.empty((ng, 0))) if ng >= pg else (lambda: model._gather_samples(U, n))
     _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb if calc_all else None, Tb, extra)

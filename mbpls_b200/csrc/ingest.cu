@@ -373,6 +373,18 @@ __global__ void __launch_bounds__(256) feature_sumsq_kernel(const double* __rest
   }
 }
 
+// Row-sharded standardisation (samples split over GPUs): the per-feature sums are all-reduced between passes, this
+// finishes var_ / scale_ from the centred sums exactly like scale_from() does for the single-GPU kernels.
+__global__ void __launch_bounds__(256)
+scaler_finish_kernel(const double* __restrict__ corr, const double* __restrict__ ssq, const double* __restrict__ mean, double cnt,
+                     double* __restrict__ var, double* __restrict__ scale, int p) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  double v;
+  scale[j] = scale_from(cnt, mean[j], corr[j], ssq[j], v);
+  var[j] = v;
+}
+
 // Deterministic segmented sum: out[s] = sum(v[off[s] .. off[s+1])), one CTA per segment.
 __global__ void __launch_bounds__(256) segsum_kernel(const double* __restrict__ v, const int* __restrict__ off,
                                                      double* __restrict__ out) {
@@ -485,6 +497,14 @@ int mbpls_feature_sumsq_f64(const double* Xt, long ld, int n, int p, double* out
   int grid = (p + 7) / 8;
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   feature_sumsq_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, out);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_scaler_finish_f64(const double* corr, const double* ssq, const double* mean, double count, double* var, double* scale,
+                            int p, void* stream) {
+  if (!corr || !ssq || !mean || !var || !scale || count <= 0) return MBPLS_ERR_ARG;
+  if (p <= 0) return MBPLS_OK;
+  scaler_finish_kernel<<<(p + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(corr, ssq, mean, count, var, scale, p);
   MBPLS_RETURN_LAST();
 }
 

@@ -140,7 +140,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
     def _gather_features(self, t_local: torch.Tensor, shard: ShardMap) -> np.ndarray:
         """K x p_local device tensor -> K x p_global numpy array (same on every rank)."""
         group, rank, world = self._group_info()
-        if world == 1:
+        if world == 1 or shard.world == 1:  # single GPU, or feature axis replicated (row-sharded fit)
             return t_local[:, :shard.p_local].cpu().numpy()
         import torch.distributed as dist
         per = -(-shard.p_global // world)
@@ -151,6 +151,22 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         dist.all_gather(parts, pad, group=group)
         full = torch.cat(parts, dim=1)[:, :shard.p_global]
         return full.cpu().numpy()
+
+    def _gather_samples(self, t: torch.Tensor, n_local: int) -> np.ndarray:
+        """K x ld device tensor of per-sample results -> n x K numpy array; concatenates the row shards when the
+        sample axis is sharded (row-sharded KERNEL fit), plain copy otherwise."""
+        rows = self.__dict__.get("_rows")
+        if rows is None:
+            return np.ascontiguousarray(t[:, :n_local].cpu().numpy().T)
+        import torch.distributed as dist
+        group, counts = rows
+        K, mx = t.shape[0], max(counts)
+        pad = torch.zeros((K, mx), dtype=t.dtype, device=t.device)
+        pad[:, :n_local] = t[:, :n_local]
+        parts = [torch.empty_like(pad) for _ in counts]
+        dist.all_gather(parts, pad, group=group)
+        full = torch.cat([pt[:, :c] for pt, c in zip(parts, counts)], dim=1)
+        return np.ascontiguousarray(full.cpu().numpy().T)
 
     # ------------------------------------------------------------------ NaN census (mbpls.py:255-271)
     def check_sparsity_level(self, data):
@@ -215,6 +231,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_lazy"] = None
         self.__dict__["_dev"] = None
         self.__dict__["_dev_scalers"] = None
+        self.__dict__["_rows"] = None
+
+        if self.method == 'KERNEL' and world > 1:
+            blocks0 = X if _is_block_list(X) else [X]
+            n0, p0 = int(_shape2(blocks0[0])[0]), sum(int(_shape2(b)[1]) for b in blocks0)
+            if n0 >= p0 and rt["global_sizes"] is None:
+                with torch.cuda.device(device):
+                    self._fit_kernel_row_sharded(X, Y, group, rank, world, device)
+                if rt["materialize"]:
+                    self._materialize_all()
+                return self
 
         with torch.cuda.device(device):
             # ---- Y (mbpls.py:293-298)
@@ -266,6 +293,73 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         if rt["materialize"]:
             self._materialize_all()
         return self
+
+    # ---- KERNEL with n >= p on several GPUs: shard the SAMPLE axis
+    def _fit_kernel_row_sharded(self, X, Y, group, rank, world, device):
+        """Every rank ingests its contiguous range of samples of all blocks; column statistics and the p x p / p x q
+        cross-products are all-reduced; the per-component p x p loop runs replicated; scores stay row-local."""
+        from . import crossmethods as CM
+        blocks = X if _is_block_list(X) else [X]
+        blocks = [_as_2d_source(b, "X") for b in blocks]
+        Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
+        if Ysrc.ndim == 1:
+            Ysrc = Ysrc.reshape(-1, 1)
+        Ysrc = _as_2d_source(Ysrc, "Y")
+        n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
+        for b in blocks:
+            if int(b.shape[0]) != n:
+                raise ValueError("Found input variables with inconsistent numbers of samples: %r" % [int(b.shape[0]), n])
+        per = -(-n // world)
+        counts = [max(0, min(n, (r + 1) * per) - min(n, r * per)) for r in range(world)]
+        r0 = min(n, rank * per)
+        nl = counts[rank]
+        if min(counts) < 1:
+            raise ValueError("fewer samples than GPUs")
+        sizes = [int(b.shape[1]) for b in blocks]
+        shard = ShardMap.build(sizes, 0, 1)  # the feature axis is replicated
+        Xt = E.ingest_blocks([b[r0:r0 + nl] for b in blocks], nl, shard, device)
+        Yt = E.alloc_feature_major(q, nl, device)
+        E.ingest_feature_major(Ysrc[r0:r0 + nl], nl, 0, q, Yt, device)
+        B, p, ld = len(sizes), shard.p_local, Xt.shape[1]
+        boff_dev = E._i32(shard.block_off, device)
+        self.__dict__["_rows"] = (group, counts)
+        ones = torch.zeros(ld, dtype=F64, device=device)
+        ones[:nl] = 1.0
+
+        def standardize_rows(Mt, feats, one_off):
+            """StandardScaler.fit_transform with the sums over samples all-reduced (two-pass, like sklearn)."""
+            tot = CM.xt_vec(Mt, nl, ones, one_off, 1).clone()
+            E.allreduce_(tot, group)
+            cnt = torch.full((1,), float(n), dtype=F64, device=device)
+            mean = tot.clone()
+            CM.scale_rows_(mean.view(1, -1), feats, cnt, True)
+            CM.rank1_update_(Mt, nl, ones, mean)  # x <- x - mean
+            corr = CM.xt_vec(Mt, nl, ones, one_off, 1).clone()
+            ssq = E.feature_sumsq(Mt, nl)[:feats].clone()
+            E.allreduce_(corr, group)
+            E.allreduce_(ssq, group)
+            var, scale = torch.empty_like(mean), torch.empty_like(mean)
+            call("mbpls_scaler_finish_f64", ptr(corr), ptr(ssq), ptr(mean), float(n), ptr(var), ptr(scale), feats,
+                 stream_ptr(device))
+            E.standardize_apply(Mt, nl, torch.zeros_like(mean), scale)
+            return mean, var, scale
+
+        zss = None
+        ok = bool(torch.isfinite(Xt).all()) and bool(torch.isfinite(Yt).all())
+        self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
+        if self.standardize:
+            xm, xv, xs = standardize_rows(Xt, p, E._i32([0, p], device))
+            ym, yv, ys = standardize_rows(Yt, q, E._i32([0, q], device))
+            seen = np.full(p, n, dtype=np.int64)
+            xm_h, xv_h, xs_h = xm.cpu().numpy(), xv.cpu().numpy(), xs.cpu().numpy()
+            self.x_scalers_, g0 = [], 0
+            for pb in sizes:
+                self.x_scalers_.append(_make_scaler(xm_h[g0:g0 + pb], xv_h[g0:g0 + pb], xs_h[g0:g0 + pb], seen[g0:g0 + pb]))
+                g0 += pb
+            self.y_scaler_ = _make_scaler(ym.cpu().numpy(), yv.cpu().numpy(), ys.cpu().numpy(), np.full(q, n, dtype=np.int64))
+            self.__dict__["_dev_scalers"] = (xm, xs, ym, ys)
+        self.num_blocks_ = B
+        CM._fit_kernel(self, Xt, Yt, nl, q, shard, boff_dev, zss, None, device, rows_group=group, n_global=n)
 
     # ---- helpers of fit
     def _raise_if_any_rank(self, bad: bool, msg: str, group):
@@ -414,6 +508,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         if dev is not None and dev["R"].device == device:
             return dev
         _, rank, world = self._group_info()
+        if self.__dict__.get("_rows") is not None:
+            rank, world = 0, 1
         P_ = self.P_
         sizes = [int(pb.shape[0]) for pb in P_]
         shard = ShardMap.build(sizes, rank, world)
@@ -468,6 +564,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         group, _, _ = self._group_info()
         with torch.cuda.device(device):
             dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=False)
+            if shard.world == 1:
+                group = None  # model replicated on every rank (single GPU or row-sharded fit): no collective
             q = dev["beta"].shape[0]
             flag = torch.zeros(1, dtype=torch.int32, device=device)
             Yh = E.skinny_gemm(Xt, m, dev["beta"], shard.block_off, group, mean, scale, flag)
@@ -485,6 +583,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         with torch.cuda.device(device):
             want_blocks = self.method != 'SIMPLS' and return_block_scores
             dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=want_blocks)
+            if shard.world == 1:
+                group = None
             if want_blocks and "W" not in dev:
                 raise AttributeError("block scores need W_ (fit with calc_all=True)")
             K = dev["R"].shape[0]

@@ -42,7 +42,8 @@ def gpu_checks(group, rank, world, dev):
         assert np.allclose(m2.beta_, m.beta_, rtol=1e-11, atol=1e-14), "pre-sharded fit differs"
         print(f"rank {rank}: world={world} nan={nan_frac} n={n} trips={m.n_iter_} worst={worst}", flush=True)
     # the other methods under the same feature sharding (KERNEL: the p > n branch; n >= p needs row sharding)
-    for method, n in (("SIMPLS", 400), ("UNIPALS", 400), ("UNIPALS", 1200), ("KERNEL", 400)):
+    # KERNEL n=1201 >= p=800 takes the row-sharded path (samples split over the ranks, p x p all-reduce)
+    for method, n in (("SIMPLS", 400), ("UNIPALS", 400), ("UNIPALS", 1200), ("KERNEL", 400), ("KERNEL", 1201)):
         sizes = (300, 50, 450)
         X, Y = latent_blocks(n, sizes, 3, 4, seed=50 + n)
         Xt, Yt = latent_blocks(13, sizes, 3, 4, seed=6)
