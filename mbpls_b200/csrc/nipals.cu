@@ -28,10 +28,8 @@ template <bool NANMODE>
 __device__ __forceinline__ void dot_accum(const double2 x, const double2 u, double& num, double& den, int& sawnan) {
   if (NANMODE) {
     const bool ox = !isnan(x.x), oy = !isnan(x.y);
-    num = fma(ox ? x.x : 0.0, u.x, num);
-    num = fma(oy ? x.y : 0.0, u.y, num);
-    den = fma(ox ? u.x : 0.0, u.x, den);
-    den = fma(oy ? u.y : 0.0, u.y, den);
+    if (ox) { num = fma(x.x, u.x, num); den = fma(u.x, u.x, den); }
+    if (oy) { num = fma(x.y, u.y, num); den = fma(u.y, u.y, den); }
     sawnan |= (!ox) | (!oy);
   } else {
     num = fma(x.x, u.x, num);
@@ -40,7 +38,7 @@ __device__ __forceinline__ void dot_accum(const double2 x, const double2 u, doub
 }
 
 template <bool NANMODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NANMODE ? 2 : 0)
 xtu_kernel(const double* __restrict__ Xt, long ld, int n, int p, int feats_per_cta, const double* __restrict__ u,
            const double* __restrict__ uu_ptr,  // plain denominator u'u; nullptr -> 1 (loadings, :920)
            const int* __restrict__ block_off, int B, double* __restrict__ w, double* __restrict__ norm_part,
