@@ -52,11 +52,12 @@ int mbpls_transpose_in_f64(const double* src, long lds, int rows, int cols, doub
 /* feature-major -> row-major */
 int mbpls_transpose_out_f64(const double* src, long ld, int rows, int cols, double* dst, long ldd, int row0, void* stream);
 
-/* ---- NaN census: MBPLS.check_sparsity_level (mbpls.py:255-271) ----------------------------------
+/* ---- NaN census: MBPLS.check_sparsity_level (mbpls.py:255-271) and check_array's finiteness test (:310,:336) ----
  * col_nan[j] = number of NaNs in feature j; row_flag[b*ldf + i] = 1 if sample i has a NaN in block b
- * (row_flag must be zeroed by the caller). block_off: B+1 ascending local feature offsets. */
+ * (optional; must be zeroed by the caller); *inf_flag = 1 if any element is +-inf (optional).
+ * block_off: B+1 ascending local feature offsets. */
 int mbpls_nan_census_f64(const double* Xt, long ld, int n, int p, const int* block_off, int B, int* col_nan,
-                         unsigned char* row_flag, long ldf, void* stream);
+                         unsigned char* row_flag, long ldf, int* inf_flag, void* stream);
 
 /* ---- StandardScaler.fit_transform on every feature, in place (mbpls.py:307,314,325-326) ----------
  * Outputs per feature: mean_, var_, scale_, n_samples_seen_ and nansum(z^2) (feeds varx, :826-829).

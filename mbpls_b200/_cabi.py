@@ -51,7 +51,7 @@ SIGNATURES = {
     "mbpls_abi_version": [],
     "mbpls_transpose_in_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
     "mbpls_transpose_out_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
-    "mbpls_nan_census_f64": [_p, _l, _i, _i, _p, _i, _p, _p, _l, _p],
+    "mbpls_nan_census_f64": [_p, _l, _i, _i, _p, _i, _p, _p, _l, _p, _p],
     "mbpls_standardize_fit_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p],
     "mbpls_standardize_apply_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_scaler_inverse_f64": [_p, _l, _i, _i, _p, _p, _p],

@@ -56,19 +56,22 @@ __global__ void __launch_bounds__(256) transpose_out_kernel(const double* __rest
 __global__ void __launch_bounds__(256) census_kernel(const double* __restrict__ Xt, long ld, int n, int p,
                                                      const int* __restrict__ block_off, int B,
                                                      int* __restrict__ col_nan, unsigned char* __restrict__ row_flag,
-                                                     long ldf) {
+                                                     long ldf, int* __restrict__ inf_flag) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
     const int b = block_of(block_off, B, j);
     const double* x = Xt + static_cast<size_t>(j) * ld;
-    int cnt = 0;
+    int cnt = 0, inf = 0;
     for (int i = lane; i < n; i += 32) {
-      if (isnan(x[i])) {
+      const double v = x[i];
+      if (isnan(v)) {
         ++cnt;
-        row_flag[static_cast<size_t>(b) * ldf + i] = 1;
+        if (row_flag) row_flag[static_cast<size_t>(b) * ldf + i] = 1;
       }
+      inf |= isinf(v);
     }
+    if (inf && inf_flag) *inf_flag = 1;  // check_array rejects infinities even when NaN is allowed
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(MBPLS_FULL_MASK, cnt, o);
     if (lane == 0) col_nan[j] = cnt;
@@ -419,12 +422,12 @@ int mbpls_transpose_out_f64(const double* src, long ld, int rows, int cols, doub
 }
 
 int mbpls_nan_census_f64(const double* Xt, long ld, int n, int p, const int* block_off, int B, int* col_nan,
-                         unsigned char* row_flag, long ldf, void* stream) {
-  if (!Xt || !block_off || !col_nan || !row_flag || B < 1) return MBPLS_ERR_ARG;
+                         unsigned char* row_flag, long ldf, int* inf_flag, void* stream) {
+  if (!Xt || !block_off || !col_nan || B < 1) return MBPLS_ERR_ARG;
   if (p == 0 || n == 0) return MBPLS_OK;
   int grid = (p + 7) / 8;
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  census_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, block_off, B, col_nan, row_flag, ldf);
+  census_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, block_off, B, col_nan, row_flag, ldf, inf_flag);
   MBPLS_RETURN_LAST();
 }
 

@@ -233,15 +233,25 @@ def segsum(v: torch.Tensor, off_dev: torch.Tensor, nseg: int) -> torch.Tensor:
     return out[:nseg]
 
 
-def nan_census(Xt: torch.Tensor, n: int, block_off_dev: torch.Tensor, B: int):
-    """Returns (col_nan int32[p], row_flag uint8[B x ldf])."""
+def nan_census(Xt: torch.Tensor, n: int, block_off_dev: torch.Tensor, B: int, want_rows: bool = True):
+    """Returns (col_nan int32[p], row_flag uint8[B x ldf] or None, inf_flag int32[1]) in one read pass."""
     p, ld = Xt.shape
     dev = Xt.device
     col_nan = torch.zeros(max(p, 1), dtype=torch.int32, device=dev)
-    row_flag = torch.zeros((B, ld), dtype=torch.uint8, device=dev)
+    row_flag = torch.zeros((B, ld), dtype=torch.uint8, device=dev) if want_rows else None
+    inf_flag = torch.zeros(1, dtype=torch.int32, device=dev)
     call("mbpls_nan_census_f64", ptr(Xt), ld, n, p, ptr(block_off_dev), B, ptr(col_nan), ptr(row_flag), ld,
-         stream_ptr(dev))
-    return col_nan[:p], row_flag
+         ptr(inf_flag), stream_ptr(dev))
+    return col_nan[:p], row_flag, inf_flag
+
+
+def all_finite(Xt: torch.Tensor, n: int) -> bool:
+    """check_array's finiteness test (mbpls.py:310,336) as one read pass of the census kernel."""
+    p = Xt.shape[0]
+    if p == 0 or n == 0:
+        return True
+    col_nan, _, inf_flag = nan_census(Xt, n, _i32([0, p], Xt.device), 1, want_rows=False)
+    return int(col_nan.sum().item()) == 0 and int(inf_flag.item()) == 0
 
 
 # --------------------------------------------------------------------------------------------- #

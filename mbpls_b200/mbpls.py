@@ -177,7 +177,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         with torch.cuda.device(device):
             Xt = E.alloc_feature_major(p, n, device)
             E.ingest_feature_major(src, n, 0, p, Xt, device)
-            col_nan, row_flag = E.nan_census(Xt, n, E._i32([0, p], device), 1)
+            col_nan, row_flag, _ = E.nan_census(Xt, n, E._i32([0, p], device), 1)
             return self._census_from_flags(row_flag[0, :n].cpu().numpy().astype(bool), (col_nan > 0).cpu().numpy())
 
     @staticmethod
@@ -262,7 +262,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             if sparse:
                 row_flag, ycol_flag = self._fit_census(Xt, Yt, n, q, shard, boff_dev, group)
             elif not self.standardize:
-                self._require_finite(Xt, Yt)
+                self._require_finite(Xt, Yt, n)
 
             # ---- standardisation (mbpls.py:299-326)
             zss = None
@@ -345,7 +345,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             return mean, var, scale
 
         zss = None
-        ok = bool(torch.isfinite(Xt).all()) and bool(torch.isfinite(Yt).all())
+        ok = E.all_finite(Xt, nl) and E.all_finite(Yt, nl)
         self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
         if self.standardize:
             xm, xv, xs = standardize_rows(Xt, p, E._i32([0, p], device))
@@ -371,23 +371,23 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         if bad:
             raise ValueError(msg)
 
-    def _require_finite(self, Xt, Yt):
-        ok = bool(torch.isfinite(Xt).all()) and bool(torch.isfinite(Yt).all())
+    def _require_finite(self, Xt, Yt, n):
+        ok = E.all_finite(Xt, n) and E.all_finite(Yt, n)
         self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", self._runtime()["group"])
 
     def _fit_census(self, Xt, Yt, n, q, shard, boff_dev, group):
         """sparse_X_info_ / sparse_Y_info_ (mbpls.py:294-296, 304-313) from the device census."""
         B = len(shard.sizes)
-        if bool(torch.isinf(Xt).any()) or bool(torch.isinf(Yt).any()):
-            raise ValueError("Input contains infinity or a value too large for dtype('float64').")
-        col_nan, row_flag = E.nan_census(Xt, n, boff_dev, B)
+        col_nan, row_flag, xinf = E.nan_census(Xt, n, boff_dev, B)
         if group is not None:
             import torch.distributed as dist
             rf = row_flag.to(torch.int32)
             dist.all_reduce(rf, op=dist.ReduceOp.MAX, group=group)
             row_flag.copy_(rf.to(torch.uint8))
         one = E._i32([0, q], Yt.device)
-        ycol_nan, yrow_flag = E.nan_census(Yt, n, one, 1)
+        ycol_nan, yrow_flag, yinf = E.nan_census(Yt, n, one, 1)
+        self._raise_if_any_rank(bool(xinf.item()) or bool(yinf.item()),
+                                "Input contains infinity or a value too large for dtype('float64').", group)
         col_full = self._gather_features(col_nan.view(1, -1).to(F64), shard)[0] > 0
         rows = row_flag[:, :n].cpu().numpy().astype(bool)
         self.sparse_Y_info_ = {'Y': self._census_from_flags(yrow_flag[0, :n].cpu().numpy().astype(bool),

@@ -116,3 +116,19 @@ def test_components_up_to_rank_budget():
     X, Y = latent_blocks(14, (6, 5), 1, 2, seed=11, noise=0.3)
     _both(dict(n_components=6, method="SIMPLS", full_svd=True), X, Y.ravel())
     _both(dict(n_components=6, method="KERNEL", full_svd=True), X, Y.ravel())
+
+
+def test_infinity_is_rejected_in_every_mode():
+    """check_array semantics (mbpls.py:310,336): +-inf is an error even when NaN is allowed (sparse_data=True)."""
+    from mbpls_b200 import MBPLS
+    rng = np.random.default_rng(12)
+    X, y = rng.standard_normal((30, 8)), rng.standard_normal((30, 1))
+    Xi = X.copy()
+    Xi[4, 2] = np.inf
+    for kw in (dict(), dict(standardize=False), dict(sparse_data=True), dict(sparse_data=True, standardize=False)):
+        with pytest.raises(ValueError), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            MBPLS(n_components=1, **kw).fit(Xi, y)
+    m = MBPLS(n_components=1).fit(X, y)
+    with pytest.raises(ValueError):
+        m.predict(Xi)
