@@ -277,8 +277,11 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                     prof.setdefault("standardize", []).append(ev)
                 ys = E.standardize_fit(Yt, n, rt["standardize_mode"])
                 if not sparse:
-                    ok = bool((xs.seen[:shard.p_local] == n).all()) and bool(torch.isfinite(xs.zss[:shard.p_local]).all()) \
-                        and bool((ys.seen[:q] == n).all()) and bool(torch.isfinite(ys.zss[:q]).all())
+                    # NaN shows up as seen < n, +-inf as a non-finite column mean / variance: no extra pass over X
+                    pl = shard.p_local
+                    ok = bool((xs.seen[:pl] == n).all()) and bool(torch.isfinite(xs.mean[:pl]).all()) \
+                        and bool(torch.isfinite(xs.var[:pl]).all()) and bool((ys.seen[:q] == n).all()) \
+                        and bool(torch.isfinite(ys.mean[:q]).all()) and bool(torch.isfinite(ys.var[:q]).all())
                     self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
                 self._store_scalers(xs, ys, shard, q)
                 zss = xs.zss
