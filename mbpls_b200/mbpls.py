@@ -585,7 +585,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         group, _, _ = self._group_info()
         with torch.cuda.device(device):
             want_blocks = self.method != 'SIMPLS' and return_block_scores
-            dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=want_blocks)
+            # only the NaN-mode block scores deflate the new data in place and need a private standardised copy
+            dev, shard, Xt, m, mean, scale = self._prepare_new_X(X, device, scaled_copy=want_blocks and bool(self.sparse_data))
             if shard.world == 1:
                 group = None
             if want_blocks and "W" not in dev:
@@ -596,7 +597,23 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             self._check_flag(flag, group)
             Ts = np.ascontiguousarray(Ts_dev[:, :m].cpu().numpy().T)
             out = [Ts]
-            if want_blocks:  # :1126-1155
+            if want_blocks and not self.sparse_data:
+                # Dense data: the K sequential deflations of :1131-1155 collapse to one product and a K x K
+                # triangular correction,  T_b = X_b W_b - Ts striu(P_b' W_b)  (SURVEY.md 8f-3): X is read once.
+                from . import crossmethods as CM
+                B = len(shard.sizes)
+                T = []
+                for b in range(B):
+                    o0, o1 = shard.block_off[b], shard.block_off[b + 1]
+                    Wb, Pb = dev["W"][:, o0:o1], dev["P"][:, o0:o1]
+                    full = E.skinny_gemm(Xt[o0:o1], m, Wb, [0, o1 - o0], group,
+                                         None if mean is None else mean[o0:o1], None if scale is None else scale[o0:o1])  # X_b W_b
+                    Cb = torch.triu(E.gram(Pb, Wb, o1 - o0, group), diagonal=1).contiguous()  # striu(P_b' W_b)
+                    cols = [CM.lincomb_sub(full[k].contiguous(), Ts_dev, k, Cb[:k, k].contiguous(), m)[:m] if k > 0
+                            else full[0, :m] for k in range(K)]
+                    T.append(np.ascontiguousarray(torch.stack(cols, dim=1).cpu().numpy()))
+                out.append(T)
+            elif want_blocks:  # NaN mode: sequential deflation, NaNs stay NaN and count as zero (:1126-1155)
                 B = len(shard.sizes)
                 T = []
                 for b in range(B):

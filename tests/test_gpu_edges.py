@@ -132,3 +132,26 @@ def test_infinity_is_rejected_in_every_mode():
     m = MBPLS(n_components=1).fit(X, y)
     with pytest.raises(ValueError):
         m.predict(Xi)
+
+
+def test_pandas_dataframes_and_dense_block_score_fast_path():
+    """DataFrame blocks (what the reference's notebooks pass) and the one-pass block-score transform."""
+    import pandas as pd
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(90, (23, 41, 12), 2, 5, seed=13)
+    Xn, Yn = latent_blocks(31, (23, 41, 12), 2, 5, seed=14)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(n_components=5).fit([x.copy() for x in X], Y.copy())
+        m = MBPLS(n_components=5).fit([pd.DataFrame(x) for x in X], pd.DataFrame(Y))
+        for std in (True, False):
+            if not std:
+                o = OracleMBPLS(n_components=5, standardize=False).fit([x.copy() for x in X], Y.copy())
+                m = MBPLS(n_components=5, standardize=False).fit([x.copy() for x in X], Y.copy())
+            Ts_o, T_o = o.transform([x.copy() for x in Xn], return_block_scores=True)
+            Ts_m, T_m = m.transform([pd.DataFrame(x) for x in Xn], return_block_scores=True)
+            assert rel_err(np.abs(Ts_m), np.abs(Ts_o)) < 1e-9
+            for a, b in zip(T_m, T_o):
+                assert a.shape == b.shape and rel_err(np.abs(a), np.abs(b)) < 1e-9
