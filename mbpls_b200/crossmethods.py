@@ -296,6 +296,7 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
     model.W_concat_ = np.empty((pg, 0))
     _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb)
+    model.__dict__["_cv_weights"] = Wc  # prefix models for model_selection.cross_val_predict
 
 
 # ---- KERNEL (mbpls.py:576-807) -------------------------------------------------------------------

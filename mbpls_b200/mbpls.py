@@ -111,7 +111,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
     def __getstate__(self):
         self._materialize_all()
         state = dict(self.__dict__)
-        for k in ("_rt", "_dev", "_lazy", "_dev_scalers"):
+        for k in ("_rt", "_dev", "_lazy", "_dev_scalers", "_cv_weights", "_rows"):
             state.pop(k, None)
         return state
 
@@ -461,6 +461,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         R = E.right_multiply(Wt, p_loc, 1.0 / colnorm, M)
         beta = E.right_multiply(R, p_loc, None, res.V[:, :q].contiguous())
         self.__dict__["_dev"] = dict(shard=shard, R=R, beta=beta, W=res.W[:, :p_loc], P=P, V=res.V[:, :q])
+        self.__dict__["_cv_weights"] = Wt  # un-normalised weights: prefix models for model_selection.cross_val_predict
 
         # ---- small host-side bookkeeping
         A = res.A[:, :B].cpu().numpy().T.copy()  # B x K

@@ -1,0 +1,127 @@
+"""Device-resident cross-validation driver.
+
+Every real-world notebook of the reference runs
+``sklearn.model_selection.cross_val_predict(MBPLS(n_components=k), X, y, cv=len(X))`` for a range of ``k``
+(``examples/real_world_applications/*.ipynb``): n refits per k, each of which re-validates, copies and -- with a
+GPU estimator -- would re-upload X.  Here X and Y are uploaded once (feature-major); each fold gathers its training
+samples on the device, runs the normal fit kernels on them, and predicts its held-out samples; with
+``n_components_list`` the predictions for every smaller model are read off the *same* fit, because a K-component
+NIPALS / UNIPALS / SIMPLS / KERNEL fit contains all of its prefixes (``beta_k = R_k V_k'`` with
+``R_k = W_k pinv(P_k' W_k)``, mbpls/mbpls.py:986-989).
+
+The result equals ``cross_val_predict(clone(estimator), X, y, cv=cv)`` (tests/test_gpu_cv.py).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+import torch
+from sklearn.base import clone
+
+from . import engine as E
+from .engine import F64
+from .mbpls import MBPLS, _as_2d_source, _is_block_list
+
+__all__ = ["cross_val_predict"]
+
+
+def _folds(n: int, cv) -> list:
+    if isinstance(cv, (int, np.integer)):
+        from sklearn.model_selection import KFold
+        return [(tr, te) for tr, te in KFold(n_splits=int(cv)).split(np.arange(n))]
+    if hasattr(cv, "split"):
+        return [(tr, te) for tr, te in cv.split(np.arange(n))]
+    return [(np.asarray(tr), np.asarray(te)) for tr, te in cv]
+
+
+def _prefix_betas(model: MBPLS, ks: Sequence[int], device) -> list:
+    """beta for the first k components, k in ks, from one fitted model (device tensors q x p each)."""
+    dev = model._device_model(device)
+    shard = dev["shard"]
+    p = shard.p_local
+    group, _, _ = model._group_info()
+    P, V = dev["P"], dev["V"]
+    if model.method == 'SIMPLS':
+        # SIMPLS: R and Q columns do not depend on later components (mbpls.py:1004-1013, :1044)
+        return [E.right_multiply(dev["R"][:k], p, None, V[:k].contiguous()) for k in ks]
+    Wfull = model.__dict__.get("_cv_weights")  # K x p un-normalised / concatenated weights kept by fit for CV
+    out = []
+    for k in ks:
+        Wk, Pk = Wfull[:k], P[:k]
+        if model.method == 'NIPALS':
+            coln = torch.sqrt(E.rows_sumsq(Wk, p, group))
+            M = E.small_pinv(E.gram(Pk, Wk, p, group) / coln.view(1, -1))
+            R = E.right_multiply(Wk, p, 1.0 / coln, M)
+        else:
+            M = E.small_pinv(E.gram(Pk, Wk, p, group))
+            R = E.right_multiply(Wk, p, None, M)
+        out.append(E.right_multiply(R, p, None, V[:k].contiguous()))
+    return out
+
+
+def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[Iterable[int]] = None):
+    """Out-of-fold predictions of ``estimator`` (an unfitted ``mbpls_b200.MBPLS``) with the data kept on the GPU.
+
+    Returns an (n, q) array like ``sklearn.model_selection.cross_val_predict``; with ``n_components_list`` a dict
+    ``{k: (n, q) array}`` obtained from one fit per fold with ``max(k)`` components.
+    KERNEL is supported through its prefix-independent quantities only when ``n_components_list`` is None.
+    """
+    rt = estimator._runtime()
+    if rt["group"] is not None:
+        raise NotImplementedError("cross_val_predict runs on one GPU")
+    device = E.require_cuda(rt["device"])
+    blocks = X if _is_block_list(X) else [X]
+    blocks = [_as_2d_source(b, "X") for b in blocks]
+    Ysrc = y if isinstance(y, torch.Tensor) else np.asarray(y)
+    y1d = Ysrc.ndim == 1
+    if y1d:
+        Ysrc = Ysrc.reshape(-1, 1)
+    Ysrc = _as_2d_source(Ysrc, "y")
+    n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
+    sizes = [int(b.shape[1]) for b in blocks]
+    ks = None if n_components_list is None else sorted(set(int(k) for k in n_components_list))
+    if ks is not None and estimator.method == 'KERNEL':
+        raise NotImplementedError("n_components_list needs prefix-stable weights; use NIPALS, UNIPALS or SIMPLS")
+    K = estimator.n_components if ks is None else max(ks)
+    folds = _folds(n, cv)
+
+    with torch.cuda.device(device):
+        shard = E.ShardMap.build(sizes, 0, 1)
+        Xraw = E.ingest_blocks(blocks, n, shard, device)          # p x ld, uploaded once
+        Yraw = E.alloc_feature_major(q, n, device)
+        E.ingest_feature_major(Ysrc, n, 0, q, Yraw, device)
+        off = shard.block_off
+        preds = {k: np.full((n, q), np.nan) for k in (ks or [K])}
+        for tr, te in folds:
+            tr_d = torch.as_tensor(np.asarray(tr), device=device, dtype=torch.long)
+            te_d = torch.as_tensor(np.asarray(te), device=device, dtype=torch.long)
+            ntr, nte = len(tr), len(te)
+            Xtr = E.alloc_feature_major(shard.p_local, ntr, device)
+            Xtr[:, :ntr] = Xraw.index_select(1, tr_d)              # gather of the training samples (device copy)
+            Ytr = Yraw.index_select(1, tr_d).t().contiguous()      # ntr x q
+            Xte = E.alloc_feature_major(shard.p_local, nte, device)
+            Xte[:, :nte] = Xraw.index_select(1, te_d)
+            m = clone(estimator)
+            m.set_params(n_components=K, copy=False)
+            m.set_runtime(device=device, materialize=False)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m.fit([Xtr[off[b]:off[b + 1], :ntr].t() for b in range(len(sizes))], Ytr)
+                te_blocks = [Xte[off[b]:off[b + 1], :nte].t() for b in range(len(sizes))]
+                if ks is None:
+                    preds[K][te] = m.predict(te_blocks)
+                else:
+                    dev, sh, Xt_new, mm, mean, scale = m._prepare_new_X(te_blocks, device, scaled_copy=False)
+                    for k, beta_k in zip(ks, _prefix_betas(m, ks, device)):
+                        Yh = E.skinny_gemm(Xt_new, mm, beta_k, sh.block_off, None, mean, scale)
+                        if m.standardize:
+                            _, _, ymean, yscale = m._device_scalers(sh, device)
+                            E.call("mbpls_scaler_inverse_f64", E.ptr(Yh), Yh.shape[1], mm, q, E.ptr(ymean), E.ptr(yscale),
+                                   E.stream_ptr(device))
+                        preds[k][te] = Yh[:, :mm].cpu().numpy().T
+    if ks is None:
+        out = preds[K]
+        return out.ravel() if y1d else out
+    return {k: (v.ravel() if y1d else v) for k, v in preds.items()}
