@@ -667,6 +667,89 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                                                 multioutput='variance_weighted')
 
 
+    # ------------------------------------------------------------------ reporting (mbpls.py:1439-1556)
+    def _component_indices(self, num_components):
+        """The reference's argument convention (:1454-1473): an int N means the first N components, a sequence
+        holds 1-based component numbers; requests beyond the fitted model are truncated with a printed note."""
+        if isinstance(num_components, (int, np.integer)):
+            comps = np.arange(int(num_components))
+        else:
+            comps = np.asarray(list(num_components), dtype=int) - 1
+        if len(comps) > self.n_components:
+            print("You requested more components to be plotted than your fitted model has.")
+            print("The requested list will be shortened to the maximum amount of components possible")
+            comps = comps[:self.n_components]
+        if len(comps) and (comps.max() + 1 > self.n_components or comps.min() < 0):
+            raise ValueError("You requested not existing indices.")
+        return comps
+
+    def plot_data(self, num_components=2):
+        """Everything ``plot`` draws, as arrays: per requested component the block importances (%), the explained
+        Y variance (%), the loadings of every block mapped back to the original variable scale through
+        ``x_scalers_[b].inverse_transform`` (:1494-1498) and the block scores."""
+        self._check_is_fitted()
+        T = getattr(self, "T_", None)
+        if self.method == 'SIMPLS' or not isinstance(T, list) or len(T) == 0 or T[0].shape[1] == 0:
+            raise AttributeError("plot needs block scores and importances (NIPALS / UNIPALS, or KERNEL with calc_all=True)")
+        out = []
+        for comp in self._component_indices(num_components):
+            loadings = []
+            for b in range(self.num_blocks_):
+                pb = self.P_[b][:, comp]
+                loadings.append(self.x_scalers_[b].inverse_transform(pb.reshape(1, -1)).ravel() if self.standardize else pb)
+            ev_y = float(100 * self.explained_var_y_[comp]) if len(self.explained_var_y_) > comp else float("nan")
+            out.append(dict(component=int(comp) + 1, explained_var_y_percent=ev_y,
+                            importance_percent=100 * np.ravel(self.A_[:, comp]), loadings=loadings,
+                            block_scores=[self.T_[b][:, comp] for b in range(self.num_blocks_)]))
+        return out
+
+    def plot(self, num_components=2):
+        """Per component: block importances, loadings (original scale) and block scores of every block; then a bar
+        chart of the block importances (mbpls.py:1439-1556).  Needs matplotlib, like the reference."""
+        data = self.plot_data(num_components)
+        from matplotlib import pyplot as plt
+        from matplotlib.gridspec import GridSpec
+        B = self.num_blocks_
+
+        def quarter_ticks(length):
+            step = max(1, length // 4)
+            plt.xticks(np.arange(0, length, step), np.arange(1, length + 1, step))
+
+        for d in data:
+            plt.figure()
+            plt.suptitle("Component {}: {}% expl. var. in Y".format(d["component"], round(d["explained_var_y_percent"], 2)),
+                         fontsize=12, fontweight='bold')
+            head = GridSpec(1, B, top=0.875, bottom=0.85, right=0.95)
+            body = GridSpec(2, B, top=0.8, hspace=0.45, wspace=0.45, right=0.95)
+            for b in range(B):
+                plt.subplot(head[0, b])
+                plt.text(0.5, 0, "X-Block {:d}\nImportance: {:.0f}%".format(b + 1, d["importance_percent"][b]),
+                         fontsize=12, horizontalalignment='center')
+                plt.axis('off')
+                for row, series, xlabel, ylabel in ((0, d["loadings"][b], "Variable", "Loading"),
+                                                    (1, d["block_scores"][b], "Sample", "Block Score")):
+                    plt.subplot(body[row, b])
+                    plt.plot(series)
+                    quarter_ticks(len(series))
+                    plt.xlabel(xlabel)
+                    if b == 0:
+                        plt.ylabel(ylabel)
+                    plt.grid()
+            plt.show()
+        plt.figure()
+        plt.suptitle("Block importances", fontsize=14, fontweight='bold')
+        ax = plt.subplot(GridSpec(1, 1, top=0.825, right=0.7, hspace=0.45, wspace=0.4)[0, 0])
+        width = 0.8 / max(1, len(data))
+        for i, d in enumerate(data):
+            ax.bar(np.arange(B) + 1 - 0.4 + (i + 0.5) * width, d["importance_percent"], width=width,
+                   label="Component {}".format(d["component"]))
+        ax.set_xticks(np.arange(B) + 1)
+        ax.legend(bbox_to_anchor=(1.04, 1), loc="upper left")
+        ax.set_xlabel("Block")
+        ax.set_ylabel("Block importance in %")
+        plt.show()
+
+
 def _make_scaler(mean, var, scale, seen) -> StandardScaler:
     """A scikit-learn StandardScaler carrying statistics computed on the device, so that
     ``x_scalers_[b].transform / inverse_transform`` work exactly as with the reference (notebooks use them)."""

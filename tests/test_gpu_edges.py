@@ -155,3 +155,33 @@ def test_pandas_dataframes_and_dense_block_score_fast_path():
             assert rel_err(np.abs(Ts_m), np.abs(Ts_o)) < 1e-9
             for a, b in zip(T_m, T_o):
                 assert a.shape == b.shape and rel_err(np.abs(a), np.abs(b)) < 1e-9
+
+
+def test_plot_data_matches_reference_recipe(capsys):
+    """plot (mbpls.py:1439-1556) draws inverse-scaled loadings, block scores and importances; plot_data hands out
+    exactly those arrays, computed here the way the reference's plot body does from the oracle's attributes."""
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(50, (14, 9), 2, 3, seed=8)
+    m, o = _both(dict(n_components=3), X, Y)
+    data = m.plot_data([1, 3])                                   # 1-based component numbers (:1459-1461)
+    assert [d["component"] for d in data] == [1, 3]
+    for d in data:
+        k = d["component"] - 1
+        s = np.sign(np.dot(m.Ts_[:, k], o.Ts_[:, k]))
+        assert rel_err(d["importance_percent"], 100 * o.A_[:, k]) < TOL
+        assert abs(d["explained_var_y_percent"] - 100 * o.explained_var_y_[k]) < 1e-6
+        for b in range(2):
+            # inverse_transform is affine, so the sign ambiguity of the component shows up around the mean
+            want = o.x_scalers_[b].inverse_transform((s * o.P_[b][:, k]).reshape(1, -1)).ravel()
+            assert rel_err(d["loadings"][b], want) < TOL
+            assert rel_err(d["block_scores"][b], s * o.T_[b][:, k]) < TOL
+    assert len(m.plot_data(2)) == 2                              # int: the first N components (:1455)
+    assert len(m.plot_data(7)) == 3                              # truncated with the reference's printed note
+    assert "shortened" in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        m.plot_data([4])
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            m.plot(1)
