@@ -292,16 +292,20 @@ def run_ours(args):
 
     x_bytes_local = 8.0 * n * shard.p_local
     kern = {}
-    for key, mult in (("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0), ("loadings", 1.0), ("standardize", 2.0)):
+    for key, mult in (("trip", 1.0), ("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0), ("loadings", 1.0), ("standardize", 2.0)):
         t = mean_ms(key)
         if t:
             kern[key] = {"ms": t, "launches": len(profile[key]), "algorithmic_bytes": mult * x_bytes_local,
                          "gbs": mult * x_bytes_local / (t / 1e3) / 1e9}
-    dominant = "xw" if "xw" in kern else None
+    # dominant kernel by share of the step: the loadings+deflation(+next first trip) pass when the one-pass kernels run
+    # (1 read + 1 write of X per launch), else the X w pass of the two-pass kernels
+    dominant = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["launches"]) if kern else None
+    names = {"trip": "fused_trip_kernel (X'u and X w in one read)", "deflate": "fused_deflate_kernel / loadings_deflate_*",
+             "xw": "xw_kernel", "xtu": "xtu_kernel", "standardize": "standardize_*", "loadings": "xtu_kernel (loadings)"}
     traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one xw launch from the committed ncu --set full capture
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        entry = prof.get("xw", {})
+        entry = prof.get(dominant, {})
         if dominant and entry.get("algorithmic_bytes_per_launch"):
             # the capture may have been taken on a different shard size: scale by the algorithmic bytes
             traffic = entry["dram_bytes_per_launch"] * kern[dominant]["algorithmic_bytes"] / entry["algorithmic_bytes_per_launch"]
@@ -309,7 +313,7 @@ def run_ours(args):
         pass
     roofline = None
     if dominant:
-        roofline = {"bound": "hbm", "kernel": "xw_kernel<false>" if args.nan_frac == 0 else "xw_kernel<true>",
+        roofline = {"bound": "hbm", "kernel": names.get(dominant, dominant) + (" [NaN mode]" if args.nan_frac > 0 else ""),
                     "achieved": kern[dominant]["gbs"], "peak": peak_gbs, "unit": "GB/s",
                     "frac": kern[dominant]["gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes"], "per_kernel": kern}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 1
+#define MBPLS_ABI_VERSION 2
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -142,6 +142,28 @@ int mbpls_nipals_record_component_f64(const mbpls_record_args* args_host, void* 
  * weights of the next component (:847,856 with u = u0).  mode as in mbpls_standardize_fit_f64. */
 int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* ts, const double* u0, const double* u0u0,
                                double* P_k, double* w_next, double* pss, int nanmode, int mode, void* stream);
+
+/* ---- one-pass NIPALS kernels (csrc/fused.cu) ---------------------------------------------------------
+ * A trip of the reference's loop reads X twice (X_b'u at mbpls.py:847/:856, then X_b w_b at :866/:875).  Because
+ * w~_j depends on feature j and u only, and t~_b is a sum over features, both are produced while a feature is
+ * resident on the SM: ONE read of X per trip.  "Workers" (groups of threads inside a persistent CTA) own one
+ * split each -- a contiguous local feature range inside one block, split_block[s] = its block -- and keep the
+ * n-vector of partial block scores in registers; outputs have the layout of mbpls_nipals_xw_f64 /
+ * mbpls_nipals_xtu_f64 (Tnum[s][.], Tden[s][.], w[j]) and norm_part[s*B + split_block[s]] = sum of w~_j^2
+ * over the split (all other entries of norm_part must be zero), so mbpls_nipals_reduce_partials_f64 and the
+ * epilogue apply unchanged.  mbpls_fused_workers_per_cta(ld) returns the workers per CTA (0: the feature is
+ * too long for the register-resident accumulators, use the two-pass kernels); size the split table to
+ * workers_per_cta * number of SMs. */
+int mbpls_fused_workers_per_cta(long ld);
+int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const int* split_f0,
+                                const int* split_f1, const int* split_block, int nsplit, int B, double* w, double* norm_part,
+                                double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream);
+/* Dense data: loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL --
+ * the complete first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0,
+ * its squared norms and its partial block scores Tnum.  1 read + 1 write of X. */
+int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* u0, const double* u0u0,
+                            const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
+                            double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream);
 
 /* ---- finalisation and new-data paths (mbpls.py:986-989, :1110-1117, :1379-1386) -------------------- */
 /* Cpart[chunk][i*K2 + j] = sum_{f in chunk} A[i][f] * Bm[j][f]; A is K1 x p (lda), Bm is K2 x p (ldb).

@@ -1,0 +1,525 @@
+// One-pass NIPALS trip (mbpls/mbpls.py:843-875): block weights AND block scores from a single read of X.
+//
+// w~_j = x_j . u / u'u depends on feature j and u only, and the block score is a sum over features,
+// t~_b = sum_j w~_j x_j (the division by ||w~_b|| is a scalar applied later, nipals.cu), so while feature j is
+// resident on the SM both halves of the trip can be done: the reference's two GEMVs (X_b' u at :847/:856 and
+// X_b w_b at :866/:875, i.e. two full reads of X per trip) become ONE read.  The price is state: a worker
+// must hold a private n-vector of score accumulators next to the resident feature.
+//
+// Layout of one CTA (persistent, one per SM, 512 threads):
+//   * the threads form G = 512/TG independent workers of TG threads; a worker owns one *split* (a contiguous
+//     feature range inside one block) and walks its features one at a time;
+//   * thread `tg` of a worker owns the same EPT 16-byte units (2 samples each) of every feature, so its
+//     score accumulators live in registers for the whole kernel (2*EPT doubles) next to the current
+//     feature's values (2*EPT doubles);
+//   * a worker's features stream through its private ring of S shared-memory stages as 1-D bulk (TMA)
+//     copies of one chunk (UC = TG*EPTC units, the last chunk of a feature shorter) each, completion
+//     tracked by one mbarrier per stage.  A stage is released as soon as its chunk sits in registers:
+//     every warp bumps a shared-memory counter after its reads and the LAST warp to arrive refills the
+//     stage itself (proxy fence + expect_tx + bulk copy).  No producer warp (a 17th warp caps the kernel at
+//     96 registers and spills the accumulators), no polling, and the refill work lands on whichever warp
+//     happens to be last instead of always delaying the same one (ncu on the first version, which had
+//     one feeder thread per worker: 52 % of all stall samples at the worker barrier behind that warp);
+//   * u (and, in NaN mode, the per-sample "missing weight" accumulators) live in shared memory.
+// Per feature: chunks -> registers with the dot product against u on the fly; one fixed-order reduction over
+// the worker (warp shuffles + one named barrier); w~_j; then acc_i += w~_j x_ij in registers.  Partial
+// scores go to Tnum[split][.] exactly like xw_kernel's, so reduce_partials / the epilogue are unchanged and
+// results are bitwise reproducible (static split -> worker map, fixed summation order).
+//
+// NaN mode (:848-852, :867-872): the masked numerator/denominator of w~_j come from the same pass; the
+// masked score denominator sum_{j observed in row i} w~_j^2 is kept as  (sum_j w~_j^2) - miss_i  with
+// miss_i accumulated in shared memory only where x_ij is NaN.
+//
+// The second kernel closes a component the same way: loadings p_j = x_j . ts, rank-1 deflation
+// x_j -= ts p_j (:917-930, :968-969) written back from registers, the next component's first weights
+// w~_j = x_j(deflated) . u0 / u0'u0 (u restarts from the same Y column, :838) AND its first block-score
+// partials, so the first trip of the next component needs no pass over X at all.
+#include "launch.cuh"
+#include "../../include/mbpls_b200.h"
+
+using namespace mbpls;
+
+namespace {
+
+struct FusedArgs {
+  const double* Xt;  // trip kernel: read only
+  double* Xw;        // deflate kernel: same matrix, written in place
+  long ld;
+  int n;
+  const double* u;   // trip: current Y scores; deflate: u0 (may be null -> no next-component outputs)
+  const double* uu;  // device scalar u'u (resp. u0'u0)
+  const double* ts;  // deflate only
+  const int* split_f0;
+  const int* split_f1;
+  const int* split_block;
+  int nsplit;
+  int B;
+  double* w;          // w~ out (trip) / next w~ out (deflate)
+  double* norm_part;  // [nsplit * B], zero except (split, block of split)
+  double* Tnum;       // [nsplit][ldt]
+  double* Tden;       // NaN mode
+  long ldt;
+  double* P_k;  // deflate: loadings out
+  double* pss;  // deflate: p_j^2 out
+  const int* done;
+};
+
+// TG threads per worker, EPTC units per thread per chunk, at most CPF chunks per feature, S ring stages
+template <int TG, int EPTC_, int CPF_, int S_>
+struct Cfg {
+  static constexpr int kTG = TG, EPTC = EPTC_, CPF = CPF_, S = S_;
+  static constexpr int G = 512 / TG, EPT = EPTC_ * CPF_, NW = TG / 32;
+  static constexpr int UC = TG * EPTC_;  // units per (full) chunk
+  static constexpr int MAX_UNITS = UC * CPF_;
+};
+
+// fixed-order sum over the TG threads of one worker; `buf` holds NV*NW doubles and must alternate between
+// two buffers from call to call (a single named barrier per call is then enough).
+template <int NV, int TG>
+__device__ __forceinline__ void worker_sum(double (&v)[NV], double* buf, int g, int warp_in_group, int lane) {
+  constexpr int NW = TG / 32;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) buf[k * NW + warp_in_group] = v[k];
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TG) : "memory");
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = lane < NW ? buf[k * NW + lane] : 0.0;
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(MBPLS_FULL_MASK, t, o);
+    v[k] = __shfl_sync(MBPLS_FULL_MASK, t, 0);
+  }
+}
+
+__device__ __forceinline__ unsigned atom_inc_acq_rel_smem(unsigned* p) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+  return old;
+}
+
+// shared-memory carve-up shared by both kernels
+template <class C>
+struct Smem {
+  double* vec0;     // u / ts
+  double* vec1;     // miss (NaN trip, one per worker) / u0 (deflate)
+  double* ring;     // [G][S][2*UC]
+  uint64_t* full;   // [G][S] mbarriers: chunk landed
+  unsigned* cnt;    // [G][S] (8-byte slots) warps that have finished reading the stage
+  double* scratch;  // [G][2][3*NW]
+  __device__ Smem(unsigned char* base, long ld, int nvec) {  // nvec n-vectors in front of the ring
+    vec0 = reinterpret_cast<double*>(base);
+    vec1 = vec0 + ld;
+    ring = vec0 + static_cast<size_t>(nvec) * ld;
+    full = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(C::G) * C::S * 2 * C::UC);
+    cnt = reinterpret_cast<unsigned*>(full + C::G * C::S);
+    scratch = reinterpret_cast<double*>(full + 2 * C::G * C::S);
+  }
+  __device__ __forceinline__ double* stage(int g, int s) const { return ring + (static_cast<size_t>(g) * C::S + s) * 2 * C::UC; }
+};
+
+template <class C>
+size_t fused_smem_bytes(long ld, int nvec) {
+  return static_cast<size_t>(nvec) * ld * 8 + static_cast<size_t>(C::G) * C::S * C::UC * 16 + static_cast<size_t>(C::G) * C::S * 16 +
+         static_cast<size_t>(C::G) * 2 * 3 * C::NW * 8 + 64;
+}
+
+// chunk c of feature f of the matrix X -> ring stage (g, s)
+template <class C>
+__device__ __forceinline__ void issue_chunk(const double* __restrict__ X, long ld, int units, int g, int s, int f, int c,
+                                            const Smem<C>& sm) {
+  const int nun = min(C::UC, units - c * C::UC);
+  const uint32_t bytes = static_cast<uint32_t>(nun) * 16u;
+  uint64_t* fb = &sm.full[g * C::S + s];
+  mbar_arrive_expect_tx(fb, bytes);
+  bulk_g2s(sm.stage(g, s), X + static_cast<size_t>(f) * ld + static_cast<size_t>(c) * C::UC * 2, bytes, fb);
+}
+
+template <class C>
+__device__ __forceinline__ void init_sync(const Smem<C>& sm) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::G * C::S; ++i) {
+      mbar_init(&sm.full[i], 1);
+      sm.cnt[2 * i] = 0;
+    }
+    fence_barrier_init();
+  }
+}
+
+// first S chunks of a worker (its thread 0, after the CTA-wide barrier that follows init_sync)
+template <class C>
+__device__ __forceinline__ void prime_ring(const double* __restrict__ X, long ld, int units, int ncf, int g, int f0, int f1,
+                                           const Smem<C>& sm) {
+  int f = f0, c = 0;
+  for (int s = 0; s < C::S && f < f1; ++s) {
+    issue_chunk<C>(X, ld, units, g, s, f, c, sm);
+    if (++c == ncf) { c = 0; ++f; }
+  }
+}
+
+// The calling warp is done reading stage (g, s), which held chunk c of feature j.  The last warp of the worker to
+// say so refills the stage with the chunk S positions further down the worker's stream.
+template <class C>
+__device__ __forceinline__ void release_stage(const double* __restrict__ X, long ld, int units, int ncf, int g, int s, int j, int c,
+                                              int f1, int lane, const Smem<C>& sm) {
+  __syncwarp();
+  if (lane == 0) {
+    unsigned* ctr = &sm.cnt[2 * (g * C::S + s)];
+    if (atom_inc_acq_rel_smem(ctr) == C::NW - 1) {
+      *reinterpret_cast<volatile unsigned*>(ctr) = 0;
+      int c2 = c + C::S, f2 = j;
+      while (c2 >= ncf) { c2 -= ncf; ++f2; }
+      if (f2 < f1) {
+        fence_proxy_async_smem();  // generic-proxy reads of the stage (all warps, ordered by the counter) before the async write
+        issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// one NIPALS trip in one pass
+// ------------------------------------------------------------------------------------------
+template <bool NANMODE, class C>
+__global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
+  if (a.done && *a.done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const long ld = a.ld;
+  const int units = static_cast<int>(ld >> 1);
+  const int ncf = (units + C::UC - 1) / C::UC;
+  const Smem<C> sm(smem_raw, ld, NANMODE ? 1 + C::G : 1);  // u | one miss vector per worker (NaN mode)
+  init_sync<C>(sm);
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.u[i] : 0.0;
+  if (NANMODE) {
+    for (int i = threadIdx.x; i < C::G * ld; i += blockDim.x) sm.vec1[i] = 0.0;
+  }
+  __syncthreads();
+
+  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
+  const int lane = threadIdx.x & 31, wig = tg >> 5;
+  const int wk = blockIdx.x * C::G + g;
+  if (wk >= a.nsplit) return;
+  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
+  if (tg == 0) prime_ring<C>(a.Xt, ld, units, ncf, g, f0, f1, sm);
+  const double uu = *a.uu;
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
+  double2* __restrict__ miss2 = reinterpret_cast<double2*>(sm.vec1 + (NANMODE ? static_cast<size_t>(g) * ld : 0));
+  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+
+  double2 acc[C::EPT];
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) acc[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0;
+  int s = 0;
+  uint32_t ph = 0;
+  int flip = 0;
+
+  for (int j = f0; j < f1; ++j) {
+    double2 x[C::EPT];
+    double v[3] = {0.0, 0.0, 0.0};  // numerator, masked u'u, NaN seen
+    double numb = 0.0;
+    uint32_t mx = 0, my = 0;  // NaN masks of this thread's units (x / y halves)
+#pragma unroll
+    for (int c = 0; c < C::CPF; ++c) {
+      if (c < ncf) {
+        mbar_wait(&sm.full[g * C::S + s], ph);
+        const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+        const bool whole = c + 1 < ncf;  // every chunk but the last of a feature is full: no bounds checks
+#pragma unroll
+        for (int e = 0; e < C::EPTC; ++e) {
+          const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+          if (whole || gi < units) {
+            double2 xv = xs[l];
+            const double2 uv = u2[gi];
+            if (NANMODE) {
+              const bool bx = isnan(xv.x), by = isnan(xv.y);
+              if (bx) { xv.x = 0.0; mx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
+              if (by) { xv.y = 0.0; my |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
+            }
+            v[0] = fma(xv.x, uv.x, v[0]);
+            numb = fma(xv.y, uv.y, numb);
+            x[k] = xv;
+          } else {
+            x[k] = make_double2(0.0, 0.0);
+          }
+        }
+        release_stage<C>(a.Xt, ld, units, ncf, g, s, j, c, f1, lane, sm);
+        if (++s == C::S) { s = 0; ph ^= 1u; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < C::EPTC; ++e) x[c * C::EPTC + e] = make_double2(0.0, 0.0);
+      }
+    }
+    v[0] += numb;
+    double wj;
+    if (NANMODE) {
+      v[2] = (mx | my) ? 1.0 : 0.0;
+      worker_sum<3, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
+      wj = v[2] > 0.0 ? v[0] / v[1] : v[0] / uu;
+    } else {
+      double one[1] = {v[0]};
+      worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
+      wj = one[0] / uu;
+    }
+    flip ^= 1;
+    if (tg == 0) a.w[j] = wj;
+    const double w2 = wj * wj;
+    normsq += w2;
+#pragma unroll
+    for (int k = 0; k < C::EPT; ++k) {
+      acc[k].x = fma(wj, x[k].x, acc[k].x);
+      acc[k].y = fma(wj, x[k].y, acc[k].y);
+    }
+    if (NANMODE) {
+      if (mx | my) {
+#pragma unroll
+        for (int k = 0; k < C::EPT; ++k) {
+          if (((mx | my) >> k) & 1u) {
+            const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+            double2 m = miss2[gi];
+            if ((mx >> k) & 1u) m.x += w2;
+            if ((my >> k) & 1u) m.y += w2;
+            miss2[gi] = m;
+          }
+        }
+      }
+    }
+  }
+
+  // partial block scores of this split (the layout xw_kernel writes)
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+  double2* td = NANMODE ? reinterpret_cast<double2*>(a.Tden + static_cast<size_t>(wk) * a.ldt) : nullptr;
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) {
+    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+    if (gi < units) {
+      tn[gi] = acc[k];
+      if (NANMODE) {
+        const double2 m = miss2[gi];
+        td[gi] = make_double2(normsq - m.x, normsq - m.y);
+      }
+    }
+  }
+  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
+// ------------------------------------------------------------------------------------------
+// loadings + deflation + the whole first trip of the next component (dense data)
+// ------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const long ld = a.ld;
+  const int units = static_cast<int>(ld >> 1);
+  const int ncf = (units + C::UC - 1) / C::UC;
+  const Smem<C> sm(smem_raw, ld, 2);  // ts | u0
+  init_sync<C>(sm);
+  const bool next = a.u != nullptr;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+    sm.vec0[i] = i < a.n ? a.ts[i] : 0.0;
+    sm.vec1[i] = (next && i < a.n) ? a.u[i] : 0.0;
+  }
+  __syncthreads();
+
+  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
+  const int lane = threadIdx.x & 31, wig = tg >> 5;
+  const int wk = blockIdx.x * C::G + g;
+  if (wk >= a.nsplit) return;
+  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
+  if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
+  const double uu = next ? *a.uu : 1.0;
+  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec1);
+  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+
+  double2 acc[C::EPT];
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) acc[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0;
+  int s = 0;
+  uint32_t ph = 0;
+  int flip = 0;
+
+  for (int j = f0; j < f1; ++j) {
+    double2 x[C::EPT];
+    double pa = 0.0, pb = 0.0;
+#pragma unroll
+    for (int c = 0; c < C::CPF; ++c) {
+      if (c < ncf) {
+        mbar_wait(&sm.full[g * C::S + s], ph);
+        const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+        const bool whole = c + 1 < ncf;
+#pragma unroll
+        for (int e = 0; e < C::EPTC; ++e) {
+          const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+          if (whole || gi < units) {
+            const double2 xv = xs[l];
+            const double2 tv = ts2[gi];
+            pa = fma(xv.x, tv.x, pa);
+            pb = fma(xv.y, tv.y, pb);
+            x[k] = xv;
+          } else {
+            x[k] = make_double2(0.0, 0.0);
+          }
+        }
+        release_stage<C>(a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm);
+        if (++s == C::S) { s = 0; ph ^= 1u; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < C::EPTC; ++e) x[c * C::EPTC + e] = make_double2(0.0, 0.0);
+      }
+    }
+    double one[1] = {pa + pb};
+    worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
+    flip ^= 1;
+    const double pj = one[0];
+    double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j) * ld);
+    double wa = 0.0, wb = 0.0;
+#pragma unroll
+    for (int k = 0; k < C::EPT; ++k) {
+      const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+      if (((k / C::EPTC) + 1 < ncf) || gi < units) {
+        const double2 tv = ts2[gi];
+        double2 xn;
+        xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
+        xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
+        st_stream(xg + gi, xn);
+        x[k] = xn;
+        if (next) {
+          const double2 uv = u2[gi];
+          wa = fma(xn.x, uv.x, wa);
+          wb = fma(xn.y, uv.y, wb);
+        }
+      }
+    }
+    double wj = 0.0;
+    if (next) {
+      double two[1] = {wa + wb};
+      worker_sum<1, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
+      flip ^= 1;
+      wj = two[0] / uu;
+      normsq = fma(wj, wj, normsq);
+#pragma unroll
+      for (int k = 0; k < C::EPT; ++k) {
+        acc[k].x = fma(wj, x[k].x, acc[k].x);
+        acc[k].y = fma(wj, x[k].y, acc[k].y);
+      }
+    }
+    if (tg == 0) {
+      a.P_k[j] = pj;
+      a.pss[j] = pj * pj;
+      if (next) a.w[j] = wj;
+    }
+  }
+  if (!next) return;
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) {
+    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+    if (gi < units) tn[gi] = acc[k];
+  }
+  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
+// configurations by feature length (units = ld/2 16-byte units per feature <= TG*EPTC*CPF)
+using CfgA = Cfg<512, 2, 5, 8>;   // ld <= 10240: one worker per CTA, 16 KB chunks, 8 in flight
+using CfgA4 = Cfg<512, 2, 5, 4>;  // same with a second resident n-vector (NaN trip, deflate): 4 in flight
+using CfgB = Cfg<256, 2, 5, 8>;   // ld <= 5120: two workers, 8 KB chunks
+using CfgC = Cfg<128, 5, 2, 4>;   // ld <= 2560: four workers, 10 KB chunks
+using CfgD = Cfg<64, 10, 1, 2>;   // ld <= 1280: eight workers, one chunk per feature
+// NaN trip: one extra n-vector PER WORKER (80 KB in total at every size), so shallower / finer rings
+using CfgBn = Cfg<256, 2, 5, 6>;
+using CfgCn = Cfg<128, 5, 2, 3>;
+using CfgDn = Cfg<64, 5, 2, 3>;
+
+template <bool NANMODE, class C>
+int launch_trip(const FusedArgs& a, cudaStream_t st) {
+  const size_t smem = fused_smem_bytes<C>(a.ld, NANMODE ? 1 + C::G : 1);
+  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
+  cudaFuncSetAttribute(fused_trip_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const int grid = (a.nsplit + C::G - 1) / C::G;
+  fused_trip_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
+  return MBPLS_OK;
+}
+
+template <class C>
+int launch_deflate(const FusedArgs& a, cudaStream_t st) {
+  const size_t smem = fused_smem_bytes<C>(a.ld, 2);
+  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
+  cudaFuncSetAttribute(fused_deflate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const int grid = (a.nsplit + C::G - 1) / C::G;
+  fused_deflate_kernel<C><<<grid, 512, smem, st>>>(a);
+  return MBPLS_OK;
+}
+
+int config_of(long ld) {  // 0: unsupported
+  if (ld < 16 || (ld % 16) != 0) return 0;
+  const long units = ld >> 1;
+  if (units <= 640) return 4;
+  if (units <= 1280) return 3;
+  if (units <= 2560) return 2;
+  if (units <= 5120) return 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* workers (splits) per CTA of the one-pass kernels for this leading dimension; 0 = feature too long */
+int mbpls_fused_workers_per_cta(long ld) {
+  switch (config_of(ld)) {
+    case 1: return CfgA::G;
+    case 2: return CfgB::G;
+    case 3: return CfgC::G;
+    case 4: return CfgD::G;
+    default: return 0;
+  }
+}
+
+int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const int* split_f0,
+                                const int* split_f1, const int* split_block, int nsplit, int B, double* w, double* norm_part,
+                                double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream) {
+  if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || (nanmode && !Tden) || ld < n ||
+      ldt < ld || B < 1)
+    return MBPLS_ERR_ARG;
+  if (nsplit == 0) return MBPLS_OK;
+  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, split_f0, split_f1, split_block, nsplit, B, w, norm_part, Tnum, Tden, ldt,
+              nullptr, nullptr, done};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = MBPLS_ERR_SIZE;
+  switch (config_of(ld)) {
+    case 1: rc = nanmode ? launch_trip<true, CfgA4>(a, st) : launch_trip<false, CfgA>(a, st); break;
+    case 2: rc = nanmode ? launch_trip<true, CfgBn>(a, st) : launch_trip<false, CfgB>(a, st); break;
+    case 3: rc = nanmode ? launch_trip<true, CfgCn>(a, st) : launch_trip<false, CfgC>(a, st); break;
+    case 4: rc = nanmode ? launch_trip<true, CfgDn>(a, st) : launch_trip<false, CfgD>(a, st); break;
+    default: break;
+  }
+  if (rc != MBPLS_OK) return rc;
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* u0, const double* u0u0,
+                            const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
+                            double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream) {
+  if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
+  if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld)) return MBPLS_ERR_ARG;
+  if (nsplit == 0) return MBPLS_OK;
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, split_f0, split_f1, split_block, nsplit, B, w_next, norm_part, Tnum, nullptr, ldt,
+              P_k, pss, nullptr};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = MBPLS_ERR_SIZE;
+  switch (config_of(ld)) {
+    case 1: rc = launch_deflate<CfgA4>(a, st); break;
+    case 2: rc = launch_deflate<CfgB>(a, st); break;
+    case 3: rc = launch_deflate<CfgC>(a, st); break;
+    case 4: rc = launch_deflate<CfgD>(a, st); break;
+    default: break;
+  }
+  if (rc != MBPLS_OK) return rc;
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"

@@ -341,7 +341,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                ycol_flag: Optional[torch.Tensor] = None, max_tol: float = 1e-14, norm_kind: int = 0,
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
-               deflate_last: bool = False) -> NipalsResult:
+               deflate_last: bool = False, one_pass: Optional[bool] = None,
+               one_pass_deflate: Optional[bool] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -362,6 +363,22 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     def buf(*shape, dtype=F64, zero=False):
         shape = tuple(max(int(s), 1) for s in shape)
         return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+
+    # one-pass kernels (csrc/fused.cu): a trip reads X once; they need the score accumulators of a whole feature in
+    # registers, i.e. ld <= 10240.  Their "workers" own one split each: size the split table to one persistent CTA per SM.
+    wpc = call("mbpls_fused_workers_per_cta", ld) if (one_pass is not False and p > 0) else 0
+    use_op = wpc > 0
+    if one_pass is True and not use_op and p > 0:
+        raise ValueError("one_pass=True needs a leading dimension of at most 10240 samples")
+    use_opd = use_op and not nan and one_pass_deflate is not False and deflate_mode == 0
+    if use_op:
+        of0, of1, obso = make_splits(block_off, 1, sm_count(dev), ctas_per_sm=wpc, min_feats=16)
+        nsplit_o = len(of0)
+        oblk = [b for b in range(B) for _ in range(obso[b + 1] - obso[b])]
+        osf0, osf1, osbso, osblk = _i32(of0, dev), _i32(of1, dev), _i32(obso, dev), _i32(oblk, dev)
+        Tnum_o = buf(nsplit_o, ld, zero=True)
+        Tden_o = buf(nsplit_o, ld, zero=True) if nan else None
+        norm_part_o = buf(nsplit_o * B, zero=True)
 
     w = buf(p)
     norm_part = buf(max(nparts, 1) * B, zero=True)
@@ -401,7 +418,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         # (a few microseconds each), so batching only removes host round-trips from the critical path
         est_ms = 2.0 * p * ld * 8 / 5e12 * 1e3
         trips_per_sync = 2 if est_ms > 1.0 else 4
-    w_ready = False  # True when w already holds the first weights of the coming component
+    # what the closing pass of the previous component left behind for the first trip of the coming one:
+    # None, "w" (its weights) or "scores" (weights, squared norms and partial block scores: no pass over X needed)
+    w_ready = None
     cur = torch.cuda.current_stream(dev)
 
     def timed(key, fn):
@@ -420,15 +439,24 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         launched = 0
         while True:
             for _ in range(trips_per_sync):
-                if launched == 0 and w_ready:
-                    call("mbpls_block_sumsq_parts_f64", ptr(w), p, ptr(boff), B, ptr(norm_part), done_p, st)
+                first = launched == 0
+                if (first and w_ready == "scores") or (use_op and not (first and w_ready == "w")):
+                    if not (first and w_ready == "scores"):
+                        timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(osf0),
+                                                   ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o), ptr(Tnum_o),
+                                                   ptr(Tden_o), ld, nan, done_p, st))
+                    call("mbpls_nipals_reduce_partials_f64", ptr(Tnum_o), ptr(Tden_o), ld, n, B, ptr(osbso),
+                         ptr(norm_part_o), nsplit_o, ptr(red_local), nan, done_p, st)
                 else:
-                    timed("xtu", lambda: call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(scal), ptr(boff), B,
-                                              ptr(w), ptr(norm_part), nan, done_p, st))
-                timed("xw", lambda: call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit,
-                                         ptr(Tnum), ptr(Tden), ld, nan, done_p, st))
-                call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
-                     nparts, ptr(red_local), nan, done_p, st)
+                    if first and w_ready == "w":
+                        call("mbpls_block_sumsq_parts_f64", ptr(w), p, ptr(boff), B, ptr(norm_part), done_p, st)
+                    else:
+                        timed("xtu", lambda: call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(u), ptr(scal), ptr(boff), B,
+                                                  ptr(w), ptr(norm_part), nan, done_p, st))
+                    timed("xw", lambda: call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit,
+                                             ptr(Tnum), ptr(Tden), ld, nan, done_p, st))
+                    call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
+                         nparts, ptr(red_local), nan, done_p, st)
                 if group is not None:
                     red.copy_(red_local)
                     allreduce_(red, group)
@@ -459,13 +487,20 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                                            ptr(res.P[k]), None, nan, None, st))
             if p > 0:
                 call("mbpls_block_sumsq_f64", ptr(res.P[k]), ptr(boff), B, ptr(res.pssb[k]), st)
+        elif use_opd:
+            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(u0) if fuse else None,
+                                          ptr(u0u0) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
+                                          ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
+                                          ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
+            call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
+            w_ready = "scores" if fuse else None
         else:
             timed("deflate", lambda: call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts),
                                           ptr(u0) if fuse else None, ptr(u0u0) if fuse else None, ptr(res.P[k]),
                                           ptr(w) if fuse else None, ptr(pss), nan, deflate_mode, st))
             if p > 0:
                 call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
-        w_ready = fuse
+            w_ready = "w" if fuse else None
     return res
 
 

@@ -45,6 +45,8 @@ _RUNTIME_DEFAULTS = dict(
     global_sizes=None,    # multi-GPU: the blocks passed in are this rank's column ranges of blocks of these sizes
     profile=None,         # dict collecting CUDA-event pairs per kernel (bench.py roofline)
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
+    one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 10240), False two-pass kernels
+    one_pass_deflate=None,  # dense data: loadings+deflation also runs the next component's whole first trip
 )
 
 
@@ -449,7 +451,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_tol=self.max_tol, norm_kind=E.norm_kind_of(self.nipals_convergence_norm),
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
-                           deflate_last=rt["deflate_last"])
+                           deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
+                           one_pass_deflate=rt["one_pass_deflate"])
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")

@@ -1,0 +1,117 @@
+"""GPU: the one-pass NIPALS kernels (csrc/fused.cu: one read of X per trip; loadings + deflation + the next
+component's first trip in one read + write) against the live numpy oracle, for every worker configuration
+(feature lengths up to 640 / 1280 / 2560 / 5120 16-byte units), dense and NaN-masked, and against the two-pass
+kernels they replace."""
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import assert_trips, compare, rel_err, snapshot_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _pair(kw, X, Y, **rt):
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(**kw).fit([x.copy() for x in X], Y.copy())
+        m = MBPLS(**kw).set_runtime(**rt).fit([x.copy() for x in X], Y.copy())
+    return m, o
+
+
+def _check(m, o, X, Y, kw, what):
+    ref, ours = snapshot_model(o, [x.copy() for x in X], Y.copy()), snapshot_model(m, [x.copy() for x in X], Y.copy())
+    worst = compare(ours, ref, TOL, what)
+    assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, kw.get("max_tol", 1e-14), what)
+    return worst
+
+
+# n chosen so that ld = round_up(n, 16) lands in each configuration, including its upper edge and ragged tails
+@pytest.mark.parametrize("n,sizes", [(37, (21, 40)), (640, (90, 33)), (1277, (70, 50)), (1300, (64, 48, 9)),
+                                     (2560, (80, 41)), (2570, (75, 30)), (5117, (60, 37)), (5200, (50, 45)),
+                                     (10000, (40, 56)), (10240, (33, 31))])
+def test_one_pass_dense_matches_oracle(n, sizes):
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(n, sizes, 2, 3, seed=n % 97)
+    kw = dict(n_components=3, method="NIPALS")
+    m, o = _pair(kw, X, Y, one_pass=True)
+    _check(m, o, X, Y, kw, f"one-pass dense n={n}")
+
+
+@pytest.mark.parametrize("n,sizes", [(45, (30, 17)), (1000, (60, 35)), (2000, (48, 40)), (4000, (40, 33)), (9000, (24, 30))])
+def test_one_pass_nan_matches_oracle(n, sizes):
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(n, sizes, 2, 2, seed=5 + n % 89, nan_frac=0.1)
+    X[1][:, 3] = np.where(np.isnan(X[1][:, 3]), 0.25, X[1][:, 3])  # one fully observed column (dense branch, :847)
+    kw = dict(n_components=2, method="NIPALS", sparse_data=True)
+    m, o = _pair(kw, X, Y, one_pass=True)
+    _check(m, o, X, Y, kw, f"one-pass NaN n={n}")
+    for b in range(2):
+        for a, r in zip(m.sparse_X_info_[b], o.sparse_X_info_[b]):
+            assert np.array_equal(a, r)
+
+
+def test_one_pass_pls1_many_blocks_single_features():
+    """Splits never straddle a block: blocks of 1 and 2 features next to wide ones, PLS1 (2 trips per component)."""
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(300, (1, 150, 2, 77, 1), 1, 4, seed=11)
+    kw = dict(n_components=4, method="NIPALS")
+    m, o = _pair(kw, X, Y.ravel(), one_pass=True)
+    _check(m, o, X, Y.ravel(), kw, "one-pass PLS1 ragged blocks")
+    assert list(m.n_iter_) == [2, 2, 2, 2]
+
+
+@pytest.mark.parametrize("nan_frac", [0.0, 0.08])
+def test_one_pass_agrees_with_two_pass_kernels(nan_frac):
+    """Same fit through the one-pass kernels, through the two-pass kernels, and with only the deflation fused."""
+    from oracle.cases import latent_blocks
+    from mbpls_b200 import MBPLS
+    X, Y = latent_blocks(3000, (700, 420, 1300), 3, 4, seed=21, nan_frac=nan_frac)
+    kw = dict(n_components=4, method="NIPALS", sparse_data=nan_frac > 0)
+    fits = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, rt in (("one", dict(one_pass=True)), ("two", dict(one_pass=False)),
+                         ("trip_only", dict(one_pass=True, one_pass_deflate=False))):
+            fits[name] = MBPLS(**kw).set_runtime(**rt).fit([x.copy() for x in X], Y.copy())
+    ref = fits["two"]
+    for name in ("one", "trip_only"):
+        m = fits[name]
+        assert list(m.n_iter_) == list(ref.n_iter_), (name, m.n_iter_, ref.n_iter_)
+        assert rel_err(m.beta_, ref.beta_) < 1e-10
+        for k in range(4):
+            s = np.sign(np.dot(m.Ts_[:, k], ref.Ts_[:, k]))
+            assert rel_err(s * m.Ts_[:, k], ref.Ts_[:, k]) < 1e-10
+            for b in range(3):
+                assert rel_err(s * m.P_[b][:, k], ref.P_[b][:, k]) < 1e-10
+                assert rel_err(s * m.W_[b][:, k], ref.W_[b][:, k]) < 1e-10
+                assert rel_err(s * m.T_[b][:, k], ref.T_[b][:, k]) < 1e-10
+        assert rel_err(m.A_, ref.A_) < 1e-10
+        assert rel_err(np.asarray(m.explained_var_xblocks_), np.asarray(ref.explained_var_xblocks_)) < 1e-10
+
+
+def test_one_pass_is_reproducible_bitwise():
+    from oracle.cases import latent_blocks
+    from mbpls_b200 import MBPLS
+    X, Y = latent_blocks(2100, (900, 650), 2, 3, seed=4)
+    outs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(2):
+            m = MBPLS(n_components=3).set_runtime(one_pass=True).fit([x.copy() for x in X], Y.copy())
+            outs.append((m.Ts_.copy(), m.beta_.copy(), list(m.n_iter_)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_one_pass_rejects_long_features():
+    from mbpls_b200 import MBPLS
+    rng = np.random.default_rng(0)
+    X, Y = rng.standard_normal((10300, 6)), rng.standard_normal(10300)
+    with pytest.raises(ValueError):
+        MBPLS(n_components=1).set_runtime(one_pass=True).fit(X, Y)
+    m = MBPLS(n_components=1).fit(X, Y)  # auto: falls back to the two-pass kernels
+    assert m.beta_.shape == (6, 1)
