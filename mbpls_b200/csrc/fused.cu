@@ -39,6 +39,10 @@
 
 using namespace mbpls;
 
+#ifndef MBPLS_FUSED_PIPE
+#define MBPLS_FUSED_PIPE 0
+#endif
+
 namespace {
 
 struct FusedArgs {
@@ -74,7 +78,8 @@ struct Cfg {
 };
 
 // fixed-order sum over the TG threads of one worker; `buf` holds NV*NW doubles and must alternate between
-// two buffers from call to call (a single named barrier per call is then enough).
+// two buffers from call to call (a single named barrier per call is then enough).  After the barrier every
+// thread reads all NW warp partials (broadcast loads) and adds them in the same fixed tree.
 template <int NV, int TG>
 __device__ __forceinline__ void worker_sum(double (&v)[NV], double* buf, int g, int warp_in_group, int lane) {
   constexpr int NW = TG / 32;
@@ -87,16 +92,28 @@ __device__ __forceinline__ void worker_sum(double (&v)[NV], double* buf, int g, 
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TG) : "memory");
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    double t = lane < NW ? buf[k * NW + lane] : 0.0;
+    const double2* pr = reinterpret_cast<const double2*>(buf + k * NW);
+    if (NW == 2) {
+      const double2 p0 = pr[0];
+      v[k] = p0.x + p0.y;
+    } else {  // groups of four partials, then the groups: few live registers next to the accumulators
+      double grp[NW >= 4 ? NW / 4 : 1];
 #pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) t += __shfl_xor_sync(MBPLS_FULL_MASK, t, o);
-    v[k] = __shfl_sync(MBPLS_FULL_MASK, t, 0);
+      for (int q = 0; q < NW / 4; ++q) {
+        const double2 p0 = pr[2 * q], p1 = pr[2 * q + 1];
+        grp[q] = (p0.x + p0.y) + (p1.x + p1.y);
+      }
+      double t = grp[0];
+      if (NW == 8) t = grp[0] + grp[1];
+      if (NW == 16) t = (grp[0] + grp[1]) + (grp[2] + grp[3]);
+      v[k] = t;
+    }
   }
 }
 
-__device__ __forceinline__ unsigned atom_inc_acq_rel_smem(unsigned* p) {
+__device__ __forceinline__ unsigned atom_inc_smem(unsigned* p) {
   unsigned old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
   return old;
 }
 
@@ -159,28 +176,38 @@ __device__ __forceinline__ void prime_ring(const double* __restrict__ X, long ld
   }
 }
 
-// The calling warp is done reading stage (g, s), which held chunk c of feature j.  The last warp of the worker to
-// say so refills the stage with the chunk S positions further down the worker's stream.
+// The calling warp is done reading stage (g, s).  Returns the number of warps that had said so before (lane 0 only).
 template <class C>
-__device__ __forceinline__ void release_stage(const double* __restrict__ X, long ld, int units, int ncf, int g, int s, int j, int c,
-                                              int f1, int lane, const Smem<C>& sm) {
+__device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const Smem<C>& sm) {
   __syncwarp();
-  if (lane == 0) {
-    unsigned* ctr = &sm.cnt[2 * (g * C::S + s)];
-    if (atom_inc_acq_rel_smem(ctr) == C::NW - 1) {
-      *reinterpret_cast<volatile unsigned*>(ctr) = 0;
-      int c2 = c + C::S, f2 = j;
-      while (c2 >= ncf) { c2 -= ncf; ++f2; }
-      if (f2 < f1) {
-        fence_proxy_async_smem();  // generic-proxy reads of the stage (all warps, ordered by the counter) before the async write
-        issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
-      }
+  return lane == 0 ? atom_inc_smem(&sm.cnt[2 * (g * C::S + s)]) : 0u;
+}
+
+// The last warp of the worker to arrive on a stage (which held chunk c of feature j) refills it with the chunk S
+// positions further down the worker's stream.  Called one chunk after arrive_stage, so that the shared-memory
+// atomic's latency is off the critical path.
+template <class C>
+__device__ __forceinline__ void refill_if_last(unsigned old, const double* __restrict__ X, long ld, int units, int ncf, int g, int s,
+                                               int j, int c, int f1, int lane, const Smem<C>& sm) {
+  if (lane == 0 && old == C::NW - 1) {
+    *reinterpret_cast<volatile unsigned*>(&sm.cnt[2 * (g * C::S + s)]) = 0;
+    int c2 = c + C::S, f2 = j;
+    while (c2 >= ncf) { c2 -= ncf; ++f2; }
+    if (f2 < f1) {
+#ifdef MBPLS_FUSED_PROXY_FENCE
+      fence_proxy_async_smem();
+#endif
+      issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // one NIPALS trip in one pass
+//
+// Software pipeline without extra registers: iteration j first applies the PREVIOUS feature's weight to the
+// accumulators (acc += w~_{j-1} x) unit by unit and reloads each x register with feature j right behind it,
+// so the score update hides under the shared-memory-bound load phase.
 // ------------------------------------------------------------------------------------------
 template <bool NANMODE, class C>
 __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
@@ -204,56 +231,120 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
   if (tg == 0) prime_ring<C>(a.Xt, ld, units, ncf, g, f0, f1, sm);
   const double uu = *a.uu;
+  const double inv_uu = 1.0 / uu;
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
   double2* __restrict__ miss2 = reinterpret_cast<double2*>(sm.vec1 + (NANMODE ? static_cast<size_t>(g) * ld : 0));
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
 
-  double2 acc[C::EPT];
+  double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
-  for (int k = 0; k < C::EPT; ++k) acc[k] = make_double2(0.0, 0.0);
-  double normsq = 0.0;
+  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0, wj = 0.0, w2 = 0.0;
+  uint32_t mx = 0, my = 0;  // NaN masks of the units held in x (x / y halves)
   int s = 0;
   uint32_t ph = 0;
   int flip = 0;
 
-  for (int j = f0; j < f1; ++j) {
-    double2 x[C::EPT];
+  for (int j = f0; j <= f1; ++j) {
+    const bool load = j < f1;  // the last iteration only applies the last weight
     double v[3] = {0.0, 0.0, 0.0};  // numerator, masked u'u, NaN seen
-    double numb = 0.0;
-    uint32_t mx = 0, my = 0;  // NaN masks of this thread's units (x / y halves)
-#pragma unroll
-    for (int c = 0; c < C::CPF; ++c) {
-      if (c < ncf) {
+    double numb = 0.0, numc = 0.0, numd = 0.0;
+    uint32_t nmx = 0, nmy = 0;
+    int s_use = s;  // s: next stage to load from; s_use: stage of the chunk being consumed
+    constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;  // few units per chunk: issue chunk c+1's loads before consuming chunk c
+    double2 ub[2][PIPE ? C::EPTC : 1];  // u values travelling with the chunk in flight
+
+    // L(c): previous feature's weight into the accumulators, then this feature's chunk c into the freed registers
+    auto load_chunk = [&](const int c) {
+      const bool have = load && c < ncf;
+      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+      if (have) {
         mbar_wait(&sm.full[g * C::S + s], ph);
-        const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
-        const bool whole = c + 1 < ncf;  // every chunk but the last of a feature is full: no bounds checks
+        if (++s == C::S) { s = 0; ph ^= 1u; }
+      }
+      const bool whole = c + 1 < ncf;  // every chunk but the last of a feature is full: no bounds checks
 #pragma unroll
-        for (int e = 0; e < C::EPTC; ++e) {
-          const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
-          if (whole || gi < units) {
-            double2 xv = xs[l];
-            const double2 uv = u2[gi];
-            if (NANMODE) {
-              const bool bx = isnan(xv.x), by = isnan(xv.y);
-              if (bx) { xv.x = 0.0; mx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
-              if (by) { xv.y = 0.0; my |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
-            }
-            v[0] = fma(xv.x, uv.x, v[0]);
-            numb = fma(xv.y, uv.y, numb);
-            x[k] = xv;
-          } else {
-            x[k] = make_double2(0.0, 0.0);
+      for (int e = 0; e < C::EPTC; ++e) {
+        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+        acc[k].x = fma(wj, x[k].x, acc[k].x);
+        acc[k].y = fma(wj, x[k].y, acc[k].y);
+        if (NANMODE) {
+          if (((mx | my) >> k) & 1u) {
+            double2 m = miss2[gi];
+            if ((mx >> k) & 1u) m.x += w2;
+            if ((my >> k) & 1u) m.y += w2;
+            miss2[gi] = m;
           }
         }
-        release_stage<C>(a.Xt, ld, units, ncf, g, s, j, c, f1, lane, sm);
-        if (++s == C::S) { s = 0; ph ^= 1u; }
-      } else {
+        double2 xv = make_double2(0.0, 0.0), uv = make_double2(0.0, 0.0);
+        if (have && (whole || gi < units)) {
+          xv = xs[l];
+          uv = u2[gi];
+        }
+        if (PIPE) {
+          ub[c & 1][e] = uv;
+        } else if (have) {  // consume on the spot
+          if (NANMODE) {
+            const bool bx = isnan(xv.x), by = isnan(xv.y);
+            if (bx) { xv.x = 0.0; nmx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
+            if (by) { xv.y = 0.0; nmy |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
+          }
+          if (e & 1) {
+            numc = fma(xv.x, uv.x, numc);
+            numd = fma(xv.y, uv.y, numd);
+          } else {
+            v[0] = fma(xv.x, uv.x, v[0]);
+            numb = fma(xv.y, uv.y, numb);
+          }
+        }
+        x[k] = xv;
+      }
+    };
+    // F(c): dot product of chunk c (its loads were issued one step earlier), then hand the stage back
+    auto use_chunk = [&](const int c) {
+      if (!(load && c < ncf)) return;
 #pragma unroll
-        for (int e = 0; e < C::EPTC; ++e) x[c * C::EPTC + e] = make_double2(0.0, 0.0);
+      for (int e = 0; e < (PIPE ? C::EPTC : 0); ++e) {
+        const int k = c * C::EPTC + e;
+        double2 xv = x[k];
+        const double2 uv = ub[c & 1][e];
+        if (NANMODE) {
+          const bool bx = isnan(xv.x), by = isnan(xv.y);
+          if (bx) { xv.x = 0.0; nmx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
+          if (by) { xv.y = 0.0; nmy |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
+          x[k] = xv;
+        }
+        if (e & 1) {
+          numc = fma(xv.x, uv.x, numc);
+          numd = fma(xv.y, uv.y, numd);
+        } else {
+          v[0] = fma(xv.x, uv.x, v[0]);
+          numb = fma(xv.y, uv.y, numb);
+        }
+      }
+      // refill at once: every cycle a free stage sits idle is ring depth lost (deferring the check by one chunk to
+      // hide the atomic's latency cost 10 % on the shallow rings)
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xt, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
+      if (++s_use == C::S) s_use = 0;
+    };
+    if (PIPE) {
+      load_chunk(0);
+#pragma unroll
+      for (int c = 0; c < C::CPF; ++c) {
+        if (c + 1 < C::CPF) load_chunk(c + 1);
+        use_chunk(c);
+      }
+    } else {  // many independent loads per chunk already (and several workers per SM): no extra registers
+#pragma unroll
+      for (int c = 0; c < C::CPF; ++c) {
+        load_chunk(c);
+        use_chunk(c);
       }
     }
-    v[0] += numb;
-    double wj;
+    if (!load) break;
+    mx = nmx;
+    my = nmy;
+    v[0] = (v[0] + numb) + (numc + numd);
     if (NANMODE) {
       v[2] = (mx | my) ? 1.0 : 0.0;
       worker_sum<3, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
@@ -261,31 +352,12 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     } else {
       double one[1] = {v[0]};
       worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
-      wj = one[0] / uu;
+      wj = one[0] * inv_uu;
     }
     flip ^= 1;
     if (tg == 0) a.w[j] = wj;
-    const double w2 = wj * wj;
+    w2 = wj * wj;
     normsq += w2;
-#pragma unroll
-    for (int k = 0; k < C::EPT; ++k) {
-      acc[k].x = fma(wj, x[k].x, acc[k].x);
-      acc[k].y = fma(wj, x[k].y, acc[k].y);
-    }
-    if (NANMODE) {
-      if (mx | my) {
-#pragma unroll
-        for (int k = 0; k < C::EPT; ++k) {
-          if (((mx | my) >> k) & 1u) {
-            const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
-            double2 m = miss2[gi];
-            if ((mx >> k) & 1u) m.x += w2;
-            if ((my >> k) & 1u) m.y += w2;
-            miss2[gi] = m;
-          }
-        }
-      }
-    }
   }
 
   // partial block scores of this split (the layout xw_kernel writes)
@@ -306,7 +378,8 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// loadings + deflation + the whole first trip of the next component (dense data)
+// loadings + deflation + the whole first trip of the next component (dense data); same pipeline: the score
+// update of feature j-1 rides on the load phase of feature j.
 // ------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
@@ -329,54 +402,96 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   if (wk >= a.nsplit) return;
   const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
   if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
-  const double uu = next ? *a.uu : 1.0;
+  const double inv_uu = next ? 1.0 / *a.uu : 1.0;
   const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec1);
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
 
-  double2 acc[C::EPT];
+  double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
-  for (int k = 0; k < C::EPT; ++k) acc[k] = make_double2(0.0, 0.0);
-  double normsq = 0.0;
+  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0, wj = 0.0;
   int s = 0;
   uint32_t ph = 0;
   int flip = 0;
 
-  for (int j = f0; j < f1; ++j) {
-    double2 x[C::EPT];
-    double pa = 0.0, pb = 0.0;
-#pragma unroll
-    for (int c = 0; c < C::CPF; ++c) {
-      if (c < ncf) {
+  for (int j = f0; j <= f1; ++j) {
+    const bool load = j < f1;
+    double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
+    int s_use = s;
+    constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;
+    double2 tb[2][PIPE ? C::EPTC : 1];  // ts values travelling with the chunk in flight
+
+    auto load_chunk = [&](const int c) {
+      const bool have = load && c < ncf;
+      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+      if (have) {
         mbar_wait(&sm.full[g * C::S + s], ph);
-        const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
-        const bool whole = c + 1 < ncf;
-#pragma unroll
-        for (int e = 0; e < C::EPTC; ++e) {
-          const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
-          if (whole || gi < units) {
-            const double2 xv = xs[l];
-            const double2 tv = ts2[gi];
-            pa = fma(xv.x, tv.x, pa);
-            pb = fma(xv.y, tv.y, pb);
-            x[k] = xv;
-          } else {
-            x[k] = make_double2(0.0, 0.0);
-          }
-        }
-        release_stage<C>(a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm);
         if (++s == C::S) { s = 0; ph ^= 1u; }
-      } else {
+      }
+      const bool whole = c + 1 < ncf;
 #pragma unroll
-        for (int e = 0; e < C::EPTC; ++e) x[c * C::EPTC + e] = make_double2(0.0, 0.0);
+      for (int e = 0; e < C::EPTC; ++e) {
+        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+        acc[k].x = fma(wj, x[k].x, acc[k].x);  // next component's block-score partials with the previous feature's weight
+        acc[k].y = fma(wj, x[k].y, acc[k].y);
+        double2 xv = make_double2(0.0, 0.0), tv = make_double2(0.0, 0.0);
+        if (have && (whole || gi < units)) {
+          xv = xs[l];
+          tv = ts2[gi];
+        }
+        if (PIPE) {
+          tb[c & 1][e] = tv;
+        } else if (e & 1) {
+          pc = fma(xv.x, tv.x, pc);
+          pd = fma(xv.y, tv.y, pd);
+        } else {
+          pa = fma(xv.x, tv.x, pa);
+          pb = fma(xv.y, tv.y, pb);
+        }
+        x[k] = xv;
+      }
+    };
+    auto use_chunk = [&](const int c) {
+      if (!(load && c < ncf)) return;
+#pragma unroll
+      for (int e = 0; e < (PIPE ? C::EPTC : 0); ++e) {
+        const int k = c * C::EPTC + e;
+        const double2 tv = tb[c & 1][e];
+        if (e & 1) {
+          pc = fma(x[k].x, tv.x, pc);
+          pd = fma(x[k].y, tv.y, pd);
+        } else {
+          pa = fma(x[k].x, tv.x, pa);
+          pb = fma(x[k].y, tv.y, pb);
+        }
+      }
+      // refill at once: every cycle a free stage sits idle is ring depth lost (deferring the check by one chunk to
+      // hide the atomic's latency cost 10 % on the shallow rings)
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xw, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
+      if (++s_use == C::S) s_use = 0;
+    };
+    if (PIPE) {
+      load_chunk(0);
+#pragma unroll
+      for (int c = 0; c < C::CPF; ++c) {
+        if (c + 1 < C::CPF) load_chunk(c + 1);
+        use_chunk(c);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C::CPF; ++c) {
+        load_chunk(c);
+        use_chunk(c);
       }
     }
-    double one[1] = {pa + pb};
+    if (!load) break;
+    double one[1] = {(pa + pb) + (pc + pd)};
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
     const double pj = one[0];
     double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j) * ld);
-    double wa = 0.0, wb = 0.0;
+    double wa = 0.0, wb = 0.0, wc = 0.0, wd = 0.0;
 #pragma unroll
     for (int k = 0; k < C::EPT; ++k) {
       const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
@@ -389,23 +504,22 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
         x[k] = xn;
         if (next) {
           const double2 uv = u2[gi];
-          wa = fma(xn.x, uv.x, wa);
-          wb = fma(xn.y, uv.y, wb);
+          if (k & 1) {
+            wc = fma(xn.x, uv.x, wc);
+            wd = fma(xn.y, uv.y, wd);
+          } else {
+            wa = fma(xn.x, uv.x, wa);
+            wb = fma(xn.y, uv.y, wb);
+          }
         }
       }
     }
-    double wj = 0.0;
     if (next) {
-      double two[1] = {wa + wb};
+      double two[1] = {(wa + wb) + (wc + wd)};
       worker_sum<1, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
       flip ^= 1;
-      wj = two[0] / uu;
+      wj = two[0] * inv_uu;
       normsq = fma(wj, wj, normsq);
-#pragma unroll
-      for (int k = 0; k < C::EPT; ++k) {
-        acc[k].x = fma(wj, x[k].x, acc[k].x);
-        acc[k].y = fma(wj, x[k].y, acc[k].y);
-      }
     }
     if (tg == 0) {
       a.P_k[j] = pj;
@@ -423,14 +537,17 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
 }
 
-// configurations by feature length (units = ld/2 16-byte units per feature <= TG*EPTC*CPF)
-using CfgA = Cfg<512, 2, 5, 8>;   // ld <= 10240: one worker per CTA, 16 KB chunks, 8 in flight
-using CfgA4 = Cfg<512, 2, 5, 4>;  // same with a second resident n-vector (NaN trip, deflate): 4 in flight
-using CfgB = Cfg<256, 2, 5, 8>;   // ld <= 5120: two workers, 8 KB chunks
+// Configurations by feature length (units = ld/2 16-byte units per feature <= TG*EPTC*CPF).  Measured (profiles/r1_notes.md):
+// every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as the ring allows:
+// the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
+using CfgA = Cfg<512, 5, 2, 3>;   // ld <= 10240: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
+using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with a second resident n-vector (NaN trip, deflate): only 64 KB of ring left
+using CfgA8 = Cfg<512, 2, 5, 8>;  // experiment (MBPLS_FUSED_ALT): 16 KB chunks, 8 in flight
+using CfgB = Cfg<256, 5, 2, 3>;   // ld <= 5120: two workers, 20 KB chunks
 using CfgC = Cfg<128, 5, 2, 4>;   // ld <= 2560: four workers, 10 KB chunks
 using CfgD = Cfg<64, 10, 1, 2>;   // ld <= 1280: eight workers, one chunk per feature
 // NaN trip: one extra n-vector PER WORKER (80 KB in total at every size), so shallower / finer rings
-using CfgBn = Cfg<256, 2, 5, 6>;
+using CfgBn = Cfg<256, 5, 2, 2>;
 using CfgCn = Cfg<128, 5, 2, 3>;
 using CfgDn = Cfg<64, 5, 2, 3>;
 
@@ -491,7 +608,11 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
-    case 1: rc = nanmode ? launch_trip<true, CfgA4>(a, st) : launch_trip<false, CfgA>(a, st); break;
+    case 1:
+      if (nanmode) rc = launch_trip<true, CfgA4>(a, st);
+      else if (getenv("MBPLS_FUSED_ALT")) rc = launch_trip<false, CfgA8>(a, st);
+      else rc = launch_trip<false, CfgA>(a, st);
+      break;
     case 2: rc = nanmode ? launch_trip<true, CfgBn>(a, st) : launch_trip<false, CfgB>(a, st); break;
     case 3: rc = nanmode ? launch_trip<true, CfgCn>(a, st) : launch_trip<false, CfgC>(a, st); break;
     case 4: rc = nanmode ? launch_trip<true, CfgDn>(a, st) : launch_trip<false, CfgD>(a, st); break;

@@ -366,7 +366,11 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
 
     # one-pass kernels (csrc/fused.cu): a trip reads X once; they need the score accumulators of a whole feature in
     # registers, i.e. ld <= 10240.  Their "workers" own one split each: size the split table to one persistent CTA per SM.
-    wpc = call("mbpls_fused_workers_per_cta", ld) if (one_pass is not False and p > 0) else 0
+    # Auto policy (measured, profiles/r1_notes.md): dense data -> one-pass whenever the feature fits; NaN-masked data ->
+    # two-pass kernels (the masked one-pass trip keeps a second n-vector per worker in shared memory, which leaves a
+    # 64 KB ring: 2.6-3.6 TB/s for one read against 2 x 6.8 TB/s), unless one_pass=True forces it.
+    want_op = one_pass is True or (one_pass is None and not nan)
+    wpc = call("mbpls_fused_workers_per_cta", ld) if (want_op and p > 0) else 0
     use_op = wpc > 0
     if one_pass is True and not use_op and p > 0:
         raise ValueError("one_pass=True needs a leading dimension of at most 10240 samples")

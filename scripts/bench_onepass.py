@@ -62,6 +62,10 @@ if "c3" in which:
 if "c3q10" in which:
     S8 = [int(s * scale) for s in (20000, 35000, 60000, 95000, 140000, 180000, 220000, 450000)]
     run("C3 8 blocks n=2000 q=10", 2000, S8, 20, 10, 0.0, reps=1, variants=VARIANTS[::2])
+if "c3nan" in which:
+    S8 = [int(s * scale) for s in (20000, 35000, 60000, 95000, 140000, 180000, 220000, 450000)]
+    run("C3 8 blocks n=2000 q=1 10% NaN", 2000, S8, 20, 1, 0.10)
+    run("n=4000 p=500k q=1 10% NaN", 4000, [int(500_000 * scale)], 10, 1, 0.10)
 if "mid" in which:
     run("n=4000 p=500k q=1", 4000, [int(500_000 * scale)], 10, 1, 0.0)
     run("n=1000 p=2M q=1", 1000, [int(2_000_000 * scale)], 10, 1, 0.0)
