@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 // the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
 using CfgA = Cfg<512, 5, 2, 3>;   // ld <= 10240: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
 using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with a second resident n-vector (NaN trip, deflate): only 64 KB of ring left
+using CfgA4x = Cfg<512, 4, 3, 2>; // experiment (MBPLS_FUSED_ALT, deflate): 32 KB chunks x 2, 12 units per thread
 using CfgA8 = Cfg<512, 2, 5, 8>;  // experiment (MBPLS_FUSED_ALT): 16 KB chunks, 8 in flight
 using CfgB = Cfg<256, 5, 2, 3>;   // ld <= 5120: two workers, 20 KB chunks
 using CfgC = Cfg<128, 5, 2, 4>;   // ld <= 2560: four workers, 10 KB chunks
@@ -633,7 +634,7 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
-    case 1: rc = launch_deflate<CfgA4>(a, st); break;
+    case 1: rc = getenv("MBPLS_FUSED_ALT") ? launch_deflate<CfgA4x>(a, st) : launch_deflate<CfgA4>(a, st); break;
     case 2: rc = launch_deflate<CfgB>(a, st); break;
     case 3: rc = launch_deflate<CfgC>(a, st); break;
     case 4: rc = launch_deflate<CfgD>(a, st); break;

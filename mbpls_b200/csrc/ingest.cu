@@ -388,14 +388,24 @@ scaler_finish_kernel(const double* __restrict__ corr, const double* __restrict__
   var[j] = v;
 }
 
-// Deterministic segmented sum: out[s] = sum(v[off[s] .. off[s+1])), one CTA per segment.
-__global__ void __launch_bounds__(256) segsum_kernel(const double* __restrict__ v, const int* __restrict__ off,
-                                                     double* __restrict__ out) {
+// Deterministic segmented sum: out[s] = sum(v[off[s] .. off[s+1])), one 1024-thread CTA per segment, four independent
+// loads in flight per thread (a block of 400k features used to take 0.7 ms with 256 threads and one load at a time).
+__global__ void __launch_bounds__(1024) segsum_kernel(const double* __restrict__ v, const int* __restrict__ off,
+                                                      double* __restrict__ out) {
   __shared__ double scratch[32];
   const int s = blockIdx.x;
   const int a = off[s], b = off[s + 1];
-  double acc = 0.0;
-  for (int i = a + threadIdx.x; i < b; i += blockDim.x) acc += v[i];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int i = a + threadIdx.x;
+  for (; i + 3 * 1024 < b; i += 4 * 1024) {
+    const double v0 = v[i], v1 = v[i + 1024], v2 = v[i + 2048], v3 = v[i + 3072];
+    a0 += v0;
+    a1 += v1;
+    a2 += v2;
+    a3 += v3;
+  }
+  for (; i < b; i += 1024) a0 += v[i];
+  double acc = (a0 + a1) + (a2 + a3);
   acc = block_sum1(acc, scratch);
   if (threadIdx.x == 0) out[s] = acc;
 }
@@ -514,7 +524,7 @@ int mbpls_scaler_finish_f64(const double* corr, const double* ssq, const double*
 int mbpls_segsum_f64(const double* v, const int* off, int nseg, double* out, void* stream) {
   if (!v || !off || !out || nseg < 0) return MBPLS_ERR_ARG;
   if (nseg == 0) return MBPLS_OK;
-  segsum_kernel<<<nseg, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, off, out);
+  segsum_kernel<<<nseg, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, off, out);
   MBPLS_RETURN_LAST();
 }
 
