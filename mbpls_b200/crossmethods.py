@@ -137,21 +137,16 @@ def _bip_corrected(a, sizes):
 def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=None):
     """Register lazily materialised attributes shared by the three methods."""
     B = len(shard.sizes)
-    bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
-
-    def split_T(full):
-        return [np.ascontiguousarray(full[:, bounds[b]:bounds[b + 1]].T) for b in range(B)]
-
     lazy = {
         "Ts_": lambda: model._gather_samples(Ts, n),
         "U_": lambda: model._gather_samples(U, n) if U is not None else np.empty((n, 0)),
         "V_": lambda: np.ascontiguousarray(V.cpu().numpy().T),
-        "P_": lambda: split_T(model._gather_features(P, shard)),
-        "R_": lambda: np.ascontiguousarray(model._gather_features(R, shard).T),
-        "beta_": lambda: np.ascontiguousarray(model._gather_features(beta, shard).T),
+        "P_": lambda: model._features_T(P, shard, True),
+        "R_": lambda: model._features_T(R, shard, False),
+        "beta_": lambda: model._features_T(beta, shard, False),
     }
     if Wb is not None:
-        lazy["W_"] = lambda: split_T(model._gather_features(Wb, shard))
+        lazy["W_"] = lambda: model._features_T(Wb, shard, True)
     if Tb is not None:
         lazy["T_"] = lambda: [model._gather_samples(Tb[b], n) for b in range(B)]
     if lazy_extra:
@@ -216,7 +211,7 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
     model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
     model.W_concat_ = np.empty((shard.p_global, 0))
     _finish_common(model, shard, n, q, R, beta, P, Tm, U, Q, None, None,
-                   {"W_": lambda: np.ascontiguousarray(model._gather_features(W, shard).T)})
+                   {"W_": lambda: model._features_T(W, shard, False)})
 
 
 # ---- UNIPALS (mbpls.py:384-574) ------------------------------------------------------------------
@@ -449,7 +444,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
     model.explained_var_x_, model.explained_var_y_, model.explained_var_xblocks_ = evx, evy, evxb
     model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
     Wc_keep = Wc
-    extra = {"W_concat_": lambda: np.ascontiguousarray(model._gather_features(Wc_keep, shard).T)}
+    extra = {"W_concat_": lambda: model._features_T(Wc_keep, shard, False)}
     if not calc_all:
         extra["W_"] = lambda: [np.empty((s, 0)) for s in shard.sizes]
         extra["T_"] = lambda: [np.empty((ng, 0)) for _ in shard.sizes]

@@ -98,6 +98,16 @@ def _i32(vals, device):
 # ingest: host / device arrays -> feature-major device matrix
 # --------------------------------------------------------------------------------------------- #
 _STAGE_BYTES = 64 << 20
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _COPY_STREAMS[key] = st
+    return st
 
 
 def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, device) -> None:
@@ -134,12 +144,26 @@ def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, dev
         torch.cuda.current_stream(device).synchronize()  # `view` may be a temporary
         return
     rows_per = max(1, min(n, _STAGE_BYTES // max(8 * cols, 1)))
-    stage = torch.empty((rows_per, cols), dtype=F64, device=device)
-    for r0 in range(0, n, rows_per):
+    # two staging buffers: the copy engine fills one (side stream) while the transpose kernel drains the other
+    main = torch.cuda.current_stream(device)
+    side = _copy_stream(device)
+    stages = [torch.empty((rows_per, cols), dtype=F64, device=device) for _ in range(2 if n > rows_per else 1)]
+    drained = [None] * len(stages)
+    side.wait_stream(main)  # dst / staging allocations and earlier writes are ordered on the main stream
+    for idx, r0 in enumerate(range(0, n, rows_per)):
         r1 = min(n, r0 + rows_per)
-        stage[:r1 - r0].copy_(view[r0:r1], non_blocking=True)
-        call("mbpls_transpose_in_f64", ptr(stage), cols, r1 - r0, cols, ptr(dst), ld, r0, stream_ptr(device))
-    torch.cuda.current_stream(device).synchronize()
+        i = idx % len(stages)
+        with torch.cuda.stream(side):
+            if drained[i] is not None:
+                side.wait_event(drained[i])
+            stages[i][:r1 - r0].copy_(view[r0:r1], non_blocking=True)
+            filled = torch.cuda.Event()
+            filled.record(side)
+        main.wait_event(filled)
+        call("mbpls_transpose_in_f64", ptr(stages[i]), cols, r1 - r0, cols, ptr(dst), ld, r0, stream_ptr(device))
+        drained[i] = torch.cuda.Event()
+        drained[i].record(main)
+    main.synchronize()
 
 
 def try_adopt_feature_major(blocks, n: int):

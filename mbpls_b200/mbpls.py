@@ -139,11 +139,11 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         import torch.distributed as dist
         return group, dist.get_rank(group), dist.get_world_size(group)
 
-    def _gather_features(self, t_local: torch.Tensor, shard: ShardMap) -> np.ndarray:
-        """K x p_local device tensor -> K x p_global numpy array (same on every rank)."""
+    def _gather_features_dev(self, t_local: torch.Tensor, shard: ShardMap) -> torch.Tensor:
+        """K x p_local device tensor -> K x p_global device tensor (same on every rank)."""
         group, rank, world = self._group_info()
         if world == 1 or shard.world == 1:  # single GPU, or feature axis replicated (row-sharded fit)
-            return t_local[:, :shard.p_local].cpu().numpy()
+            return t_local[:, :shard.p_local]
         import torch.distributed as dist
         per = -(-shard.p_global // world)
         K = t_local.shape[0]
@@ -151,8 +151,21 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         pad[:, :shard.p_local] = t_local[:, :shard.p_local]
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad, group=group)
-        full = torch.cat(parts, dim=1)[:, :shard.p_global]
-        return full.cpu().numpy()
+        return torch.cat(parts, dim=1)[:, :shard.p_global]
+
+    def _gather_features(self, t_local: torch.Tensor, shard: ShardMap) -> np.ndarray:
+        """K x p_local device tensor -> K x p_global numpy array (same on every rank)."""
+        return self._gather_features_dev(t_local, shard).cpu().numpy()
+
+    def _features_T(self, t_local: torch.Tensor, shard: ShardMap, split: bool):
+        """Component-major K x p_local device result -> the reference's layout: one p_global x K numpy array, or (split)
+        the list of per-block p_b x K arrays.  The transposition runs on the device, so the host only receives
+        contiguous copies (the strided numpy transposes of five 160 MB arrays cost 0.4 s at the headline size)."""
+        full = self._gather_features_dev(t_local, shard)
+        if not split:
+            return full.t().contiguous().cpu().numpy()
+        bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
+        return [full[:, int(bounds[b]):int(bounds[b + 1])].t().contiguous().cpu().numpy() for b in range(len(shard.sizes))]
 
     def _gather_samples(self, t: torch.Tensor, n_local: int) -> np.ndarray:
         """K x ld device tensor of per-sample results -> n x K numpy array; concatenates the row shards when the
@@ -484,21 +497,16 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             self.A_corrected_ = np.empty((B, 0))
         self.W_concat_ = np.empty((shard.p_global, 0))
 
-        bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
-
-        def split_T(full):  # K x p_global -> list of p_b x K
-            return [np.ascontiguousarray(full[:, bounds[b]:bounds[b + 1]].T) for b in range(B)]
-
         lazy = {
             "Ts_": lambda: np.ascontiguousarray(res.Ts[:, :n].cpu().numpy().T),
             "U_": lambda: np.ascontiguousarray(res.U[:, :n].cpu().numpy().T),
             "V_": lambda: np.ascontiguousarray(res.V[:, :q].cpu().numpy().T),
             "T_": lambda: [np.ascontiguousarray(res.Tb[b, :, :n].cpu().numpy().T) for b in range(B)],
-            "W_": lambda: split_T(self._gather_features(res.W, shard)),
-            "W_non_normal_": lambda: split_T(self._gather_features(res.Wt, shard)),
-            "P_": lambda: split_T(self._gather_features(res.P, shard)),
-            "R_": lambda: np.ascontiguousarray(self._gather_features(R, shard).T),
-            "beta_": lambda: np.ascontiguousarray(self._gather_features(beta, shard).T),
+            "W_": lambda: self._features_T(res.W, shard, True),
+            "W_non_normal_": lambda: self._features_T(res.Wt, shard, True),
+            "P_": lambda: self._features_T(res.P, shard, True),
+            "R_": lambda: self._features_T(R, shard, False),
+            "beta_": lambda: self._features_T(beta, shard, False),
         }
         self.__dict__["_lazy"] = lazy
 
