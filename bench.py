@@ -294,7 +294,7 @@ def run_ours(args):
         nan_ms, nan_model = one_fit(nan_frac=0.10)
         nt = list(nan_model.n_iter_)
         variants["nan_10pct"] = {"fit_s": nan_ms / 1e3, "value": fit_bytes(n, p, K, nt) / (nan_ms / 1e3) / 1e9, "unit": "GB/s",
-                                 "trips_per_component": nt, "kernels": "two-pass masked kernels (DESIGN.md 3)"}
+                                 "trips_per_component": nt, "kernels": "one-pass kernels with NaN read as zero + masked denominators from the NaN bit matrix (DESIGN.md 3a)"}
         del nan_model
     trips = list(model.n_iter_)
     ms_step = sum(times) / len(times)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 2
+#define MBPLS_ABI_VERSION 3
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -149,21 +149,38 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
  * resident on the SM: ONE read of X per trip.  "Workers" (groups of threads inside a persistent CTA) own one
  * split each -- a contiguous local feature range inside one block, split_block[s] = its block -- and keep the
  * n-vector of partial block scores in registers; outputs have the layout of mbpls_nipals_xw_f64 /
- * mbpls_nipals_xtu_f64 (Tnum[s][.], Tden[s][.], w[j]) and norm_part[s*B + split_block[s]] = sum of w~_j^2
+ * mbpls_nipals_xtu_f64 (Tnum[s][.], w[j]) and norm_part[s*B + split_block[s]] = sum of w~_j^2
  * over the split (all other entries of norm_part must be zero), so mbpls_nipals_reduce_partials_f64 and the
  * epilogue apply unchanged.  mbpls_fused_workers_per_cta(ld) returns the workers per CTA (0: the feature is
  * too long for the register-resident accumulators, use the two-pass kernels); size the split table to
  * workers_per_cta * number of SMs. */
 int mbpls_fused_workers_per_cta(long ld);
-int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const int* split_f0,
-                                const int* split_f1, const int* split_block, int nsplit, int B, double* w, double* norm_part,
-                                double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream);
-/* Dense data: loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL --
- * the complete first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0,
- * its squared norms and its partial block scores Tnum.  1 read + 1 write of X. */
-int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* u0, const double* u0u0,
-                            const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
-                            double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream);
+/* rden == NULL: dense data.  NaN mode: rden[j] = reciprocal masked denominator of feature j for this u
+ * (mbpls_masked_colden_f64); NaN entries count as zero; the masked score denominators come from
+ * mbpls_masked_rowden_f64 afterwards. */
+int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
+                                const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* w,
+                                double* norm_part, double* Tnum, long ldt, const int* done, void* stream);
+/* Loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL -- the complete
+ * first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0, its squared norms
+ * and its partial block scores Tnum.  1 read + 1 write of X.  NaN mode (rden_ts != NULL): masked loadings / weights through
+ * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0); NaN entries stay NaN. */
+int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
+                            const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
+                            const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
+                            double* Tnum, long ldt, void* stream);
+
+/* ---- NaN bit matrix and the masked denominators derived from it (csrc/nanmask.cu; mbpls.py:848-852, :867-872, :923-925)
+ * bits[j*ldw + (i >> 5)] bit (i & 31) = 1 iff x_ij is NaN; ldw = mbpls_nan_bitmask_ldw(n) 32-bit words per feature. */
+int mbpls_nan_bitmask_ldw(int n);
+int mbpls_nan_bitmask_f64(const double* Xt, long ld, int n, int p, unsigned* bits, long ldw, void* stream);
+/* rden[j] = 1 / sum_{i observed in feature j} v_i^2 for features with NaN (col_nan[j] > 0, from mbpls_nan_census_f64);
+ * fully observed features: 1 / *vv (divide_dense) or 1 (dense loadings are not divided, :920).  *vv = v'v. */
+int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* vv,
+                            int divide_dense, double* rden, const int* done, void* stream);
+/* Tden[s*ldt + i] = sum over the features j of split s observed in sample i of w_j^2 (:867-872) */
+int mbpls_masked_rowden_f64(const unsigned* bits, long ldw, int n, const double* w, const int* split_f0, const int* split_f1,
+                            int nsplit, double* Tden, long ldt, const int* done, void* stream);
 
 /* ---- finalisation and new-data paths (mbpls.py:986-989, :1110-1117, :1379-1386) -------------------- */
 /* Cpart[chunk][i*K2 + j] = sum_{f in chunk} A[i][f] * Bm[j][f]; A is K1 x p (lda), Bm is K2 x p (ldb).

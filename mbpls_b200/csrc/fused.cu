@@ -26,9 +26,11 @@
 // scores go to Tnum[split][.] exactly like xw_kernel's, so reduce_partials / the epilogue are unchanged and
 // results are bitwise reproducible (static split -> worker map, fixed summation order).
 //
-// NaN mode (:848-852, :867-872): the masked numerator/denominator of w~_j come from the same pass; the
-// masked score denominator sum_{j observed in row i} w~_j^2 is kept as  (sum_j w~_j^2) - miss_i  with
-// miss_i accumulated in shared memory only where x_ij is NaN.
+// NaN mode (:848-852, :867-872, :923-925): NaN entries are read as zero, so the masked numerators come out of the same
+// arithmetic; every masked DENOMINATOR is derived from the NaN bit matrix (csrc/nanmask.cu) by two tiny kernels -- per
+// feature before the pass (the reciprocal `rden[j]` the kernel multiplies with), per sample after it (Tden) -- instead
+// of being accumulated here.  (The first NaN version kept per-sample "missing weight" sums in a second shared-memory
+// n-vector per worker; that left a 64 KB ring and ran at 2.6-3.6 TB/s.)
 //
 // The second kernel closes a component the same way: loadings p_j = x_j . ts, rank-1 deflation
 // x_j -= ts p_j (:917-930, :968-969) written back from registers, the next component's first weights
@@ -53,6 +55,8 @@ struct FusedArgs {
   const double* u;   // trip: current Y scores; deflate: u0 (may be null -> no next-component outputs)
   const double* uu;  // device scalar u'u (resp. u0'u0)
   const double* ts;  // deflate only
+  const double* rden;   // NaN mode: per-feature reciprocal masked denominator for u (trip) / ts (deflate)
+  const double* rden2;  // NaN mode, deflate: same for u0
   const int* split_f0;
   const int* split_f1;
   const int* split_block;
@@ -61,7 +65,6 @@ struct FusedArgs {
   double* w;          // w~ out (trip) / next w~ out (deflate)
   double* norm_part;  // [nsplit * B], zero except (split, block of split)
   double* Tnum;       // [nsplit][ldt]
-  double* Tden;       // NaN mode
   long ldt;
   double* P_k;  // deflate: loadings out
   double* pss;  // deflate: p_j^2 out
@@ -209,6 +212,12 @@ __device__ __forceinline__ void refill_if_last(unsigned old, const double* __res
 // accumulators (acc += w~_{j-1} x) unit by unit and reloads each x register with feature j right behind it,
 // so the score update hides under the shared-memory-bound load phase.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 nan_to_zero(double2 v) {
+  if (isnan(v.x)) v.x = 0.0;
+  if (isnan(v.y)) v.y = 0.0;
+  return v;
+}
+
 template <bool NANMODE, class C>
 __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   if (a.done && *a.done) return;
@@ -216,12 +225,9 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   const long ld = a.ld;
   const int units = static_cast<int>(ld >> 1);
   const int ncf = (units + C::UC - 1) / C::UC;
-  const Smem<C> sm(smem_raw, ld, NANMODE ? 1 + C::G : 1);  // u | one miss vector per worker (NaN mode)
+  const Smem<C> sm(smem_raw, ld, 1);  // u
   init_sync<C>(sm);
   for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.u[i] : 0.0;
-  if (NANMODE) {
-    for (int i = threadIdx.x; i < C::G * ld; i += blockDim.x) sm.vec1[i] = 0.0;
-  }
   __syncthreads();
 
   const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
@@ -230,26 +236,22 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   if (wk >= a.nsplit) return;
   const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
   if (tg == 0) prime_ring<C>(a.Xt, ld, units, ncf, g, f0, f1, sm);
-  const double uu = *a.uu;
-  const double inv_uu = 1.0 / uu;
+  const double inv_uu = 1.0 / *a.uu;
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
-  double2* __restrict__ miss2 = reinterpret_cast<double2*>(sm.vec1 + (NANMODE ? static_cast<size_t>(g) * ld : 0));
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
 
   double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
   for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
-  double normsq = 0.0, wj = 0.0, w2 = 0.0;
-  uint32_t mx = 0, my = 0;  // NaN masks of the units held in x (x / y halves)
+  double normsq = 0.0, wj = 0.0;
   int s = 0;
   uint32_t ph = 0;
   int flip = 0;
 
   for (int j = f0; j <= f1; ++j) {
     const bool load = j < f1;  // the last iteration only applies the last weight
-    double v[3] = {0.0, 0.0, 0.0};  // numerator, masked u'u, NaN seen
-    double numb = 0.0, numc = 0.0, numd = 0.0;
-    uint32_t nmx = 0, nmy = 0;
+    const double rd = (NANMODE && load) ? a.rden[j] : inv_uu;  // 1 / (masked) u'u of this feature
+    double numa = 0.0, numb = 0.0, numc = 0.0, numd = 0.0;
     int s_use = s;  // s: next stage to load from; s_use: stage of the chunk being consumed
     constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;  // few units per chunk: issue chunk c+1's loads before consuming chunk c
     double2 ub[2][PIPE ? C::EPTC : 1];  // u values travelling with the chunk in flight
@@ -268,32 +270,20 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
         const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
         acc[k].x = fma(wj, x[k].x, acc[k].x);
         acc[k].y = fma(wj, x[k].y, acc[k].y);
-        if (NANMODE) {
-          if (((mx | my) >> k) & 1u) {
-            double2 m = miss2[gi];
-            if ((mx >> k) & 1u) m.x += w2;
-            if ((my >> k) & 1u) m.y += w2;
-            miss2[gi] = m;
-          }
-        }
         double2 xv = make_double2(0.0, 0.0), uv = make_double2(0.0, 0.0);
         if (have && (whole || gi < units)) {
           xv = xs[l];
           uv = u2[gi];
+          if (NANMODE) xv = nan_to_zero(xv);  // masked sums: a missing entry contributes nothing (:848-852, :867-872)
         }
         if (PIPE) {
           ub[c & 1][e] = uv;
         } else if (have) {  // consume on the spot
-          if (NANMODE) {
-            const bool bx = isnan(xv.x), by = isnan(xv.y);
-            if (bx) { xv.x = 0.0; nmx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
-            if (by) { xv.y = 0.0; nmy |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
-          }
           if (e & 1) {
             numc = fma(xv.x, uv.x, numc);
             numd = fma(xv.y, uv.y, numd);
           } else {
-            v[0] = fma(xv.x, uv.x, v[0]);
+            numa = fma(xv.x, uv.x, numa);
             numb = fma(xv.y, uv.y, numb);
           }
         }
@@ -306,19 +296,12 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
 #pragma unroll
       for (int e = 0; e < (PIPE ? C::EPTC : 0); ++e) {
         const int k = c * C::EPTC + e;
-        double2 xv = x[k];
-        const double2 uv = ub[c & 1][e];
-        if (NANMODE) {
-          const bool bx = isnan(xv.x), by = isnan(xv.y);
-          if (bx) { xv.x = 0.0; nmx |= 1u << k; } else v[1] = fma(uv.x, uv.x, v[1]);
-          if (by) { xv.y = 0.0; nmy |= 1u << k; } else v[1] = fma(uv.y, uv.y, v[1]);
-          x[k] = xv;
-        }
+        const double2 xv = x[k], uv = ub[c & 1][e];
         if (e & 1) {
           numc = fma(xv.x, uv.x, numc);
           numd = fma(xv.y, uv.y, numd);
         } else {
-          v[0] = fma(xv.x, uv.x, v[0]);
+          numa = fma(xv.x, uv.x, numa);
           numb = fma(xv.y, uv.y, numb);
         }
       }
@@ -342,46 +325,30 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
       }
     }
     if (!load) break;
-    mx = nmx;
-    my = nmy;
-    v[0] = (v[0] + numb) + (numc + numd);
-    if (NANMODE) {
-      v[2] = (mx | my) ? 1.0 : 0.0;
-      worker_sum<3, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
-      wj = v[2] > 0.0 ? v[0] / v[1] : v[0] / uu;
-    } else {
-      double one[1] = {v[0]};
-      worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
-      wj = one[0] * inv_uu;
-    }
+    double one[1] = {(numa + numb) + (numc + numd)};
+    worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
+    wj = one[0] * rd;
     if (tg == 0) a.w[j] = wj;
-    w2 = wj * wj;
-    normsq += w2;
+    normsq = fma(wj, wj, normsq);
   }
 
   // partial block scores of this split (the layout xw_kernel writes)
   double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
-  double2* td = NANMODE ? reinterpret_cast<double2*>(a.Tden + static_cast<size_t>(wk) * a.ldt) : nullptr;
 #pragma unroll
   for (int k = 0; k < C::EPT; ++k) {
     const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
-    if (gi < units) {
-      tn[gi] = acc[k];
-      if (NANMODE) {
-        const double2 m = miss2[gi];
-        td[gi] = make_double2(normsq - m.x, normsq - m.y);
-      }
-    }
+    if (gi < units) tn[gi] = acc[k];
   }
   if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
 }
 
 // ------------------------------------------------------------------------------------------
-// loadings + deflation + the whole first trip of the next component (dense data); same pipeline: the score
-// update of feature j-1 rides on the load phase of feature j.
+// loadings + deflation + the whole first trip of the next component; same pipeline: the score update of
+// feature j-1 rides on the load phase of feature j.  NaN mode: NaN entries take part as zeros and are written
+// back as NaN (:969 keeps them); loadings and next weights use the masked reciprocal denominators rden / rden2.
 // ------------------------------------------------------------------------------------------
-template <class C>
+template <bool NANMODE, class C>
 __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const long ld = a.ld;
@@ -406,6 +373,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec1);
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
@@ -417,7 +385,10 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 
   for (int j = f0; j <= f1; ++j) {
     const bool load = j < f1;
+    const double rdp = (NANMODE && load) ? a.rden[j] : 1.0;                      // loadings: 1 / masked ts'ts (dense: not divided, :920)
+    const double rdw = (NANMODE && load && next) ? a.rden2[j] : inv_uu;          // next weights: 1 / masked u0'u0
     double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
+    uint32_t mx = 0, my = 0;  // NaN mode: which of this thread's entries are NaN (they must be stored back as NaN)
     int s_use = s;
     constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;
     double2 tb[2][PIPE ? C::EPTC : 1];  // ts values travelling with the chunk in flight
@@ -439,6 +410,10 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
         if (have && (whole || gi < units)) {
           xv = xs[l];
           tv = ts2[gi];
+          if (NANMODE) {
+            if (isnan(xv.x)) { xv.x = 0.0; mx |= 1u << k; }
+            if (isnan(xv.y)) { xv.y = 0.0; my |= 1u << k; }
+          }
         }
         if (PIPE) {
           tb[c & 1][e] = tv;
@@ -466,8 +441,6 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
           pb = fma(x[k].y, tv.y, pb);
         }
       }
-      // refill at once: every cycle a free stage sits idle is ring depth lost (deferring the check by one chunk to
-      // hide the atomic's latency cost 10 % on the shallow rings)
       refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xw, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
       if (++s_use == C::S) s_use = 0;
     };
@@ -489,7 +462,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
     double one[1] = {(pa + pb) + (pc + pd)};
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
-    const double pj = one[0];
+    const double pj = one[0] * rdp;
     double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j) * ld);
     double wa = 0.0, wb = 0.0, wc = 0.0, wd = 0.0;
 #pragma unroll
@@ -500,7 +473,14 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
         double2 xn;
         xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
         xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
-        st_stream(xg + gi, xn);
+        if (NANMODE) {
+          double2 out = xn;
+          if ((mx >> k) & 1u) { out.x = qnan; xn.x = 0.0; }
+          if ((my >> k) & 1u) { out.y = qnan; xn.y = 0.0; }
+          st_stream(xg + gi, out);
+        } else {
+          st_stream(xg + gi, xn);
+        }
         x[k] = xn;
         if (next) {
           const double2 uv = u2[gi];
@@ -518,7 +498,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
       double two[1] = {(wa + wb) + (wc + wd)};
       worker_sum<1, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
       flip ^= 1;
-      wj = two[0] * inv_uu;
+      wj = two[0] * rdw;
       normsq = fma(wj, wj, normsq);
     }
     if (tg == 0) {
@@ -541,20 +521,14 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 // every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as the ring allows:
 // the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
 using CfgA = Cfg<512, 5, 2, 3>;   // ld <= 10240: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
-using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with a second resident n-vector (NaN trip, deflate): only 64 KB of ring left
-using CfgA4x = Cfg<512, 4, 3, 2>; // experiment (MBPLS_FUSED_ALT, deflate): 32 KB chunks x 2, 12 units per thread
-using CfgA8 = Cfg<512, 2, 5, 8>;  // experiment (MBPLS_FUSED_ALT): 16 KB chunks, 8 in flight
+using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with two resident n-vectors (deflate: ts and u0): only 64 KB of ring left
 using CfgB = Cfg<256, 5, 2, 3>;   // ld <= 5120: two workers, 20 KB chunks
 using CfgC = Cfg<128, 5, 2, 4>;   // ld <= 2560: four workers, 10 KB chunks
 using CfgD = Cfg<64, 10, 1, 2>;   // ld <= 1280: eight workers, one chunk per feature
-// NaN trip: one extra n-vector PER WORKER (80 KB in total at every size), so shallower / finer rings
-using CfgBn = Cfg<256, 5, 2, 2>;
-using CfgCn = Cfg<128, 5, 2, 3>;
-using CfgDn = Cfg<64, 5, 2, 3>;
 
 template <bool NANMODE, class C>
 int launch_trip(const FusedArgs& a, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes<C>(a.ld, NANMODE ? 1 + C::G : 1);
+  const size_t smem = fused_smem_bytes<C>(a.ld, 1);
   if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
   cudaFuncSetAttribute(fused_trip_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int grid = (a.nsplit + C::G - 1) / C::G;
@@ -562,13 +536,13 @@ int launch_trip(const FusedArgs& a, cudaStream_t st) {
   return MBPLS_OK;
 }
 
-template <class C>
+template <bool NANMODE, class C>
 int launch_deflate(const FusedArgs& a, cudaStream_t st) {
   const size_t smem = fused_smem_bytes<C>(a.ld, 2);
   if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
-  cudaFuncSetAttribute(fused_deflate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaFuncSetAttribute(fused_deflate_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int grid = (a.nsplit + C::G - 1) / C::G;
-  fused_deflate_kernel<C><<<grid, 512, smem, st>>>(a);
+  fused_deflate_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
   return MBPLS_OK;
 }
 
@@ -597,47 +571,43 @@ int mbpls_fused_workers_per_cta(long ld) {
   }
 }
 
-int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const int* split_f0,
-                                const int* split_f1, const int* split_block, int nsplit, int B, double* w, double* norm_part,
-                                double* Tnum, double* Tden, long ldt, int nanmode, const int* done, void* stream) {
-  if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || (nanmode && !Tden) || ld < n ||
-      ldt < ld || B < 1)
+int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
+                                const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* w,
+                                double* norm_part, double* Tnum, long ldt, const int* done, void* stream) {
+  if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || ld < n || ldt < ld || B < 1)
     return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
-  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, split_f0, split_f1, split_block, nsplit, B, w, norm_part, Tnum, Tden, ldt,
+  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, split_f0, split_f1, split_block, nsplit, B, w, norm_part, Tnum, ldt,
               nullptr, nullptr, done};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
-    case 1:
-      if (nanmode) rc = launch_trip<true, CfgA4>(a, st);
-      else if (getenv("MBPLS_FUSED_ALT")) rc = launch_trip<false, CfgA8>(a, st);
-      else rc = launch_trip<false, CfgA>(a, st);
-      break;
-    case 2: rc = nanmode ? launch_trip<true, CfgBn>(a, st) : launch_trip<false, CfgB>(a, st); break;
-    case 3: rc = nanmode ? launch_trip<true, CfgCn>(a, st) : launch_trip<false, CfgC>(a, st); break;
-    case 4: rc = nanmode ? launch_trip<true, CfgDn>(a, st) : launch_trip<false, CfgD>(a, st); break;
+    case 1: rc = rden ? launch_trip<true, CfgA>(a, st) : launch_trip<false, CfgA>(a, st); break;
+    case 2: rc = rden ? launch_trip<true, CfgB>(a, st) : launch_trip<false, CfgB>(a, st); break;
+    case 3: rc = rden ? launch_trip<true, CfgC>(a, st) : launch_trip<false, CfgC>(a, st); break;
+    case 4: rc = rden ? launch_trip<true, CfgD>(a, st) : launch_trip<false, CfgD>(a, st); break;
     default: break;
   }
   if (rc != MBPLS_OK) return rc;
   MBPLS_RETURN_LAST();
 }
 
-int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* u0, const double* u0u0,
-                            const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
-                            double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream) {
+int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
+                            const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
+                            const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
+                            double* Tnum, long ldt, void* stream) {
   if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
-  if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld)) return MBPLS_ERR_ARG;
+  if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && !rden_u0))) return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
-  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, split_f0, split_f1, split_block, nsplit, B, w_next, norm_part, Tnum, nullptr, ldt,
-              P_k, pss, nullptr};
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, split_f0, split_f1, split_block, nsplit, B, w_next, norm_part, Tnum,
+              ldt, P_k, pss, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
-    case 1: rc = getenv("MBPLS_FUSED_ALT") ? launch_deflate<CfgA4x>(a, st) : launch_deflate<CfgA4>(a, st); break;
-    case 2: rc = launch_deflate<CfgB>(a, st); break;
-    case 3: rc = launch_deflate<CfgC>(a, st); break;
-    case 4: rc = launch_deflate<CfgD>(a, st); break;
+    case 1: rc = rden_ts ? launch_deflate<true, CfgA4>(a, st) : launch_deflate<false, CfgA4>(a, st); break;
+    case 2: rc = rden_ts ? launch_deflate<true, CfgB>(a, st) : launch_deflate<false, CfgB>(a, st); break;
+    case 3: rc = rden_ts ? launch_deflate<true, CfgC>(a, st) : launch_deflate<false, CfgC>(a, st); break;
+    case 4: rc = rden_ts ? launch_deflate<true, CfgD>(a, st) : launch_deflate<false, CfgD>(a, st); break;
     default: break;
   }
   if (rc != MBPLS_OK) return rc;

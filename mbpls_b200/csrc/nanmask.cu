@@ -1,0 +1,169 @@
+// NaN pattern as a bit matrix, and the masked denominators of the NaN-mode NIPALS (mbpls/mbpls.py:848-852, :867-872,
+// :923-925) computed from it.
+//
+// The NaN pattern of X never changes during a fit (deflation keeps NaN as NaN, :969), so it is extracted once:
+// bits[j][i >> 5] bit (i & 31) = 1 iff x_ij is NaN (1/64 of the size of X).  With it, every masked sum of the
+// reference becomes "total minus what sits under the holes":
+//   * per feature:  sum_{i observed in column j} v_i^2 = v'v - sum_{i: x_ij NaN} v_i^2      (v = u, ts, u0)
+//   * per sample:   sum_{j in block, observed in row i} w_j^2                                 (score denominators)
+// Both are tiny passes over the bit matrix instead of full passes over X, which is what lets the NaN-mode trip run
+// through the same one-read kernel as dense data (csrc/fused.cu) with NaN entries read as zero.
+#include "launch.cuh"
+#include "../../include/mbpls_b200.h"
+
+using namespace mbpls;
+
+namespace {
+
+// one warp per feature; lanes read consecutive samples, so a ballot is the mask word
+__global__ void __launch_bounds__(256) nan_bitmask_kernel(const double* __restrict__ Xt, long ld, int n, int p,
+                                                          unsigned* __restrict__ bits, long ldw) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nwords = (n + 31) >> 5;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
+    const double* x = Xt + static_cast<size_t>(j) * ld;
+    unsigned* row = bits + static_cast<size_t>(j) * ldw;
+    for (int w = 0; w < nwords; w += 4) {  // four independent loads in flight per lane
+      double v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = (w + k) * 32 + lane;
+        v[k] = i < n ? x[i] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned m = __ballot_sync(MBPLS_FULL_MASK, isnan(v[k]));
+        if (lane == 0 && w + k < ldw) row[w + k] = m;
+      }
+    }
+    for (int w = ((nwords + 3) & ~3) + lane; w < ldw; w += 32) row[w] = 0u;
+  }
+}
+
+// rden[j] = 1 / (sum over the observed samples of feature j of v_i^2) for features with NaN; for fully observed
+// features 1 / v'v (divide_dense) or 1 (the reference does not divide dense loadings, :920).
+__global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __restrict__ bits, long ldw, int n, int p,
+                                                            const int* __restrict__ col_nan, const double* __restrict__ v,
+                                                            const double* __restrict__ vv_ptr, int divide_dense,
+                                                            double* __restrict__ rden, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nwords = (n + 31) >> 5;
+  const double vv = *vv_ptr;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
+    if (col_nan[j] == 0) {
+      if (lane == 0) rden[j] = divide_dense ? 1.0 / vv : 1.0;
+      continue;
+    }
+    const unsigned* row = bits + static_cast<size_t>(j) * ldw;
+    double miss = 0.0;
+    for (int w = lane; w < nwords; w += 32) {
+      unsigned m = row[w];
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const double t = v[w * 32 + b];
+        miss = fma(t, t, miss);
+      }
+    }
+    miss = warp_sum(miss);
+    if (lane == 0) rden[j] = 1.0 / (vv - miss);
+  }
+}
+
+// Tden[s][i] = sum over the features j of split s that are observed in sample i of w_j^2.
+// A lane owns one 32-bit mask word = 32 consecutive samples and keeps their 32 sums in registers, so one 4-byte load feeds
+// 32 predicated additions; a warp covers 1024 consecutive samples (its lanes read 128 contiguous bytes of a feature's bit
+// row), the 8 warps of a CTA take every 8th feature of the split and their partials are added in a fixed order.
+__global__ void __launch_bounds__(256) masked_rowden_kernel(const unsigned* __restrict__ bits, long ldw, int n,
+                                                            const double* __restrict__ w, const int* __restrict__ split_f0,
+                                                            const int* __restrict__ split_f1, double* __restrict__ Tden, long ldt,
+                                                            const int* __restrict__ done) {
+  if (done && *done) return;
+  __shared__ double part[8][16][33];  // [warp][bit (half)][lane], padded against bank conflicts
+  const int s = blockIdx.y;
+  const int f0 = split_f0[s], f1 = split_f1[s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wi = blockIdx.x * 32 + lane;
+  const bool valid = wi < ldw;
+  const unsigned* col = bits + (valid ? wi : 0);
+  double acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0.0;
+  int j = f0 + warp;
+  for (; j + 8 < f1; j += 16) {  // two features per step: both loads in flight before the additions
+    const unsigned m0 = valid ? __ldg(col + static_cast<size_t>(j) * ldw) : 0u;
+    const unsigned m1 = valid ? __ldg(col + static_cast<size_t>(j + 8) * ldw) : 0u;
+    const double a0 = __ldg(w + j), a1 = __ldg(w + j + 8);
+    const double q0 = a0 * a0, q1 = a1 * a1;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      acc[b] += ((m0 >> b) & 1u) ? 0.0 : q0;
+      acc[b] += ((m1 >> b) & 1u) ? 0.0 : q1;
+    }
+  }
+  for (; j < f1; j += 8) {
+    const unsigned m0 = valid ? __ldg(col + static_cast<size_t>(j) * ldw) : 0u;
+    const double a0 = __ldg(w + j);
+    const double q0 = a0 * a0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] += ((m0 >> b) & 1u) ? 0.0 : q0;
+  }
+  double* out = Tden + static_cast<size_t>(s) * ldt;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 16; ++b) part[warp][b][lane] = acc[half * 16 + b];
+    __syncthreads();
+    // 16 bits x 32 lanes = 512 sums per half, 256 threads: two each, warps 0..7 added in order
+    for (int e = threadIdx.x; e < 512; e += 256) {
+      const int b = e & 15, l = e >> 4;
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += part[k][b][l];
+      const long i = (static_cast<long>(blockIdx.x) * 32 + l) * 32 + half * 16 + b;
+      if (i < n) out[i] = t;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+/* words per feature row of the NaN bit matrix for n samples (multiple of 4: rows are 16-byte aligned) */
+int mbpls_nan_bitmask_ldw(int n) { return (((n + 31) >> 5) + 3) & ~3; }
+
+int mbpls_nan_bitmask_f64(const double* Xt, long ld, int n, int p, unsigned* bits, long ldw, void* stream) {
+  if (!Xt || !bits || ld < n || ldw < ((n + 31) >> 5)) return MBPLS_ERR_ARG;
+  if (p == 0 || n == 0) return MBPLS_OK;
+  int grid = (p + 7) / 8;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  nan_bitmask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Xt, ld, n, p, bits, ldw);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* vv,
+                            int divide_dense, double* rden, const int* done, void* stream) {
+  if (!bits || !col_nan || !v || !vv || !rden) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  int grid = (p + 7) / 8;
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  masked_colden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, ldw, n, p, col_nan, v, vv, divide_dense, rden, done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_masked_rowden_f64(const unsigned* bits, long ldw, int n, const double* w, const int* split_f0, const int* split_f1,
+                            int nsplit, double* Tden, long ldt, const int* done, void* stream) {
+  if (!bits || !w || !split_f0 || !split_f1 || !Tden) return MBPLS_ERR_ARG;
+  if (nsplit == 0 || n == 0) return MBPLS_OK;
+  if (nsplit > 65535) return MBPLS_ERR_SIZE;
+  dim3 grid((((n + 31) >> 5) + 31) / 32, nsplit);  // 32 mask words (1024 samples) per CTA
+  masked_rowden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, ldw, n, w, split_f0, split_f1, Tden, ldt, done);
+  MBPLS_RETURN_LAST();
+}
+
+}  // extern "C"

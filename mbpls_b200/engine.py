@@ -366,7 +366,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
                deflate_last: bool = False, one_pass: Optional[bool] = None,
-               one_pass_deflate: Optional[bool] = None) -> NipalsResult:
+               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -390,15 +390,14 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
 
     # one-pass kernels (csrc/fused.cu): a trip reads X once; they need the score accumulators of a whole feature in
     # registers, i.e. ld <= 10240.  Their "workers" own one split each: size the split table to one persistent CTA per SM.
-    # Auto policy (measured, profiles/r1_notes.md): dense data -> one-pass whenever the feature fits; NaN-masked data ->
-    # two-pass kernels (the masked one-pass trip keeps a second n-vector per worker in shared memory, which leaves a
-    # 64 KB ring: 2.6-3.6 TB/s for one read against 2 x 6.8 TB/s), unless one_pass=True forces it.
-    want_op = one_pass is True or (one_pass is None and not nan)
+    # NaN-masked data runs through the same kernels with NaN read as zero; every masked denominator is derived from the
+    # NaN bit matrix (csrc/nanmask.cu), which needs the per-feature NaN counts of the census (col_nan).
+    want_op = one_pass is not False and (not nan or col_nan is not None)
     wpc = call("mbpls_fused_workers_per_cta", ld) if (want_op and p > 0) else 0
     use_op = wpc > 0
     if one_pass is True and not use_op and p > 0:
-        raise ValueError("one_pass=True needs a leading dimension of at most 10240 samples")
-    use_opd = use_op and not nan and one_pass_deflate is not False and deflate_mode == 0
+        raise ValueError("one_pass=True needs a leading dimension of at most 10240 samples (and, for NaN data, the census)")
+    use_opd = use_op and one_pass_deflate is not False and deflate_mode == 0
     if use_op:
         of0, of1, obso = make_splits(block_off, 1, sm_count(dev), ctas_per_sm=wpc, min_feats=16)
         nsplit_o = len(of0)
@@ -427,6 +426,17 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     ctrl_h = torch.empty(_cabi.CTRL_COUNT, dtype=torch.int32).pin_memory()
     u0u0 = buf(1)
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
+    bits = rden_u = rden_ts = rden_u0 = None
+    ldw = 0
+    if nan and use_op:
+        # NaN bit matrix (the pattern never changes: deflation keeps NaN, mbpls.py:969) and the masked denominators
+        # that do not change either: sum over the observed samples of u0^2 per feature
+        ldw = call("mbpls_nan_bitmask_ldw", n)
+        bits = torch.empty((p, ldw), dtype=torch.int32, device=dev)
+        call("mbpls_nan_bitmask_f64", ptr(Xt), ld, n, p, ptr(bits), ldw, st)
+        col_nan = col_nan.to(torch.int32).contiguous()
+        rden_u, rden_ts, rden_u0 = buf(p), buf(p), buf(p)
+        call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u0), ptr(u0u0), 1, ptr(rden_u0), None, st)
 
     res = NipalsResult(Wt=buf(K, p), W=buf(K, p), P=buf(K, p), Ts=buf(K, ld, zero=True), U=buf(K, ld, zero=True),
                        Tb=buf(B, K, ld, zero=True), V=buf(K, q), A=buf(K, B), pssb=buf(K, B, zero=True),
@@ -470,9 +480,15 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 first = launched == 0
                 if (first and w_ready == "scores") or (use_op and not (first and w_ready == "w")):
                     if not (first and w_ready == "scores"):
-                        timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(osf0),
-                                                   ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o), ptr(Tnum_o),
-                                                   ptr(Tden_o), ld, nan, done_p, st))
+                        if nan:  # 1 / sum over the observed samples of u^2, per feature (mbpls.py:848-852)
+                            timed("colden", lambda: call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u),
+                                                         ptr(scal), 1, ptr(rden_u), done_p, st))
+                        timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(rden_u),
+                                                   ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o),
+                                                   ptr(Tnum_o), ld, done_p, st))
+                        if nan:  # sum over the observed features of w~^2, per sample and split (:867-872)
+                            timed("rowden", lambda: call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1),
+                                                         nsplit_o, ptr(Tden_o), ld, done_p, st))
                     call("mbpls_nipals_reduce_partials_f64", ptr(Tnum_o), ptr(Tden_o), ld, n, B, ptr(osbso),
                          ptr(norm_part_o), nsplit_o, ptr(red_local), nan, done_p, st)
                 else:
@@ -516,10 +532,17 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if p > 0:
                 call("mbpls_block_sumsq_f64", ptr(res.P[k]), ptr(boff), B, ptr(res.pssb[k]), st)
         elif use_opd:
-            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(u0) if fuse else None,
-                                          ptr(u0u0) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
+            if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
+                call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(scal[_cabi.SCAL_TT:]), 0,
+                     ptr(rden_ts), None, st)
+            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
+                                          ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
+                                          ptr(rden_u0) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
                                           ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
                                           ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
+            if nan and fuse:
+                call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1), nsplit_o, ptr(Tden_o), ld,
+                     None, st)
             call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
             w_ready = "scores" if fuse else None
         else:

@@ -46,7 +46,7 @@ _RUNTIME_DEFAULTS = dict(
     profile=None,         # dict collecting CUDA-event pairs per kernel (bench.py roofline)
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
     one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 10240), False two-pass kernels
-    one_pass_deflate=None,  # dense data: loadings+deflation also runs the next component's whole first trip
+    one_pass_deflate=None,  # loadings+deflation also runs the next component's whole first trip (None auto, False off)
 )
 
 
@@ -113,7 +113,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
     def __getstate__(self):
         self._materialize_all()
         state = dict(self.__dict__)
-        for k in ("_rt", "_dev", "_lazy", "_dev_scalers", "_cv_weights", "_rows"):
+        for k in ("_rt", "_dev", "_lazy", "_dev_scalers", "_cv_weights", "_rows", "_col_nan"):
             state.pop(k, None)
         return state
 
@@ -415,6 +415,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         for b, pb in enumerate(shard.sizes):
             self.sparse_X_info_[b] = self._census_from_flags(rows[b], col_full[g0:g0 + pb])
             g0 += pb
+        self.__dict__["_col_nan"] = col_nan  # per local feature, for the masked denominators of the one-pass kernels
         return row_flag, (ycol_nan[:q] > 0).to(torch.uint8).contiguous()
 
     def _store_scalers(self, xs, ys, shard, q):
@@ -465,7 +466,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
-                           one_pass_deflate=rt["one_pass_deflate"])
+                           one_pass_deflate=rt["one_pass_deflate"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")

@@ -15,7 +15,7 @@ which = set(a for a in args if not a.replace(".", "").isdigit()) or {"dense", "n
 
 VARIANTS = (("two-pass", dict(one_pass=False)), ("one-pass trip", dict(one_pass=True, one_pass_deflate=False)),
             ("one-pass trip+deflate", dict(one_pass=True)))
-MULT = {"trip": 1.0, "xtu": 1.0, "xw": 1.0, "deflate": 2.0, "loadings": 1.0, "standardize": 2.0}
+MULT = {"colden": 1.0 / 64, "rowden": 1.0 / 64, "trip": 1.0, "xtu": 1.0, "xw": 1.0, "deflate": 2.0, "loadings": 1.0, "standardize": 2.0}
 
 
 def run(case, n, sizes, K, q, nan_frac, max_iter=300, variants=VARIANTS, reps=2):
@@ -25,8 +25,6 @@ def run(case, n, sizes, K, q, nan_frac, max_iter=300, variants=VARIANTS, reps=2)
     Y = synth.response(n, q, K, dev, 31, decay=0.85)
     off = np.concatenate(([0], np.cumsum(sizes)))
     for name, rt in variants:
-        if nan_frac > 0 and name.endswith("deflate"):
-            continue
         best = None
         for _ in range(reps):
             synth.fill_feature_major(Xbuf, n, 0, p, K, 32, noise=0.02, decay=0.85, nan_frac=nan_frac)
