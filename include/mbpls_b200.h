@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 3
+#define MBPLS_ABI_VERSION 4
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -164,9 +164,12 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
 /* Loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL -- the complete
  * first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0, its squared norms
  * and its partial block scores Tnum.  1 read + 1 write of X.  NaN mode (rden_ts != NULL): masked loadings / weights through
- * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0); NaN entries stay NaN. */
+ * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0) and the per-feature masked dot
+ * product tsu0_masked[j] = sum_{i observed in j} ts_i u0_i (mbpls_masked_colden_f64 mode 2); NaN entries stay NaN.
+ * The next weight is formed from the two dot products of the undeflated feature,
+ * x_j(deflated) . u0 = x_j . u0 - p_j (ts . u0), so the feature is loaded, reduced ONCE, and updated on the fly. */
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
-                            const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
+                            const double* u0u0, const double* rden_u0, const double* tsu0_masked, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream);
 
@@ -174,10 +177,14 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
  * bits[j*ldw + (i >> 5)] bit (i & 31) = 1 iff x_ij is NaN; ldw = mbpls_nan_bitmask_ldw(n) 32-bit words per feature. */
 int mbpls_nan_bitmask_ldw(int n);
 int mbpls_nan_bitmask_f64(const double* Xt, long ld, int n, int p, unsigned* bits, long ldw, void* stream);
-/* rden[j] = 1 / sum_{i observed in feature j} v_i^2 for features with NaN (col_nan[j] > 0, from mbpls_nan_census_f64);
- * fully observed features: 1 / *vv (divide_dense) or 1 (dense loadings are not divided, :920).  *vv = v'v. */
-int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* vv,
-                            int divide_dense, double* rden, const int* done, void* stream);
+/* Masked column sums from the bit matrix.  m_j = *vv - sum_{i: x_ij NaN} v_i v2_i  (v2 == NULL: v2 = v), *vv = v . v2 over all
+ * samples; fully observed features (col_nan[j] == 0, from mbpls_nan_census_f64) have m_j = *vv.
+ * mode 0: out[j] = 1 / m_j for features with NaN, 1 for fully observed ones (dense loadings are not divided, :920)
+ * mode 1: out[j] = 1 / m_j (weights, :847-852)          mode 2: out[j] = m_j */
+int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* v2,
+                            const double* vv, int mode, double* out, const int* done, void* stream);
+/* out[0] = a . b over n samples (single CTA, fixed order) */
+int mbpls_vec_dot_f64(const double* a, const double* b, int n, double* out, void* stream);
 /* Tden[s*ldt + i] = sum over the features j of split s observed in sample i of w_j^2 (:867-872) */
 int mbpls_masked_rowden_f64(const unsigned* bits, long ldw, int n, const double* w, const int* split_f0, const int* split_f1,
                             int nsplit, double* Tden, long ldt, const int* done, void* stream);

@@ -41,12 +41,13 @@ __global__ void __launch_bounds__(256) nan_bitmask_kernel(const double* __restri
   }
 }
 
-// rden[j] = 1 / (sum over the observed samples of feature j of v_i^2) for features with NaN; for fully observed
-// features 1 / v'v (divide_dense) or 1 (the reference does not divide dense loadings, :920).
+// m_j = v . v2 - sum_{i: x_ij NaN} v_i v2_i, the sum of v_i v2_i over the observed samples of feature j (fully observed
+// features: v . v2).  mode 0: 1/m_j for features with NaN, 1 otherwise (the reference does not divide dense loadings,
+// :920); mode 1: 1/m_j; mode 2: m_j.
 __global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __restrict__ bits, long ldw, int n, int p,
                                                             const int* __restrict__ col_nan, const double* __restrict__ v,
-                                                            const double* __restrict__ vv_ptr, int divide_dense,
-                                                            double* __restrict__ rden, const int* __restrict__ done) {
+                                                            const double* __restrict__ v2, const double* __restrict__ vv_ptr, int mode,
+                                                            double* __restrict__ out, const int* __restrict__ done) {
   if (done && *done) return;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __re
   const double vv = *vv_ptr;
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < p; j += warps) {
     if (col_nan[j] == 0) {
-      if (lane == 0) rden[j] = divide_dense ? 1.0 / vv : 1.0;
+      if (lane == 0) out[j] = mode == 0 ? 1.0 : (mode == 1 ? 1.0 / vv : vv);
       continue;
     }
     const unsigned* row = bits + static_cast<size_t>(j) * ldw;
@@ -64,13 +65,21 @@ __global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __re
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const double t = v[w * 32 + b];
-        miss = fma(t, t, miss);
+        miss = fma(v[w * 32 + b], v2[w * 32 + b], miss);
       }
     }
     miss = warp_sum(miss);
-    if (lane == 0) rden[j] = 1.0 / (vv - miss);
+    if (lane == 0) out[j] = mode == 2 ? vv - miss : 1.0 / (vv - miss);
   }
+}
+
+__global__ void __launch_bounds__(1024) vec_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int n,
+                                                       double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(a[i], b[i], acc);
+  acc = block_sum1(acc, scratch);
+  if (threadIdx.x == 0) out[0] = acc;
 }
 
 // Tden[s][i] = sum over the features j of split s that are observed in sample i of w_j^2.
@@ -146,13 +155,20 @@ int mbpls_nan_bitmask_f64(const double* Xt, long ld, int n, int p, unsigned* bit
   MBPLS_RETURN_LAST();
 }
 
-int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* vv,
-                            int divide_dense, double* rden, const int* done, void* stream) {
-  if (!bits || !col_nan || !v || !vv || !rden) return MBPLS_ERR_ARG;
+int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const int* col_nan, const double* v, const double* v2,
+                            const double* vv, int mode, double* out, const int* done, void* stream) {
+  if (!bits || !col_nan || !v || !vv || !out || mode < 0 || mode > 2) return MBPLS_ERR_ARG;
   if (p == 0) return MBPLS_OK;
   int grid = (p + 7) / 8;
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  masked_colden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, ldw, n, p, col_nan, v, vv, divide_dense, rden, done);
+  masked_colden_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, ldw, n, p, col_nan, v, v2 ? v2 : v, vv, mode, out,
+                                                                           done);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_vec_dot_f64(const double* a, const double* b, int n, double* out, void* stream) {
+  if (!a || !b || !out || n < 0) return MBPLS_ERR_ARG;
+  vec_dot_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out);
   MBPLS_RETURN_LAST();
 }
 

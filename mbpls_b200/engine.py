@@ -9,6 +9,7 @@ to 16), results component-major ``K x p`` / ``K x ld``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -426,7 +427,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     ctrl_h = torch.empty(_cabi.CTRL_COUNT, dtype=torch.int32).pin_memory()
     u0u0 = buf(1)
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
-    bits = rden_u = rden_ts = rden_u0 = None
+    bits = rden_u = rden_ts = rden_u0 = tsu0_m = tsu0 = None
+    deflate_v2 = bool(os.environ.get("MBPLS_DEFLATE_V2"))  # experiment switch, see csrc/fused.cu launch_deflate
     ldw = 0
     if nan and use_op:
         # NaN bit matrix (the pattern never changes: deflation keeps NaN, mbpls.py:969) and the masked denominators
@@ -435,8 +437,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         bits = torch.empty((p, ldw), dtype=torch.int32, device=dev)
         call("mbpls_nan_bitmask_f64", ptr(Xt), ld, n, p, ptr(bits), ldw, st)
         col_nan = col_nan.to(torch.int32).contiguous()
-        rden_u, rden_ts, rden_u0 = buf(p), buf(p), buf(p)
-        call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u0), ptr(u0u0), 1, ptr(rden_u0), None, st)
+        rden_u, rden_ts, rden_u0, tsu0_m, tsu0 = buf(p), buf(p), buf(p), buf(p), buf(1)
+        call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u0), None, ptr(u0u0), 1, ptr(rden_u0), None, st)
 
     res = NipalsResult(Wt=buf(K, p), W=buf(K, p), P=buf(K, p), Ts=buf(K, ld, zero=True), U=buf(K, ld, zero=True),
                        Tb=buf(B, K, ld, zero=True), V=buf(K, q), A=buf(K, B), pssb=buf(K, B, zero=True),
@@ -481,7 +483,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 if (first and w_ready == "scores") or (use_op and not (first and w_ready == "w")):
                     if not (first and w_ready == "scores"):
                         if nan:  # 1 / sum over the observed samples of u^2, per feature (mbpls.py:848-852)
-                            timed("colden", lambda: call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u),
+                            timed("colden", lambda: call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u), None,
                                                          ptr(scal), 1, ptr(rden_u), done_p, st))
                         timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(rden_u),
                                                    ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o),
@@ -533,11 +535,16 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 call("mbpls_block_sumsq_f64", ptr(res.P[k]), ptr(boff), B, ptr(res.pssb[k]), st)
         elif use_opd:
             if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
-                call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(scal[_cabi.SCAL_TT:]), 0,
+                call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
                      ptr(rden_ts), None, st)
+                if fuse and deflate_v2:  # sum over the observed samples of ts u0 per feature (fused_deflate2_kernel, opt-in)
+                    call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
+                    call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(u0), ptr(tsu0), 2,
+                         ptr(tsu0_m), None, st)
             timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
                                           ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
-                                          ptr(rden_u0) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
+                                          ptr(rden_u0) if fuse else None, ptr(tsu0_m) if (fuse and deflate_v2) else None, ptr(osf0),
+                                          ptr(osf1), ptr(osblk), nsplit_o, B,
                                           ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
                                           ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
             if nan and fuse:
