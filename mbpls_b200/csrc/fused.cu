@@ -57,7 +57,9 @@ struct FusedArgs {
   const double* ts;  // deflate only
   const double* rden;   // NaN mode: per-feature reciprocal masked denominator for u (trip) / ts (deflate)
   const double* rden2;  // NaN mode, deflate: same for u0
-  const double* cmask;  // NaN mode, deflate v2: per-feature masked ts . u0
+  const double* cmask;  // NaN mode, deflate v2/v3: per-feature masked ts . u0
+  const double* cscal;  // deflate v3: device scalar ts . u0
+  double* gdef;         // deflate v3: running x_j(deflated) . u0 per feature (read, updated); trip: raw dot products out
   const int* split_f0;
   const int* split_f1;
   const int* split_block;
@@ -330,7 +332,10 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
     wj = one[0] * rd;
-    if (tg == 0) a.w[j] = wj;
+    if (tg == 0) {
+      a.w[j] = wj;
+      if (a.gdef) a.gdef[j] = one[0];  // x_j . u (numerator only): seeds the running x_j . u0 of the recurrence deflation
+    }
     normsq = fma(wj, wj, normsq);
   }
 
@@ -655,6 +660,139 @@ __global__ void __launch_bounds__(512, 1) fused_deflate2_kernel(const FusedArgs 
   if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
 }
 
+// ------------------------------------------------------------------------------------------
+// Deflation, third version (the default): the second version without the resident u0.
+//
+// The dot product a_j = x_j . u0 of the second version obeys a recurrence over the components: deflation turns it into
+// a_j - p_j (ts . u0) (masked data: the sum of ts_i u0_i over the observed samples of the feature).  Keeping that scalar
+// per feature in global memory (`gdef`, seeded with the raw dot products of a first trip, whose u IS u0, and re-seeded the
+// same way every few components so that rounding cannot pile up) removes u0 from shared memory: the kernel then has the
+// trip kernel's footprint -- one n-vector and the ring -- i.e. 40 KB chunks instead of 16 KB at n = 10,000, which is what
+// limited the other two versions (30.4 -> 26.6 ms for 160 GB, 6.0 TB/s read + write).  One loop, one reduction per
+// feature; update, write-back and score accumulation of feature j-1 ride on the load loop of feature j.  The weights it
+// produces start the next component's first trip; every later trip recomputes them from the stored matrix.
+// ------------------------------------------------------------------------------------------
+template <bool NANMODE, class C>
+__global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const long ld = a.ld;
+  const int units = static_cast<int>(ld >> 1);
+  const int ncf = (units + C::UC - 1) / C::UC;
+  const Smem<C> sm(smem_raw, ld, 1);  // ts
+  init_sync<C>(sm);
+  const bool next = a.gdef != nullptr;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.ts[i] : 0.0;
+  const double c_dense = next ? *a.cscal : 0.0;  // ts . u0
+  __syncthreads();
+
+  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
+  const int lane = threadIdx.x & 31, wig = tg >> 5;
+  const int wk = blockIdx.x * C::G + g;
+  if (wk >= a.nsplit) return;
+  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
+  if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
+  const double inv_uu = next ? 1.0 / *a.uu : 1.0;
+  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
+  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  double2 acc[C::EPT], x[C::EPT];
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0, wj = 0.0, pj = 0.0;
+  uint32_t mx = 0, my = 0;  // NaN mode: NaN positions of the feature held in x (written back as NaN)
+  int s = 0;
+  uint32_t ph = 0;
+  int flip = 0;
+
+  for (int j = f0; j <= f1; ++j) {
+    const bool load = j < f1, store = j > f0;
+    const double rdp = (NANMODE && load) ? a.rden[j] : 1.0;               // loadings: 1 / masked ts'ts (dense: not divided, :920)
+    const double rdw = (NANMODE && load && next) ? a.rden2[j] : inv_uu;   // next weights: 1 / masked u0'u0
+    const double cj = (NANMODE && load && next) ? a.cmask[j] : c_dense;   // (masked) ts . u0
+    double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j - 1) * ld);  // row of the feature held in x
+    const double gj = (load && next) ? a.gdef[j] : 0.0;  // x_j . u0 before this deflation
+    double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
+    uint32_t nmx = 0, nmy = 0;
+#pragma unroll
+    for (int c = 0; c < C::CPF; ++c) {
+      const bool have = load && c < ncf;
+      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+      if (have) mbar_wait(&sm.full[g * C::S + s], ph);
+      const bool whole = c + 1 < ncf;
+#pragma unroll
+      for (int e = 0; e < C::EPTC; ++e) {
+        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+        if (c < ncf && (whole || gi < units)) {
+          const double2 tv = ts2[gi];
+          if (store) {  // feature j-1: deflate, write back, accumulate the next component's score partials
+            double2 xn;
+            xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
+            xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
+            if (NANMODE) {
+              double2 out = xn;
+              if ((mx >> k) & 1u) { out.x = qnan; xn.x = 0.0; }
+              if ((my >> k) & 1u) { out.y = qnan; xn.y = 0.0; }
+              st_stream(xg + gi, out);
+            } else {
+              st_stream(xg + gi, xn);
+            }
+            acc[k].x = fma(wj, xn.x, acc[k].x);
+            acc[k].y = fma(wj, xn.y, acc[k].y);
+          }
+          if (have) {  // feature j: into the freed registers, both dot products on the fly
+            double2 xv = xs[l];
+            if (NANMODE) {
+              if (isnan(xv.x)) { xv.x = 0.0; nmx |= 1u << k; }
+              if (isnan(xv.y)) { xv.y = 0.0; nmy |= 1u << k; }
+            }
+            if (e & 1) {
+              pc = fma(xv.x, tv.x, pc);
+              pd = fma(xv.y, tv.y, pd);
+            } else {
+              pa = fma(xv.x, tv.x, pa);
+              pb = fma(xv.y, tv.y, pb);
+            }
+            x[k] = xv;
+          }
+        }
+      }
+      if (have) {
+        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm), a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm);
+        if (++s == C::S) { s = 0; ph ^= 1u; }
+      }
+    }
+    if (!load) break;
+    mx = nmx;
+    my = nmy;
+    double v[1] = {(pa + pb) + (pc + pd)};
+    worker_sum<1, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
+    flip ^= 1;
+    pj = v[0] * rdp;
+    const double gnew = gj - pj * cj;  // x_j(deflated) . u0
+    if (next) {
+      wj = gnew * rdw;
+      normsq = fma(wj, wj, normsq);
+    }
+    if (tg == 0) {
+      a.P_k[j] = pj;
+      a.pss[j] = pj * pj;
+      if (next) {
+        a.w[j] = wj;
+        a.gdef[j] = gnew;
+      }
+    }
+  }
+  if (!next) return;
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) {
+    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+    if (gi < units) tn[gi] = acc[k];
+  }
+  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
 // Configurations by feature length (units = ld/2 16-byte units per feature <= TG*EPTC*CPF).  Measured (profiles/r1_notes.md):
 // every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as the ring allows:
 // the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
@@ -692,6 +830,16 @@ int launch_deflate(const FusedArgs& a, cudaStream_t st) {
   return MBPLS_OK;
 }
 
+template <bool NANMODE, class C>
+int launch_deflate3(const FusedArgs& a, cudaStream_t st) {
+  const size_t smem = fused_smem_bytes<C>(a.ld, 1);
+  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
+  const int grid = (a.nsplit + C::G - 1) / C::G;
+  cudaFuncSetAttribute(fused_deflate3_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  fused_deflate3_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
+  return MBPLS_OK;
+}
+
 int config_of(long ld) {  // 0: unsupported
   if (ld < 16 || (ld % 16) != 0) return 0;
   const long units = ld >> 1;
@@ -719,12 +867,12 @@ int mbpls_fused_workers_per_cta(long ld) {
 
 int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
                                 const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* w,
-                                double* norm_part, double* Tnum, long ldt, const int* done, void* stream) {
+                                double* norm_part, double* Tnum, long ldt, double* dots_out, const int* done, void* stream) {
   if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || ld < n || ldt < ld || B < 1)
     return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
-  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B, w, norm_part,
-              Tnum, ldt, nullptr, nullptr, done};
+  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, nullptr, nullptr, dots_out, split_f0, split_f1, split_block, nsplit, B,
+              w, norm_part, Tnum, ldt, nullptr, nullptr, done};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
@@ -745,8 +893,8 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
   if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
   if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && !rden_u0))) return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
-  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, tsu0_masked, split_f0, split_f1, split_block, nsplit, B, w_next,
-              norm_part, Tnum, ldt, P_k, pss, nullptr};
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, tsu0_masked, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
+              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;
   switch (config_of(ld)) {
@@ -754,6 +902,29 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
     case 2: rc = rden_ts ? launch_deflate<true, CfgB>(a, st) : launch_deflate<false, CfgB>(a, st); break;
     case 3: rc = rden_ts ? launch_deflate<true, CfgC>(a, st) : launch_deflate<false, CfgC>(a, st); break;
     case 4: rc = rden_ts ? launch_deflate<true, CfgD>(a, st) : launch_deflate<false, CfgD>(a, st); break;
+    default: break;
+  }
+  if (rc != MBPLS_OK) return rc;
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_fused_deflate_rec_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0u0,
+                                const double* rden_u0, const double* tsu0, const double* tsu0_masked, double* gdef,
+                                const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
+                                double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream) {
+  if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
+  if (gdef && (!u0u0 || !tsu0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && (!rden_u0 || !tsu0_masked))))
+    return MBPLS_ERR_ARG;
+  if (nsplit == 0) return MBPLS_OK;
+  FusedArgs a{nullptr, Xt, ld, n, nullptr, u0u0, ts, rden_ts, rden_u0, tsu0_masked, tsu0, gdef, split_f0, split_f1, split_block, nsplit, B,
+              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = MBPLS_ERR_SIZE;
+  switch (config_of(ld)) {
+    case 1: rc = rden_ts ? launch_deflate3<true, CfgA>(a, st) : launch_deflate3<false, CfgA>(a, st); break;
+    case 2: rc = rden_ts ? launch_deflate3<true, CfgB>(a, st) : launch_deflate3<false, CfgB>(a, st); break;
+    case 3: rc = rden_ts ? launch_deflate3<true, CfgC>(a, st) : launch_deflate3<false, CfgC>(a, st); break;
+    case 4: rc = rden_ts ? launch_deflate3<true, CfgD>(a, st) : launch_deflate3<false, CfgD>(a, st); break;
     default: break;
   }
   if (rc != MBPLS_OK) return rc;

@@ -99,6 +99,12 @@ def _i32(vals, device):
 # ingest: host / device arrays -> feature-major device matrix
 # --------------------------------------------------------------------------------------------- #
 _STAGE_BYTES = 64 << 20
+# Recurrence deflation (csrc/fused.cu fused_deflate3_kernel) is 8 % faster at the headline size but opt-in
+# (set_runtime(deflate_rec=True)): the carried x_j . u0 is noisier than a fresh dot product by the ratio |x_j| / |x_j deflated|,
+# which can push diff_t of a late component's second trip over the reference's max_tol = 1e-14 and cost a third trip
+# (observed: component 11 of 19 on a 260 x 115 problem) -- results stay within 1e-8 but n_iter_ no longer matches.
+_DEFLATE_REC_DEFAULT = False
+_REC_REFRESH = 16             # the carried x_j . u0 is recomputed from X every so many components (bounds the drift)
 _COPY_STREAMS: dict = {}
 
 
@@ -367,7 +373,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
                deflate_last: bool = False, one_pass: Optional[bool] = None,
-               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None) -> NipalsResult:
+               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None,
+               deflate_rec: Optional[bool] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -429,6 +436,11 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
     bits = rden_u = rden_ts = rden_u0 = tsu0_m = tsu0 = None
     deflate_v2 = bool(os.environ.get("MBPLS_DEFLATE_V2"))  # experiment switch, see csrc/fused.cu launch_deflate
+    # recurrence deflation (fused_deflate3_kernel): x_j . u0 is carried per feature instead of keeping u0 in shared memory
+    use_rec = use_opd and fuse_next_xtu and (deflate_rec is True or (deflate_rec is None and _DEFLATE_REC_DEFAULT))
+    gdef = buf(p) if use_rec else None
+    if use_rec and tsu0 is None:
+        tsu0 = buf(1)
     ldw = 0
     if nan and use_op:
         # NaN bit matrix (the pattern never changes: deflation keeps NaN, mbpls.py:969) and the masked denominators
@@ -480,14 +492,18 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         while True:
             for _ in range(trips_per_sync):
                 first = launched == 0
-                if (first and w_ready == "scores") or (use_op and not (first and w_ready == "w")):
-                    if not (first and w_ready == "scores"):
+                # recurrence deflation: every _REC_REFRESH components the first trip is recomputed from X (its u is u0), which
+                # re-seeds the carried x_j . u0 exactly; otherwise the deflation pass has already left the first trip's scores
+                have_scores = first and w_ready == "scores" and not (use_rec and k % _REC_REFRESH == 0)
+                if have_scores or (use_op and not (first and w_ready == "w")):
+                    if not have_scores:
                         if nan:  # 1 / sum over the observed samples of u^2, per feature (mbpls.py:848-852)
                             timed("colden", lambda: call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u), None,
                                                          ptr(scal), 1, ptr(rden_u), done_p, st))
                         timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(rden_u),
                                                    ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o),
-                                                   ptr(Tnum_o), ld, done_p, st))
+                                                   ptr(Tnum_o), ld, ptr(gdef) if (use_rec and first) else None,
+                                                   done_p, st))
                         if nan:  # sum over the observed features of w~^2, per sample and split (:867-872)
                             timed("rowden", lambda: call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1),
                                                          nsplit_o, ptr(Tden_o), ld, done_p, st))
@@ -537,16 +553,26 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
                 call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
                      ptr(rden_ts), None, st)
-                if fuse and deflate_v2:  # sum over the observed samples of ts u0 per feature (fused_deflate2_kernel, opt-in)
+                if fuse and (deflate_v2 or use_rec):  # sum over the observed samples of ts u0 per feature
                     call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
                     call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(u0), ptr(tsu0), 2,
                          ptr(tsu0_m), None, st)
-            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
-                                          ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
-                                          ptr(rden_u0) if fuse else None, ptr(tsu0_m) if (fuse and deflate_v2) else None, ptr(osf0),
-                                          ptr(osf1), ptr(osblk), nsplit_o, B,
-                                          ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
-                                          ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
+            elif fuse and use_rec:
+                call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
+            if use_rec:
+                timed("deflate", lambda: call("mbpls_fused_deflate_rec_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
+                                              ptr(u0u0) if fuse else None, ptr(rden_u0) if fuse else None,
+                                              ptr(tsu0) if fuse else None, ptr(tsu0_m) if fuse else None,
+                                              ptr(gdef) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
+                                              ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
+                                              ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
+            else:
+                timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
+                                              ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
+                                              ptr(rden_u0) if fuse else None, ptr(tsu0_m) if (fuse and deflate_v2) else None,
+                                              ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
+                                              ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
+                                              ptr(Tnum_o) if fuse else None, ld, st))
             if nan and fuse:
                 call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1), nsplit_o, ptr(Tden_o), ld,
                      None, st)

@@ -47,6 +47,7 @@ _RUNTIME_DEFAULTS = dict(
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
     one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 10240), False two-pass kernels
     one_pass_deflate=None,  # loadings+deflation also runs the next component's whole first trip (None auto, False off)
+    deflate_rec=None,     # that pass without a resident u0: x_j.u0 carried per feature across components (csrc/fused.cu v3)
 )
 
 
@@ -466,7 +467,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
-                           one_pass_deflate=rt["one_pass_deflate"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
+                           one_pass_deflate=rt["one_pass_deflate"], deflate_rec=rt["deflate_rec"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
