@@ -33,6 +33,8 @@ __all__ = ["MBPLS"]
 _SPARSITY_MSG = ("The sparsity of your data is likely to high for this algorithm. This can cause either convergence"
                  "problems or crash the algorithm.")
 
+_LAZY_NAMES = ("Ts_", "U_", "V_", "T_", "W_", "W_non_normal_", "W_concat_", "P_", "R_", "beta_", "x_scalers_", "y_scaler_")
+
 _RUNTIME_DEFAULTS = dict(
     device=None,          # torch device (default: current CUDA device)
     group=None,           # torch.distributed process group: shard the feature axis over its ranks
@@ -248,6 +250,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_dev"] = None
         self.__dict__["_dev_scalers"] = None
         self.__dict__["_rows"] = None
+        for name in _LAZY_NAMES:  # results of an earlier fit must not shadow the lazily materialised ones of this fit
+            self.__dict__.pop(name, None)
 
         if self.method == 'KERNEL' and world > 1:
             blocks0 = X if _is_block_list(X) else [X]
@@ -282,6 +286,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
 
             # ---- standardisation (mbpls.py:299-326)
             zss = None
+            pre_lazy = None
             if self.standardize:
                 prof = rt["profile"]
                 if prof is not None:
@@ -299,7 +304,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                         and bool(torch.isfinite(xs.var[:pl]).all()) and bool((ys.seen[:q] == n).all()) \
                         and bool(torch.isfinite(ys.mean[:q]).all()) and bool(torch.isfinite(ys.var[:q]).all())
                     self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
-                self._store_scalers(xs, ys, shard, q)
+                pre_lazy = self._lazy_scalers(xs, ys, shard, q)
                 zss = xs.zss
                 self.__dict__["_dev_scalers"] = (xs.mean[:shard.p_local], xs.scale[:shard.p_local], ys.mean[:q], ys.scale[:q])
             self.num_blocks_ = B
@@ -309,6 +314,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             else:
                 from . import crossmethods
                 crossmethods.fit(self, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
+            if pre_lazy:
+                self.__dict__["_lazy"].update(pre_lazy)
         if rt["materialize"]:
             self._materialize_all()
         return self
@@ -419,18 +426,28 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_col_nan"] = col_nan  # per local feature, for the masked denominators of the one-pass kernels
         return row_flag, (ycol_nan[:q] > 0).to(torch.uint8).contiguous()
 
-    def _store_scalers(self, xs, ys, shard, q):
-        mean = self._gather_features(xs.mean.view(1, -1), shard)[0]
-        var = self._gather_features(xs.var.view(1, -1), shard)[0]
-        scale = self._gather_features(xs.scale.view(1, -1), shard)[0]
-        seen = self._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
-        self.x_scalers_ = []
-        g0 = 0
-        for pb in shard.sizes:
-            self.x_scalers_.append(_make_scaler(mean[g0:g0 + pb], var[g0:g0 + pb], scale[g0:g0 + pb], seen[g0:g0 + pb]))
-            g0 += pb
-        self.y_scaler_ = _make_scaler(ys.mean[:q].cpu().numpy(), ys.var[:q].cpu().numpy(), ys.scale[:q].cpu().numpy(),
-                                      ys.seen[:q].cpu().numpy())
+    def _lazy_scalers(self, xs, ys, shard, q):
+        """x_scalers_ / y_scaler_ as lazily materialised attributes: the statistics stay on the device (predict / transform
+        use them there) and are gathered into scikit-learn StandardScaler objects on first access (32 MB of D2H per
+        million features that a fit should not wait for)."""
+        box = {}
+
+        def build():
+            if not box:
+                mean = self._gather_features(xs.mean.view(1, -1), shard)[0]
+                var = self._gather_features(xs.var.view(1, -1), shard)[0]
+                scale = self._gather_features(xs.scale.view(1, -1), shard)[0]
+                seen = self._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
+                xsc, g0 = [], 0
+                for pb in shard.sizes:
+                    xsc.append(_make_scaler(mean[g0:g0 + pb], var[g0:g0 + pb], scale[g0:g0 + pb], seen[g0:g0 + pb]))
+                    g0 += pb
+                box["x"] = xsc
+                box["y"] = _make_scaler(ys.mean[:q].cpu().numpy(), ys.var[:q].cpu().numpy(), ys.scale[:q].cpu().numpy(),
+                                        ys.seen[:q].cpu().numpy())
+            return box
+
+        return {"x_scalers_": lambda: build()["x"], "y_scaler_": lambda: build()["y"]}
 
     def _block_sums(self, per_feature: torch.Tensor, boff_dev, B, group) -> np.ndarray:
         s = E.segsum(per_feature, boff_dev, B).clone()
