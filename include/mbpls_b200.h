@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 5
+#define MBPLS_ABI_VERSION 6
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -165,12 +165,9 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
 /* Loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL -- the complete
  * first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0, its squared norms
  * and its partial block scores Tnum.  1 read + 1 write of X.  NaN mode (rden_ts != NULL): masked loadings / weights through
- * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0) and the per-feature masked dot
- * product tsu0_masked[j] = sum_{i observed in j} ts_i u0_i (mbpls_masked_colden_f64 mode 2); NaN entries stay NaN.
- * The next weight is formed from the two dot products of the undeflated feature,
- * x_j(deflated) . u0 = x_j . u0 - p_j (ts . u0), so the feature is loaded, reduced ONCE, and updated on the fly. */
+ * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0); NaN entries stay NaN. */
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
-                            const double* u0u0, const double* rden_u0, const double* tsu0_masked, const int* split_f0, const int* split_f1,
+                            const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream);
 

@@ -41,10 +41,6 @@
 
 using namespace mbpls;
 
-#ifndef MBPLS_FUSED_PIPE
-#define MBPLS_FUSED_PIPE 0
-#endif
-
 namespace {
 
 struct FusedArgs {
@@ -57,9 +53,9 @@ struct FusedArgs {
   const double* ts;  // deflate only
   const double* rden;   // NaN mode: per-feature reciprocal masked denominator for u (trip) / ts (deflate)
   const double* rden2;  // NaN mode, deflate: same for u0
-  const double* cmask;  // NaN mode, deflate v2/v3: per-feature masked ts . u0
-  const double* cscal;  // deflate v3: device scalar ts . u0
-  double* gdef;         // deflate v3: running x_j(deflated) . u0 per feature (read, updated); trip: raw dot products out
+  const double* cmask;  // recurrence deflation, NaN mode: per-feature masked ts . u0
+  const double* cscal;  // recurrence deflation: device scalar ts . u0
+  double* gdef;         // recurrence deflation: running x_j(deflated) . u0 per feature (read, updated); trip: raw dot products out
   const int* split_f0;
   const int* split_f1;
   const int* split_block;
@@ -256,10 +252,8 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     const double rd = (NANMODE && load) ? a.rden[j] : inv_uu;  // 1 / (masked) u'u of this feature
     double numa = 0.0, numb = 0.0, numc = 0.0, numd = 0.0;
     int s_use = s;  // s: next stage to load from; s_use: stage of the chunk being consumed
-    constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;  // few units per chunk: issue chunk c+1's loads before consuming chunk c
-    double2 ub[2][PIPE ? C::EPTC : 1];  // u values travelling with the chunk in flight
 
-    // L(c): previous feature's weight into the accumulators, then this feature's chunk c into the freed registers
+    // previous feature's weight into the accumulators, then this feature's chunk c into the freed registers
     auto load_chunk = [&](const int c) {
       const bool have = load && c < ncf;
       const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
@@ -279,9 +273,7 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
           uv = u2[gi];
           if (NANMODE) xv = nan_to_zero(xv);  // masked sums: a missing entry contributes nothing (:848-852, :867-872)
         }
-        if (PIPE) {
-          ub[c & 1][e] = uv;
-        } else if (have) {  // consume on the spot
+        if (have) {
           if (e & 1) {
             numc = fma(xv.x, uv.x, numc);
             numd = fma(xv.y, uv.y, numd);
@@ -293,39 +285,18 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
         x[k] = xv;
       }
     };
-    // F(c): dot product of chunk c (its loads were issued one step earlier), then hand the stage back
-    auto use_chunk = [&](const int c) {
+    // hand the stage back as soon as the chunk sits in registers; refill at once: every cycle a free stage sits idle is
+    // ring depth lost (deferring the check by one chunk to hide the atomic's latency cost 10 % on the shallow rings, and
+    // issuing chunk c+1's shared-memory loads before consuming chunk c changed nothing: profiles/r1_notes.md)
+    auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-#pragma unroll
-      for (int e = 0; e < (PIPE ? C::EPTC : 0); ++e) {
-        const int k = c * C::EPTC + e;
-        const double2 xv = x[k], uv = ub[c & 1][e];
-        if (e & 1) {
-          numc = fma(xv.x, uv.x, numc);
-          numd = fma(xv.y, uv.y, numd);
-        } else {
-          numa = fma(xv.x, uv.x, numa);
-          numb = fma(xv.y, uv.y, numb);
-        }
-      }
-      // refill at once: every cycle a free stage sits idle is ring depth lost (deferring the check by one chunk to
-      // hide the atomic's latency cost 10 % on the shallow rings)
       refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xt, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
       if (++s_use == C::S) s_use = 0;
     };
-    if (PIPE) {
-      load_chunk(0);
 #pragma unroll
-      for (int c = 0; c < C::CPF; ++c) {
-        if (c + 1 < C::CPF) load_chunk(c + 1);
-        use_chunk(c);
-      }
-    } else {  // many independent loads per chunk already (and several workers per SM): no extra registers
-#pragma unroll
-      for (int c = 0; c < C::CPF; ++c) {
-        load_chunk(c);
-        use_chunk(c);
-      }
+    for (int c = 0; c < C::CPF; ++c) {
+      load_chunk(c);
+      release_chunk(c);
     }
     if (!load) break;
     double one[1] = {(numa + numb) + (numc + numd)};
@@ -396,8 +367,6 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
     double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
     uint32_t mx = 0, my = 0;  // NaN mode: which of this thread's entries are NaN (they must be stored back as NaN)
     int s_use = s;
-    constexpr bool PIPE = MBPLS_FUSED_PIPE && C::EPTC <= 2;
-    double2 tb[2][PIPE ? C::EPTC : 1];  // ts values travelling with the chunk in flight
 
     auto load_chunk = [&](const int c) {
       const bool have = load && c < ncf;
@@ -421,9 +390,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
             if (isnan(xv.y)) { xv.y = 0.0; my |= 1u << k; }
           }
         }
-        if (PIPE) {
-          tb[c & 1][e] = tv;
-        } else if (e & 1) {
+        if (e & 1) {
           pc = fma(xv.x, tv.x, pc);
           pd = fma(xv.y, tv.y, pd);
         } else {
@@ -433,36 +400,15 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
         x[k] = xv;
       }
     };
-    auto use_chunk = [&](const int c) {
+    auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-#pragma unroll
-      for (int e = 0; e < (PIPE ? C::EPTC : 0); ++e) {
-        const int k = c * C::EPTC + e;
-        const double2 tv = tb[c & 1][e];
-        if (e & 1) {
-          pc = fma(x[k].x, tv.x, pc);
-          pd = fma(x[k].y, tv.y, pd);
-        } else {
-          pa = fma(x[k].x, tv.x, pa);
-          pb = fma(x[k].y, tv.y, pb);
-        }
-      }
       refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xw, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
       if (++s_use == C::S) s_use = 0;
     };
-    if (PIPE) {
-      load_chunk(0);
 #pragma unroll
-      for (int c = 0; c < C::CPF; ++c) {
-        if (c + 1 < C::CPF) load_chunk(c + 1);
-        use_chunk(c);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < C::CPF; ++c) {
-        load_chunk(c);
-        use_chunk(c);
-      }
+    for (int c = 0; c < C::CPF; ++c) {
+      load_chunk(c);
+      release_chunk(c);
     }
     if (!load) break;
     double one[1] = {(pa + pb) + (pc + pd)};
@@ -524,153 +470,20 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 }
 
 // ------------------------------------------------------------------------------------------
-// Deflation, second version: ONE loop and ONE reduction per feature.
+// Recurrence deflation (opt-in, set_runtime(deflate_rec=True)): the same pass without a resident u0.
 //
-// With both dot products of the *undeflated* feature in hand, a = x_j . u0 and p_j = x_j . ts, the next weight follows
-// from the identity  x_j(deflated) . u0 = a - p_j (ts . u0)  (masked data: all three sums over the observed samples of
-// the feature), so it is known right after the loading, before the feature has been updated.  The update
-// x <- x - ts p_j, its write-back and the score accumulation acc += w~ x(deflated) of feature j-1 then ride, unit by
-// unit, on the load loop of feature j, exactly like the trip kernel: each register is updated, stored, accumulated
-// and reloaded in turn, `ts` is read from shared memory once per unit for both uses, and the ring is drained at an
-// even pace.  (The first version updated the whole feature between two reductions: ncu showed 12 % of all stall
-// samples on the wait for the chunk that does not fit the 64 KB ring, and two barriers per feature.)
-// The weight differs from "dot product of the rounded deflated feature" by rounding only (a few ulp of |x_j||u0|); it is
-// used for the first trip of the next component, every later trip recomputes the weights from the stored matrix.
-// ------------------------------------------------------------------------------------------
-template <bool NANMODE, class C>
-__global__ void __launch_bounds__(512, 1) fused_deflate2_kernel(const FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const long ld = a.ld;
-  const int units = static_cast<int>(ld >> 1);
-  const int ncf = (units + C::UC - 1) / C::UC;
-  const Smem<C> sm(smem_raw, ld, 2);  // ts | u0
-  init_sync<C>(sm);
-  const bool next = a.u != nullptr;
-  double cpart = 0.0;
-  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
-    const double t = i < a.n ? a.ts[i] : 0.0, uv = (next && i < a.n) ? a.u[i] : 0.0;
-    sm.vec0[i] = t;
-    sm.vec1[i] = uv;
-    cpart = fma(t, uv, cpart);
-  }
-  const double c_dense = block_sum1(cpart, sm.scratch);  // ts . u0 (two __syncthreads inside: the vectors are in place)
-  __syncthreads();
-
-  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
-  const int lane = threadIdx.x & 31, wig = tg >> 5;
-  const int wk = blockIdx.x * C::G + g;
-  if (wk >= a.nsplit) return;
-  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
-  if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
-  const double inv_uu = next ? 1.0 / *a.uu : 1.0;
-  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
-  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec1);
-  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-
-  double2 acc[C::EPT], x[C::EPT];
-#pragma unroll
-  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
-  double normsq = 0.0, wj = 0.0, pj = 0.0;
-  uint32_t mx = 0, my = 0;  // NaN mode: NaN positions of the feature held in x (written back as NaN)
-  int s = 0;
-  uint32_t ph = 0;
-  int flip = 0;
-
-  for (int j = f0; j <= f1; ++j) {
-    const bool load = j < f1, store = j > f0;
-    const double rdp = (NANMODE && load) ? a.rden[j] : 1.0;               // loadings: 1 / masked ts'ts (dense: not divided, :920)
-    const double rdw = (NANMODE && load && next) ? a.rden2[j] : inv_uu;   // next weights: 1 / masked u0'u0
-    const double cj = (NANMODE && load && next) ? a.cmask[j] : c_dense;   // (masked) ts . u0
-    double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j - 1) * ld);  // row of the feature held in x
-    double pa = 0.0, pb = 0.0, qa = 0.0, qb = 0.0;
-    uint32_t nmx = 0, nmy = 0;
-#pragma unroll
-    for (int c = 0; c < C::CPF; ++c) {
-      const bool have = load && c < ncf;
-      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
-      if (have) mbar_wait(&sm.full[g * C::S + s], ph);
-      const bool whole = c + 1 < ncf;
-#pragma unroll
-      for (int e = 0; e < C::EPTC; ++e) {
-        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
-        if (c < ncf && (whole || gi < units)) {
-          const double2 tv = ts2[gi];
-          if (store) {  // feature j-1: deflate, write back, accumulate the next component's score partials
-            double2 xn;
-            xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
-            xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
-            if (NANMODE) {
-              double2 out = xn;
-              if ((mx >> k) & 1u) { out.x = qnan; xn.x = 0.0; }
-              if ((my >> k) & 1u) { out.y = qnan; xn.y = 0.0; }
-              st_stream(xg + gi, out);
-            } else {
-              st_stream(xg + gi, xn);
-            }
-            acc[k].x = fma(wj, xn.x, acc[k].x);
-            acc[k].y = fma(wj, xn.y, acc[k].y);
-          }
-          if (have) {  // feature j: into the freed registers, both dot products on the fly
-            double2 xv = xs[l];
-            if (NANMODE) {
-              if (isnan(xv.x)) { xv.x = 0.0; nmx |= 1u << k; }
-              if (isnan(xv.y)) { xv.y = 0.0; nmy |= 1u << k; }
-            }
-            pa = fma(xv.x, tv.x, pa);
-            pb = fma(xv.y, tv.y, pb);
-            if (next) {
-              const double2 uv = u2[gi];
-              qa = fma(xv.x, uv.x, qa);
-              qb = fma(xv.y, uv.y, qb);
-            }
-            x[k] = xv;
-          }
-        }
-      }
-      if (have) {
-        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm), a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm);
-        if (++s == C::S) { s = 0; ph ^= 1u; }
-      }
-    }
-    if (!load) break;
-    mx = nmx;
-    my = nmy;
-    double v[2] = {pa + pb, qa + qb};
-    worker_sum<2, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
-    flip ^= 1;
-    pj = v[0] * rdp;
-    if (next) {
-      wj = (v[1] - pj * cj) * rdw;
-      normsq = fma(wj, wj, normsq);
-    }
-    if (tg == 0) {
-      a.P_k[j] = pj;
-      a.pss[j] = pj * pj;
-      if (next) a.w[j] = wj;
-    }
-  }
-  if (!next) return;
-  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
-#pragma unroll
-  for (int k = 0; k < C::EPT; ++k) {
-    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
-    if (gi < units) tn[gi] = acc[k];
-  }
-  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
-}
-
-// ------------------------------------------------------------------------------------------
-// Deflation, third version (the default): the second version without the resident u0.
-//
-// The dot product a_j = x_j . u0 of the second version obeys a recurrence over the components: deflation turns it into
-// a_j - p_j (ts . u0) (masked data: the sum of ts_i u0_i over the observed samples of the feature).  Keeping that scalar
-// per feature in global memory (`gdef`, seeded with the raw dot products of a first trip, whose u IS u0, and re-seeded the
-// same way every few components so that rounding cannot pile up) removes u0 from shared memory: the kernel then has the
-// trip kernel's footprint -- one n-vector and the ring -- i.e. 40 KB chunks instead of 16 KB at n = 10,000, which is what
-// limited the other two versions (30.4 -> 26.6 ms for 160 GB, 6.0 TB/s read + write).  One loop, one reduction per
-// feature; update, write-back and score accumulation of feature j-1 ride on the load loop of feature j.  The weights it
-// produces start the next component's first trip; every later trip recomputes them from the stored matrix.
+// With p_j = x_j . ts in hand, the dot product of the DEFLATED feature with u0 follows from that of the undeflated one:
+// x_j(deflated) . u0 = x_j . u0 - p_j (ts . u0)   (masked data: all sums over the observed samples of the feature).
+// So a_j = x_j . u0 obeys a recurrence over the components.  Keeping that scalar per feature in global memory (`gdef`,
+// seeded with the raw dot products of a first trip, whose u IS u0, and re-seeded the same way every few components so that
+// rounding cannot pile up) removes u0 from shared memory: the kernel then has the trip kernel's footprint -- one n-vector
+// and the ring -- i.e. 40 KB chunks instead of 16 KB at n = 10,000 (30.4 -> 26.6 ms for 160 GB, 6.0 TB/s read + write),
+// and the next weight is known right after the ONE reduction, so update, write-back and score accumulation of feature j-1
+// ride, unit by unit, on the load loop of feature j (each register is updated, stored, accumulated and reloaded in turn).
+// Not the default: the carried scalar is noisier than a fresh dot product by the ratio |x_j| / |x_j deflated|, which can
+// push diff_t of a late component's second trip over the reference's max_tol = 1e-14 and cost a third trip
+// (profiles/r1_notes.md).  A variant that keeps u0 resident and forms x_j . u0 afresh (one reduction, same footprint as
+// fused_deflate_kernel) measured 29.0 vs 30.0 ms and was dropped.
 // ------------------------------------------------------------------------------------------
 template <bool NANMODE, class C>
 __global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs a) {
@@ -817,16 +630,8 @@ int launch_deflate(const FusedArgs& a, cudaStream_t st) {
   const size_t smem = fused_smem_bytes<C>(a.ld, 2);
   if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
   const int grid = (a.nsplit + C::G - 1) / C::G;
-  // The single-reduction version (fused_deflate2_kernel) measured 29.0 vs 30.0 ms dense and 32.9 vs 30.6 ms masked at the
-  // headline size (profiles/r1_notes.md): not worth giving up "weights from the rounded deflated feature"; opt-in.
-  static const bool v2 = getenv("MBPLS_DEFLATE_V2") != nullptr;
-  if (!v2 || (NANMODE && a.u && !a.cmask)) {
-    cudaFuncSetAttribute(fused_deflate_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    fused_deflate_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(fused_deflate2_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    fused_deflate2_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
-  }
+  cudaFuncSetAttribute(fused_deflate_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  fused_deflate_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
   return MBPLS_OK;
 }
 
@@ -887,13 +692,13 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
 }
 
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
-                            const double* u0u0, const double* rden_u0, const double* tsu0_masked, const int* split_f0, const int* split_f1,
+                            const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream) {
   if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
   if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && !rden_u0))) return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
-  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, tsu0_masked, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, nullptr, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
               w_next, norm_part, Tnum, ldt, P_k, pss, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = MBPLS_ERR_SIZE;

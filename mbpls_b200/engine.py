@@ -435,7 +435,6 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     u0u0 = buf(1)
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
     bits = rden_u = rden_ts = rden_u0 = tsu0_m = tsu0 = None
-    deflate_v2 = bool(os.environ.get("MBPLS_DEFLATE_V2"))  # experiment switch, see csrc/fused.cu launch_deflate
     # recurrence deflation (fused_deflate3_kernel): x_j . u0 is carried per feature instead of keeping u0 in shared memory
     use_rec = use_opd and fuse_next_xtu and (deflate_rec is True or (deflate_rec is None and _DEFLATE_REC_DEFAULT))
     gdef = buf(p) if use_rec else None
@@ -553,7 +552,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
                 call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
                      ptr(rden_ts), None, st)
-                if fuse and (deflate_v2 or use_rec):  # sum over the observed samples of ts u0 per feature
+                if fuse and use_rec:  # sum over the observed samples of ts u0 per feature
                     call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
                     call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(u0), ptr(tsu0), 2,
                          ptr(tsu0_m), None, st)
@@ -569,7 +568,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             else:
                 timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
                                               ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
-                                              ptr(rden_u0) if fuse else None, ptr(tsu0_m) if (fuse and deflate_v2) else None,
+                                              ptr(rden_u0) if fuse else None,
                                               ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
                                               ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
                                               ptr(Tnum_o) if fuse else None, ld, st))
