@@ -323,6 +323,18 @@ def run_ours(args):
         if t:
             kern[key] = {"ms": t, "launches": len(profile[key]), "algorithmic_bytes": mult * x_bytes_local,
                          "gbs": mult * x_bytes_local / (t / 1e3) / 1e9}
+    # multi-GPU: every trip ends in an all-reduce, so the slowest rank sets the pace; report the spread of the per-rank means
+    rank_skew = None
+    if world > 1:
+        try:
+            keys = ("trip", "deflate", "standardize", "loadings")
+            mine = torch.tensor([kern[k]["ms"] if k in kern else 0.0 for k in keys], dtype=torch.float64, device=dev)
+            allv = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine, group=group)
+            stack = torch.stack(allv).cpu()
+            rank_skew = {k: {"min_ms": float(stack[:, i].min()), "max_ms": float(stack[:, i].max())} for i, k in enumerate(keys)}
+        except Exception as exc:  # diagnostics must never take the benchmark line down
+            rank_skew = {"error": repr(exc)[:200]}
     # dominant kernel by share of the step: the loadings+deflation(+next first trip) pass when the one-pass kernels run
     # (1 read + 1 write of X per launch), else the X w pass of the two-pass kernels
     dominant = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["launches"]) if kern else None
@@ -412,7 +424,7 @@ def run_ours(args):
             "config": workload_config(args), "trips_per_component": trips, "algorithmic_bytes_per_step": fit_bytes(n, p, K, trips),
             "frac_of_hbm_peak": value / (peak_gbs * world),
             "frac_of_hbm_peak_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9 / (peak_gbs * world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants,
+            "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
             "passes_over_X_per_step": passes, "hbm_gbs_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9,
         }
         print(json.dumps(line), flush=True)
