@@ -16,11 +16,12 @@
 //     copies of one chunk (UC = TG*EPTC units, the last chunk of a feature shorter) each, completion
 //     tracked by one mbarrier per stage.  A stage is released as soon as its chunk sits in registers:
 //     every warp bumps a shared-memory counter after its reads and the LAST warp to arrive refills the
-//     stage itself (proxy fence + expect_tx + bulk copy).  No producer warp (a 17th warp caps the kernel at
+//     stage itself (expect_tx + bulk copy; a warp's reads of the stage have completed before the arithmetic
+//     that precedes its arrival could issue, so the refill cannot overtake them).  No producer warp (a 17th warp caps the kernel at
 //     96 registers and spills the accumulators), no polling, and the refill work lands on whichever warp
 //     happens to be last instead of always delaying the same one (ncu on the first version, which had
 //     one feeder thread per worker: 52 % of all stall samples at the worker barrier behind that warp);
-//   * u (and, in NaN mode, the per-sample "missing weight" accumulators) live in shared memory.
+//   * u lives in shared memory.
 // Per feature: chunks -> registers with the dot product against u on the fly; one fixed-order reduction over
 // the worker (warp shuffles + one named barrier); w~_j; then acc_i += w~_j x_ij in registers.  Partial
 // scores go to Tnum[split][.] exactly like xw_kernel's, so reduce_partials / the epilogue are unchanged and
@@ -179,6 +180,8 @@ __device__ __forceinline__ void prime_ring(const double* __restrict__ X, long ld
 }
 
 // The calling warp is done reading stage (g, s).  Returns the number of warps that had said so before (lane 0 only).
+// Relaxed atomic: every shared-memory read of the stage feeds a dot-product FMA that precedes this call in program order,
+// and an instruction cannot issue before its operands have arrived, so the reads have completed when the counter moves.
 template <class C>
 __device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const Smem<C>& sm) {
   __syncwarp();
@@ -186,8 +189,8 @@ __device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const S
 }
 
 // The last warp of the worker to arrive on a stage (which held chunk c of feature j) refills it with the chunk S
-// positions further down the worker's stream.  Called one chunk after arrive_stage, so that the shared-memory
-// atomic's latency is off the critical path.
+// positions further down the worker's stream, immediately (a free stage is lost ring depth).  -DMBPLS_FUSED_PROXY_FENCE adds
+// an explicit generic->async proxy fence in front of the bulk copy.
 template <class C>
 __device__ __forceinline__ void refill_if_last(unsigned old, const double* __restrict__ X, long ld, int units, int ncf, int g, int s,
                                                int j, int c, int f1, int lane, const Smem<C>& sm) {
