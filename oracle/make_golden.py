@@ -223,18 +223,28 @@ def live_cases():
     Yy[last_sparse[:5], 1] = np.nan
     Yy[last_sparse[3:8], 2] = np.nan
     cases["nan_y_nipals"] = (Xy, Yy, Xmt, Ymt, dict(n_components=3, method="NIPALS", sparse_data=True))
+    # deep PLS1: 19 components (two trips each), far into the deflated residual; also longer than the refresh period of the
+    # opt-in recurrence deflation of the CUDA path
+    Xd, Yd = latent_blocks(260, (70, 45), 1, 19, seed=17, decay=0.9)
+    Xdt, Ydt = latent_blocks(9, (70, 45), 1, 19, seed=18, decay=0.9)
+    cases["pls1_deep_nipals"] = (Xd, Yd.ravel(), Xdt, Ydt.ravel(), dict(n_components=19, method="NIPALS"))
     return cases
 
 
 def main():
+    """python -m oracle.make_golden [case ...]: regenerate everything, or only the named live cases."""
     os.makedirs(GOLDEN, exist_ok=True)
     Ref = refshim.load()
-    print("pinning against the reference's known-answer CSVs")
-    kat_case(50, "pn", ["UNIPALS", "NIPALS", "KERNEL", "SIMPLS"])
-    kat_case(150, "np", ["UNIPALS", "KERNEL"])
+    only = set(sys.argv[1:])
+    if not only:
+        print("pinning against the reference's known-answer CSVs")
+        kat_case(50, "pn", ["UNIPALS", "NIPALS", "KERNEL", "SIMPLS"])
+        kat_case(150, "np", ["UNIPALS", "KERNEL"])
     print("live reference runs")
     worst_all = 0.0
     for name, (X, Y, Xt, Yt, kwargs) in live_cases().items():
+        if only and name not in only:
+            continue
         cp = (lambda a: [x.copy() for x in a] if isinstance(a, list) else a.copy())
         ref = run_model(Ref, kwargs, cp(X), cp(Y), cp(Xt), cp(Yt), traced=True)
         ours = run_model(OracleMBPLS, kwargs, cp(X), cp(Y), cp(Xt), cp(Yt))
