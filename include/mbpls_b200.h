@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 6
+#define MBPLS_ABI_VERSION 7
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -151,10 +151,16 @@ int mbpls_loadings_deflate_f64(double* Xt, long ld, int n, int p, const double* 
  * n-vector of partial block scores in registers; outputs have the layout of mbpls_nipals_xw_f64 /
  * mbpls_nipals_xtu_f64 (Tnum[s][.], w[j]) and norm_part[s*B + split_block[s]] = sum of w~_j^2
  * over the split (all other entries of norm_part must be zero), so mbpls_nipals_reduce_partials_f64 and the
- * epilogue apply unchanged.  mbpls_fused_workers_per_cta(ld) returns the workers per CTA (0: the feature is
- * too long for the register-resident accumulators, use the two-pass kernels); size the split table to
- * workers_per_cta * number of SMs. */
-int mbpls_fused_workers_per_cta(long ld);
+ * epilogue apply unchanged.  Features of up to 10,240 samples are handled by one CTA; the deflation pass of features
+ * longer than 5,120 samples, and both passes of features of up to 20,480 samples, split every feature by samples over
+ * the two CTAs of a thread-block cluster (each keeps half of ts / u0 / u in shared memory; partial dot products meet
+ * through distributed shared memory).  mbpls_fused_total_workers(ld) returns the number of splits to build on the
+ * current device (0: the feature is too long for the register-resident accumulators, use the two-pass kernels);
+ * mbpls_fused_workers_per_sm_pair(ld) is the device-independent density behind it; mbpls_fused_uses_clusters(ld)
+ * reports which passes run on CTA pairs (bit 0: trip, bit 1: deflation). */
+int mbpls_fused_workers_per_sm_pair(long ld);
+int mbpls_fused_total_workers(long ld);
+int mbpls_fused_uses_clusters(long ld);
 /* rden == NULL: dense data.  NaN mode: rden[j] = reciprocal masked denominator of feature j for this u
  * (mbpls_masked_colden_f64); NaN entries count as zero; the masked score denominators come from
  * mbpls_masked_rowden_f64 afterwards. */

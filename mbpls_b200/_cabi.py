@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -69,7 +69,9 @@ SIGNATURES = {
     "mbpls_nipals_epilogue_f64": [C.POINTER(EpilogueArgs), _p],
     "mbpls_nipals_record_component_f64": [C.POINTER(RecordArgs), _p],
     "mbpls_loadings_deflate_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "mbpls_fused_workers_per_cta": [_l],
+    "mbpls_fused_workers_per_sm_pair": [_l],
+    "mbpls_fused_total_workers": [_l],
+    "mbpls_fused_uses_clusters": [_l],
     "mbpls_nipals_fused_trip_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _l, _p, _p, _p],
     "mbpls_fused_deflate_rec_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p],
     "mbpls_fused_deflate_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p],
@@ -102,7 +104,7 @@ SIGNATURES = {
 }
 
 # functions whose int return value is a plain number, not a status
-_PLAIN = {"mbpls_abi_version", "mbpls_fused_workers_per_cta", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
+_PLAIN = {"mbpls_abi_version", "mbpls_fused_workers_per_sm_pair", "mbpls_fused_total_workers", "mbpls_fused_uses_clusters", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
           "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits"}
 
 

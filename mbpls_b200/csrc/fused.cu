@@ -37,6 +37,17 @@
 // x_j -= ts p_j (:917-930, :968-969) written back from registers, the next component's first weights
 // w~_j = x_j(deflated) . u0 / u0'u0 (u restarts from the same Y column, :838) AND its first block-score
 // partials, so the first trip of the next component needs no pass over X at all.
+//
+// Cluster variants (template parameter CL): a feature is split by SAMPLES over the two CTAs of a thread-block cluster.
+// Each CTA keeps only its half of the resident n-vectors (ts, u0 / u), which frees shared memory for the ring -- at
+// n = 10,000 the deflation kernel's ring grows from 64 KB (16 KB chunks) to 120 KB (20 KB chunks x 3 x 2 workers) -- and
+// lifts the longest one-pass feature from 10,240 to 20,480 samples.  The two halves of a feature meet in its dot products:
+// after the worker-level reduction, thread 0 of the worker sends its partial into the peer CTA's shared memory with
+// st.async (data + mbarrier complete_tx in one message over DSMEM), every thread waits on the local mbarrier and adds
+// own + peer (commutative, so both CTAs hold bit-identical sums).  Two slots per worker alternate; a slot is rewritten only
+// after the peer has passed the next exchange, which in turn needs this worker's next send, which follows the named barrier
+// that every thread reaches after reading the slot -- no further handshake.  Outputs per feature (w~, p, p^2) are written by
+// cluster rank 0 only; score partials by the CTA that owns the samples.
 #include "launch.cuh"
 #include "../../include/mbpls_b200.h"
 
@@ -69,6 +80,7 @@ struct FusedArgs {
   double* P_k;  // deflate: loadings out
   double* pss;  // deflate: p_j^2 out
   const int* done;
+  int sync_mode;  // 0: relaxed stage counter (default); 1: acq_rel counter + generic->async proxy fence before the refill
 };
 
 // TG threads per worker, EPTC units per thread per chunk, at most CPF chunks per feature, S ring stages
@@ -119,6 +131,11 @@ __device__ __forceinline__ unsigned atom_inc_smem(unsigned* p) {
   asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
   return old;
 }
+__device__ __forceinline__ unsigned atom_inc_smem_acqrel(unsigned* p) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+  return old;
+}
 
 // shared-memory carve-up shared by both kernels
 template <class C>
@@ -129,21 +146,25 @@ struct Smem {
   uint64_t* full;   // [G][S] mbarriers: chunk landed
   unsigned* cnt;    // [G][S] (8-byte slots) warps that have finished reading the stage
   double* scratch;  // [G][2][3*NW]
-  __device__ Smem(unsigned char* base, long ld, int nvec) {  // nvec n-vectors in front of the ring
+  uint64_t* xbar;   // [G][2] mbarriers of the cluster exchange: the peer's partial has landed in xval
+  double* xval;     // [G][2]
+  __device__ Smem(unsigned char* base, long vlen, int nvec) {  // nvec vectors of vlen doubles in front of the ring
     vec0 = reinterpret_cast<double*>(base);
-    vec1 = vec0 + ld;
-    ring = vec0 + static_cast<size_t>(nvec) * ld;
+    vec1 = vec0 + vlen;
+    ring = vec0 + static_cast<size_t>(nvec) * vlen;
     full = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(C::G) * C::S * 2 * C::UC);
     cnt = reinterpret_cast<unsigned*>(full + C::G * C::S);
     scratch = reinterpret_cast<double*>(full + 2 * C::G * C::S);
+    xbar = reinterpret_cast<uint64_t*>(scratch + static_cast<size_t>(C::G) * 2 * 3 * C::NW);
+    xval = reinterpret_cast<double*>(xbar + 2 * C::G);
   }
   __device__ __forceinline__ double* stage(int g, int s) const { return ring + (static_cast<size_t>(g) * C::S + s) * 2 * C::UC; }
 };
 
 template <class C>
-size_t fused_smem_bytes(long ld, int nvec) {
-  return static_cast<size_t>(nvec) * ld * 8 + static_cast<size_t>(C::G) * C::S * C::UC * 16 + static_cast<size_t>(C::G) * C::S * 16 +
-         static_cast<size_t>(C::G) * 2 * 3 * C::NW * 8 + 64;
+size_t fused_smem_bytes(long vlen, int nvec) {
+  return static_cast<size_t>(nvec) * vlen * 8 + static_cast<size_t>(C::G) * C::S * C::UC * 16 + static_cast<size_t>(C::G) * C::S * 16 +
+         static_cast<size_t>(C::G) * 2 * 3 * C::NW * 8 + static_cast<size_t>(C::G) * 32 + 64;
 }
 
 // chunk c of feature f of the matrix X -> ring stage (g, s)
@@ -164,6 +185,7 @@ __device__ __forceinline__ void init_sync(const Smem<C>& sm) {
       mbar_init(&sm.full[i], 1);
       sm.cnt[2 * i] = 0;
     }
+    for (int i = 0; i < 2 * C::G; ++i) mbar_init(&sm.xbar[i], 1);
     fence_barrier_init();
   }
 }
@@ -183,9 +205,10 @@ __device__ __forceinline__ void prime_ring(const double* __restrict__ X, long ld
 // Relaxed atomic: every shared-memory read of the stage feeds a dot-product FMA that precedes this call in program order,
 // and an instruction cannot issue before its operands have arrived, so the reads have completed when the counter moves.
 template <class C>
-__device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const Smem<C>& sm) {
+__device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const Smem<C>& sm, int sync_mode) {
   __syncwarp();
-  return lane == 0 ? atom_inc_smem(&sm.cnt[2 * (g * C::S + s)]) : 0u;
+  if (lane != 0) return 0u;
+  return sync_mode ? atom_inc_smem_acqrel(&sm.cnt[2 * (g * C::S + s)]) : atom_inc_smem(&sm.cnt[2 * (g * C::S + s)]);
 }
 
 // The last warp of the worker to arrive on a stage (which held chunk c of feature j) refills it with the chunk S
@@ -193,18 +216,32 @@ __device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const S
 // an explicit generic->async proxy fence in front of the bulk copy.
 template <class C>
 __device__ __forceinline__ void refill_if_last(unsigned old, const double* __restrict__ X, long ld, int units, int ncf, int g, int s,
-                                               int j, int c, int f1, int lane, const Smem<C>& sm) {
+                                               int j, int c, int f1, int lane, const Smem<C>& sm, int sync_mode) {
   if (lane == 0 && old == C::NW - 1) {
     *reinterpret_cast<volatile unsigned*>(&sm.cnt[2 * (g * C::S + s)]) = 0;
     int c2 = c + C::S, f2 = j;
     while (c2 >= ncf) { c2 -= ncf; ++f2; }
     if (f2 < f1) {
-#ifdef MBPLS_FUSED_PROXY_FENCE
-      fence_proxy_async_smem();
-#endif
+      if (sync_mode) fence_proxy_async_smem();
       issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
     }
   }
+}
+
+// Sum of the two CTAs' partials of one worker pair (cluster variants).  `xs` (slot) and `xp` (phase bits) are per-thread state.
+template <class C>
+__device__ __forceinline__ double pair_sum(double own, int g, int tg, uint32_t peer, int& xs, uint32_t& xp, const Smem<C>& sm) {
+  uint64_t* bar = &sm.xbar[2 * g + xs];
+  double* slot = &sm.xval[2 * g + xs];
+  if (tg == 0) {
+    mbar_arrive_expect_tx(bar, 8);
+    st_async_f64(mapa_shared(smem_u32(slot), peer), own, mapa_shared(smem_u32(bar), peer));
+  }
+  mbar_wait_cluster(bar, (xp >> xs) & 1u);
+  const double other = *reinterpret_cast<volatile double*>(slot);
+  xp ^= 1u << xs;
+  xs ^= 1;
+  return own + other;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -220,27 +257,53 @@ __device__ __forceinline__ double2 nan_to_zero(double2 v) {
   return v;
 }
 
-template <bool NANMODE, class C>
-__global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
-  if (a.done && *a.done) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const long ld = a.ld;
-  const int units = static_cast<int>(ld >> 1);
-  const int ncf = (units + C::UC - 1) / C::UC;
-  const Smem<C> sm(smem_raw, ld, 1);  // u
-  init_sync<C>(sm);
-  for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.u[i] : 0.0;
-  __syncthreads();
+// Geometry of one CTA's share of a feature: the whole feature, or (cluster variants) the half owned by this cluster rank.
+struct Geo {
+  int units;      // 16-byte units of a feature handled by this CTA
+  int uoff;       // first unit (0, or units_total / 2 for cluster rank 1)
+  int nloc;       // samples of this CTA's share that are real (< n)
+  int wbase;      // first worker (split) index of this CTA
+  uint32_t peer;  // cluster rank of the other CTA
+  bool lead;      // this CTA writes the per-feature outputs
+};
+template <class C, bool CL>
+__device__ __forceinline__ Geo make_geo(long ld, int n) {
+  Geo ge;
+  const int total = static_cast<int>(ld >> 1);
+  if (CL) {
+    const uint32_t r = cluster_ctarank();
+    ge.units = total >> 1;  // ld % 16 == 0, so the halves are equal and 64-byte aligned
+    ge.uoff = static_cast<int>(r) * ge.units;
+    ge.wbase = static_cast<int>(blockIdx.x >> 1) * C::G;
+    ge.peer = r ^ 1u;
+    ge.lead = r == 0;
+  } else {
+    ge.units = total;
+    ge.uoff = 0;
+    ge.wbase = static_cast<int>(blockIdx.x) * C::G;
+    ge.peer = 0;
+    ge.lead = true;
+  }
+  ge.nloc = max(0, min(2 * ge.units, n - 2 * ge.uoff));
+  return ge;
+}
 
+template <bool NANMODE, class C, bool CL>
+__device__ __forceinline__ void fused_trip_body(const FusedArgs& a, const Smem<C>& sm, const Geo& ge) {
+  const long ld = a.ld;
+  const int units = ge.units;
+  const int ncf = (units + C::UC - 1) / C::UC;
   const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
   const int lane = threadIdx.x & 31, wig = tg >> 5;
-  const int wk = blockIdx.x * C::G + g;
+  const int wk = ge.wbase + g;
   if (wk >= a.nsplit) return;
+  const double* __restrict__ X = a.Xt + 2 * static_cast<size_t>(ge.uoff);  // this CTA's share of every feature
   const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
-  if (tg == 0) prime_ring<C>(a.Xt, ld, units, ncf, g, f0, f1, sm);
+  if (tg == 0) prime_ring<C>(X, ld, units, ncf, g, f0, f1, sm);
   const double inv_uu = 1.0 / *a.uu;
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+  const int sync_mode = a.sync_mode;
 
   double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
@@ -249,6 +312,8 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   int s = 0;
   uint32_t ph = 0;
   int flip = 0;
+  int xs = 0;
+  uint32_t xp = 0;
 
   for (int j = f0; j <= f1; ++j) {
     const bool load = j < f1;  // the last iteration only applies the last weight
@@ -259,7 +324,7 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     // previous feature's weight into the accumulators, then this feature's chunk c into the freed registers
     auto load_chunk = [&](const int c) {
       const bool have = load && c < ncf;
-      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+      const double2* __restrict__ xs_ = reinterpret_cast<const double2*>(sm.stage(g, s));
       if (have) {
         mbar_wait(&sm.full[g * C::S + s], ph);
         if (++s == C::S) { s = 0; ph ^= 1u; }
@@ -272,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
         acc[k].y = fma(wj, x[k].y, acc[k].y);
         double2 xv = make_double2(0.0, 0.0), uv = make_double2(0.0, 0.0);
         if (have && (whole || gi < units)) {
-          xv = xs[l];
+          xv = xs_[l];
           uv = u2[gi];
           if (NANMODE) xv = nan_to_zero(xv);  // masked sums: a missing entry contributes nothing (:848-852, :867-872)
         }
@@ -293,7 +358,7 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     // issuing chunk c+1's shared-memory loads before consuming chunk c changed nothing: profiles/r1_notes.md)
     auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xt, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode), X, ld, units, ncf, g, s_use, j, c, f1, lane, sm, sync_mode);
       if (++s_use == C::S) s_use = 0;
     };
 #pragma unroll
@@ -305,8 +370,9 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
     double one[1] = {(numa + numb) + (numc + numd)};
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
+    if (CL) one[0] = pair_sum<C>(one[0], g, tg, ge.peer, xs, xp, sm);
     wj = one[0] * rd;
-    if (tg == 0) {
+    if (tg == 0 && ge.lead) {
       a.w[j] = wj;
       if (a.gdef) a.gdef[j] = one[0];  // x_j . u (numerator only): seeds the running x_j . u0 of the recurrence deflation
     }
@@ -314,13 +380,27 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   }
 
   // partial block scores of this split (the layout xw_kernel writes)
-  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt) + ge.uoff;
 #pragma unroll
   for (int k = 0; k < C::EPT; ++k) {
     const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
     if (gi < units) tn[gi] = acc[k];
   }
-  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+  if (tg == 0 && ge.lead) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
+template <bool NANMODE, class C, bool CL>
+__global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
+  if (a.done && *a.done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Geo ge = make_geo<C, CL>(a.ld, a.n);
+  const Smem<C> sm(smem_raw, 2 * ge.units, 1);  // u (this CTA's share)
+  init_sync<C>(sm);
+  for (int i = threadIdx.x; i < 2 * ge.units; i += blockDim.x) sm.vec0[i] = i < ge.nloc ? a.u[2 * ge.uoff + i] : 0.0;
+  __syncthreads();
+  if (CL) cluster_sync_all();  // the peer's exchange barriers are initialised before anything is sent to them
+  fused_trip_body<NANMODE, C, CL>(a, sm, ge);
+  if (CL) cluster_sync_all();  // no CTA exits while its peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,32 +408,25 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
 // feature j-1 rides on the load phase of feature j.  NaN mode: NaN entries take part as zeros and are written
 // back as NaN (:969 keeps them); loadings and next weights use the masked reciprocal denominators rden / rden2.
 // ------------------------------------------------------------------------------------------
-template <bool NANMODE, class C>
-__global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+template <bool NANMODE, class C, bool CL>
+__device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Smem<C>& sm, const Geo& ge) {
   const long ld = a.ld;
-  const int units = static_cast<int>(ld >> 1);
+  const int units = ge.units;
   const int ncf = (units + C::UC - 1) / C::UC;
-  const Smem<C> sm(smem_raw, ld, 2);  // ts | u0
-  init_sync<C>(sm);
   const bool next = a.u != nullptr;
-  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
-    sm.vec0[i] = i < a.n ? a.ts[i] : 0.0;
-    sm.vec1[i] = (next && i < a.n) ? a.u[i] : 0.0;
-  }
-  __syncthreads();
-
   const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
   const int lane = threadIdx.x & 31, wig = tg >> 5;
-  const int wk = blockIdx.x * C::G + g;
+  const int wk = ge.wbase + g;
   if (wk >= a.nsplit) return;
+  double* __restrict__ X = a.Xw + 2 * static_cast<size_t>(ge.uoff);  // this CTA's share of every feature
   const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
-  if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
+  if (tg == 0) prime_ring<C>(X, ld, units, ncf, g, f0, f1, sm);
   const double inv_uu = next ? 1.0 / *a.uu : 1.0;
   const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec1);
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int sync_mode = a.sync_mode;
 
   double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
@@ -362,6 +435,8 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   int s = 0;
   uint32_t ph = 0;
   int flip = 0;
+  int xs = 0;
+  uint32_t xp = 0;
 
   for (int j = f0; j <= f1; ++j) {
     const bool load = j < f1;
@@ -373,7 +448,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 
     auto load_chunk = [&](const int c) {
       const bool have = load && c < ncf;
-      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
+      const double2* __restrict__ xs_ = reinterpret_cast<const double2*>(sm.stage(g, s));
       if (have) {
         mbar_wait(&sm.full[g * C::S + s], ph);
         if (++s == C::S) { s = 0; ph ^= 1u; }
@@ -386,7 +461,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
         acc[k].y = fma(wj, x[k].y, acc[k].y);
         double2 xv = make_double2(0.0, 0.0), tv = make_double2(0.0, 0.0);
         if (have && (whole || gi < units)) {
-          xv = xs[l];
+          xv = xs_[l];
           tv = ts2[gi];
           if (NANMODE) {
             if (isnan(xv.x)) { xv.x = 0.0; mx |= 1u << k; }
@@ -405,7 +480,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
     };
     auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm), a.Xw, ld, units, ncf, g, s_use, j, c, f1, lane, sm);
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode), X, ld, units, ncf, g, s_use, j, c, f1, lane, sm, sync_mode);
       if (++s_use == C::S) s_use = 0;
     };
 #pragma unroll
@@ -417,8 +492,9 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
     double one[1] = {(pa + pb) + (pc + pd)};
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
+    if (CL) one[0] = pair_sum<C>(one[0], g, tg, ge.peer, xs, xp, sm);
     const double pj = one[0] * rdp;
-    double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j) * ld);
+    double2* __restrict__ xg = reinterpret_cast<double2*>(X + static_cast<size_t>(j) * ld);
     double wa = 0.0, wb = 0.0, wc = 0.0, wd = 0.0;
 #pragma unroll
     for (int k = 0; k < C::EPT; ++k) {
@@ -453,23 +529,41 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
       double two[1] = {(wa + wb) + (wc + wd)};
       worker_sum<1, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
       flip ^= 1;
+      if (CL) two[0] = pair_sum<C>(two[0], g, tg, ge.peer, xs, xp, sm);
       wj = two[0] * rdw;
       normsq = fma(wj, wj, normsq);
     }
-    if (tg == 0) {
+    if (tg == 0 && ge.lead) {
       a.P_k[j] = pj;
       a.pss[j] = pj * pj;
       if (next) a.w[j] = wj;
     }
   }
   if (!next) return;
-  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt) + ge.uoff;
 #pragma unroll
   for (int k = 0; k < C::EPT; ++k) {
     const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
     if (gi < units) tn[gi] = acc[k];
   }
-  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+  if (tg == 0 && ge.lead) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
+template <bool NANMODE, class C, bool CL>
+__global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Geo ge = make_geo<C, CL>(a.ld, a.n);
+  const Smem<C> sm(smem_raw, 2 * ge.units, 2);  // ts | u0 (this CTA's share)
+  init_sync<C>(sm);
+  const bool next = a.u != nullptr;
+  for (int i = threadIdx.x; i < 2 * ge.units; i += blockDim.x) {
+    sm.vec0[i] = i < ge.nloc ? a.ts[2 * ge.uoff + i] : 0.0;
+    sm.vec1[i] = (next && i < ge.nloc) ? a.u[2 * ge.uoff + i] : 0.0;
+  }
+  __syncthreads();
+  if (CL) cluster_sync_all();
+  fused_deflate_body<NANMODE, C, CL>(a, sm, ge);
+  if (CL) cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -574,7 +668,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs 
         }
       }
       if (have) {
-        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm), a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm);
+        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm, a.sync_mode), a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm, a.sync_mode);
         if (++s == C::S) { s = 0; ph ^= 1u; }
       }
     }
@@ -609,68 +703,177 @@ __global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs 
   if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
 }
 
-// Configurations by feature length (units = ld/2 16-byte units per feature <= TG*EPTC*CPF).  Measured (profiles/r1_notes.md):
-// every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as the ring allows:
-// the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
-using CfgA = Cfg<512, 5, 2, 3>;   // ld <= 10240: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
-using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with two resident n-vectors (deflate: ts and u0): only 64 KB of ring left
-using CfgB = Cfg<256, 5, 2, 3>;   // ld <= 5120: two workers, 20 KB chunks
-using CfgC = Cfg<128, 5, 2, 4>;   // ld <= 2560: four workers, 10 KB chunks
-using CfgD = Cfg<64, 10, 1, 2>;   // ld <= 1280: eight workers, one chunk per feature
+// Configurations by feature length (units = 16-byte units per feature handled by ONE CTA <= TG*EPTC*CPF).  Measured
+// (profiles/r1_notes.md): every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as
+// the ring allows: the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
+using CfgA = Cfg<512, 5, 2, 3>;   // <= 5120 units: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
+using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with two resident vectors (deflate: ts and u0): only 64 KB of ring left
+using CfgB = Cfg<256, 5, 2, 3>;   // <= 2560 units: two workers, 20 KB chunks
+using CfgC = Cfg<128, 5, 2, 4>;   // <= 1280 units: four workers, 10 KB chunks
+using CfgD = Cfg<64, 10, 1, 2>;   // <= 640 units: eight workers, one chunk per feature
 
-template <bool NANMODE, class C>
-int launch_trip(const FusedArgs& a, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes<C>(a.ld, 1);
-  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
-  cudaFuncSetAttribute(fused_trip_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  const int grid = (a.nsplit + C::G - 1) / C::G;
-  fused_trip_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
-  return MBPLS_OK;
+// MBPLS_FUSED_CLUSTER=0 keeps features of up to 10,240 samples on the single-CTA deflation kernel (A/B measurements);
+// MBPLS_FUSED_SYNC=1 selects the acq_rel stage counter + proxy fence (FusedArgs::sync_mode)
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+bool cluster_enabled() {
+  static int v = -1;
+  if (v < 0) v = env_int("MBPLS_FUSED_CLUSTER", 1) != 0;
+  return v != 0;
+}
+int default_sync_mode() {
+  static int v = -1;
+  if (v < 0) v = env_int("MBPLS_FUSED_SYNC", 0) != 0;
+  return v;
 }
 
-template <bool NANMODE, class C>
-int launch_deflate(const FusedArgs& a, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes<C>(a.ld, 2);
-  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
-  const int grid = (a.nsplit + C::G - 1) / C::G;
-  cudaFuncSetAttribute(fused_deflate_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  fused_deflate_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
-  return MBPLS_OK;
+template <class K>
+int launch_fused(K kernel, const FusedArgs& a, int workers_per_cta, size_t smem, bool cluster, cudaStream_t st) {
+  if (smem > static_cast<size_t>(smem_optin())) return MBPLS_ERR_SIZE;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const int groups = (a.nsplit + workers_per_cta - 1) / workers_per_cta;  // CTAs, or CTA pairs
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster ? 2 * groups : groups), 1, 1);
+  cfg.blockDim = dim3(512, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+  return e == cudaSuccess ? MBPLS_OK : MBPLS_CUDA_ERR(e);
+}
+
+// CTA pairs of a cluster kernel that can be resident at once (the one-pass kernels are persistent: one wave only)
+template <class K>
+int max_active_pairs(K kernel, size_t smem) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(num_sms() / 2 * 2), 1, 1);
+  cfg.blockDim = dim3(512, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// Kernel plan for a leading dimension.  trip / deflate: configuration letter, cluster flag; workers: splits the split table
+// should hold (= persistent workers of one wave).  A feature of up to 10,240 samples keeps the single-CTA trip kernel (its ring
+// is already 120 KB) but deflates through CTA pairs (ts and u0 halved per CTA: 120 KB of ring instead of 64 KB); features of up
+// to 20,480 samples run both kernels on CTA pairs.
+struct Plan {
+  int trip = 0, deflate = 0;  // 0: unsupported; 1..4 = CfgA..CfgD per CTA; 5 = CfgA4
+  bool trip_cl = false, deflate_cl = false;
+  int workers = 0;
+};
+
+Plan plan_of(long ld) {
+  Plan pl;
+  if (ld < 16 || (ld % 16) != 0) return pl;
+  const long units = ld >> 1;
+  const int sms = num_sms();
+  if (units <= 640) { pl.trip = pl.deflate = 4; pl.workers = sms * CfgD::G; return pl; }
+  if (units <= 1280) { pl.trip = pl.deflate = 3; pl.workers = sms * CfgC::G; return pl; }
+  if (units <= 2560) { pl.trip = pl.deflate = 2; pl.workers = sms * CfgB::G; return pl; }
+  static int pairs_b = -1, pairs_a = -1, pairs_a4 = -1;  // resident CTA pairs of the three cluster kernels (device 0's answer is reused)
+  if (units <= 5120) {
+    pl.trip = 1;
+    pl.deflate = 5;
+    pl.workers = sms * CfgA::G;
+    if (cluster_enabled()) {
+      if (pairs_b < 0) pairs_b = max_active_pairs(fused_deflate_kernel<false, CfgB, true>, fused_smem_bytes<CfgB>(ld >> 1, 2));
+      if (pairs_b * CfgB::G >= pl.workers * 9 / 10) {  // (almost) every SM gets a CTA: worth it
+        pl.deflate = 2;
+        pl.deflate_cl = true;
+        pl.workers = min(pl.workers, pairs_b * CfgB::G);
+      }
+    }
+    return pl;
+  }
+  if (units <= 10240 && cluster_enabled()) {
+    if (pairs_a < 0) pairs_a = max_active_pairs(fused_trip_kernel<false, CfgA, true>, fused_smem_bytes<CfgA>(ld >> 1, 1));
+    if (pairs_a4 < 0) pairs_a4 = max_active_pairs(fused_deflate_kernel<false, CfgA4, true>, fused_smem_bytes<CfgA4>(ld >> 1, 2));
+    const int pairs = min(pairs_a, pairs_a4);
+    if (pairs > 0) {
+      pl.trip = 1;
+      pl.deflate = 5;
+      pl.trip_cl = pl.deflate_cl = true;
+      pl.workers = pairs * CfgA::G;
+    }
+  }
+  return pl;
+}
+
+template <bool NANMODE, bool CL>
+int dispatch_trip(int cfg, const FusedArgs& a, cudaStream_t st) {
+  const long vlen = CL ? a.ld >> 1 : a.ld;
+  switch (cfg) {
+    case 1: return launch_fused(fused_trip_kernel<NANMODE, CfgA, CL>, a, CfgA::G, fused_smem_bytes<CfgA>(vlen, 1), CL, st);
+    case 2: return launch_fused(fused_trip_kernel<NANMODE, CfgB, CL>, a, CfgB::G, fused_smem_bytes<CfgB>(vlen, 1), CL, st);
+    case 3: return launch_fused(fused_trip_kernel<NANMODE, CfgC, false>, a, CfgC::G, fused_smem_bytes<CfgC>(a.ld, 1), false, st);
+    case 4: return launch_fused(fused_trip_kernel<NANMODE, CfgD, false>, a, CfgD::G, fused_smem_bytes<CfgD>(a.ld, 1), false, st);
+    default: return MBPLS_ERR_SIZE;
+  }
+}
+
+template <bool NANMODE, bool CL>
+int dispatch_deflate(int cfg, const FusedArgs& a, cudaStream_t st) {
+  const long vlen = CL ? a.ld >> 1 : a.ld;
+  switch (cfg) {
+    case 5: return launch_fused(fused_deflate_kernel<NANMODE, CfgA4, CL>, a, CfgA4::G, fused_smem_bytes<CfgA4>(vlen, 2), CL, st);
+    case 2: return launch_fused(fused_deflate_kernel<NANMODE, CfgB, CL>, a, CfgB::G, fused_smem_bytes<CfgB>(vlen, 2), CL, st);
+    case 3: return launch_fused(fused_deflate_kernel<NANMODE, CfgC, false>, a, CfgC::G, fused_smem_bytes<CfgC>(a.ld, 2), false, st);
+    case 4: return launch_fused(fused_deflate_kernel<NANMODE, CfgD, false>, a, CfgD::G, fused_smem_bytes<CfgD>(a.ld, 2), false, st);
+    default: return MBPLS_ERR_SIZE;
+  }
 }
 
 template <bool NANMODE, class C>
 int launch_deflate3(const FusedArgs& a, cudaStream_t st) {
   const size_t smem = fused_smem_bytes<C>(a.ld, 1);
-  if (smem > static_cast<size_t>(smem_optin()) || (a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
-  const int grid = (a.nsplit + C::G - 1) / C::G;
-  cudaFuncSetAttribute(fused_deflate3_kernel<NANMODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  fused_deflate3_kernel<NANMODE, C><<<grid, 512, smem, st>>>(a);
-  return MBPLS_OK;
-}
-
-int config_of(long ld) {  // 0: unsupported
-  if (ld < 16 || (ld % 16) != 0) return 0;
-  const long units = ld >> 1;
-  if (units <= 640) return 4;
-  if (units <= 1280) return 3;
-  if (units <= 2560) return 2;
-  if (units <= 5120) return 1;
-  return 0;
+  if ((a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
+  return launch_fused(fused_deflate3_kernel<NANMODE, C>, a, C::G, smem, false, st);
 }
 
 }  // namespace
 
 extern "C" {
 
-/* workers (splits) per CTA of the one-pass kernels for this leading dimension; 0 = feature too long */
-int mbpls_fused_workers_per_cta(long ld) {
-  switch (config_of(ld)) {
-    case 1: return CfgA::G;
-    case 2: return CfgB::G;
-    case 3: return CfgC::G;
-    case 4: return CfgD::G;
-    default: return 0;
-  }
+/* persistent workers of the one-pass kernels per PAIR of SMs for this leading dimension (pure function of ld, no device
+ * needed): 16 / 8 / 4 / 2 for features of up to 1280 / 2560 / 5120 / 10240 samples, 1 up to 20480 (a feature is then split
+ * over the CTA pair of a cluster), 0 = too long: use the two-pass kernels */
+int mbpls_fused_workers_per_sm_pair(long ld) {
+  if (ld < 16 || (ld % 16) != 0) return 0;
+  const long units = ld >> 1;
+  return units <= 640 ? 16 : units <= 1280 ? 8 : units <= 2560 ? 4 : units <= 5120 ? 2 : units <= 10240 ? 1 : 0;
+}
+
+/* splits (persistent workers of one wave) to size the split table to on the current device; 0 = feature too long */
+int mbpls_fused_total_workers(long ld) { return plan_of(ld).workers; }
+
+/* 1 if the deflation pass for this leading dimension runs on CTA pairs (thread-block clusters), else 0 */
+int mbpls_fused_uses_clusters(long ld) {
+  const Plan pl = plan_of(ld);
+  return (pl.trip_cl ? 1 : 0) | (pl.deflate_cl ? 2 : 0);
 }
 
 int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
@@ -679,19 +882,13 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
   if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || ld < n || ldt < ld || B < 1)
     return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
+  const Plan pl = plan_of(ld);
+  if (!pl.trip || nsplit > pl.workers) return MBPLS_ERR_SIZE;
   FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, nullptr, nullptr, dots_out, split_f0, split_f1, split_block, nsplit, B,
-              w, norm_part, Tnum, ldt, nullptr, nullptr, done};
+              w, norm_part, Tnum, ldt, nullptr, nullptr, done, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = MBPLS_ERR_SIZE;
-  switch (config_of(ld)) {
-    case 1: rc = rden ? launch_trip<true, CfgA>(a, st) : launch_trip<false, CfgA>(a, st); break;
-    case 2: rc = rden ? launch_trip<true, CfgB>(a, st) : launch_trip<false, CfgB>(a, st); break;
-    case 3: rc = rden ? launch_trip<true, CfgC>(a, st) : launch_trip<false, CfgC>(a, st); break;
-    case 4: rc = rden ? launch_trip<true, CfgD>(a, st) : launch_trip<false, CfgD>(a, st); break;
-    default: break;
-  }
-  if (rc != MBPLS_OK) return rc;
-  MBPLS_RETURN_LAST();
+  if (pl.trip_cl) return rden ? dispatch_trip<true, true>(pl.trip, a, st) : dispatch_trip<false, true>(pl.trip, a, st);
+  return rden ? dispatch_trip<true, false>(pl.trip, a, st) : dispatch_trip<false, false>(pl.trip, a, st);
 }
 
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
@@ -701,19 +898,13 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
   if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
   if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && !rden_u0))) return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
+  const Plan pl = plan_of(ld);
+  if (!pl.deflate || nsplit > pl.workers) return MBPLS_ERR_SIZE;
   FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, nullptr, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
-              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr};
+              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = MBPLS_ERR_SIZE;
-  switch (config_of(ld)) {
-    case 1: rc = rden_ts ? launch_deflate<true, CfgA4>(a, st) : launch_deflate<false, CfgA4>(a, st); break;
-    case 2: rc = rden_ts ? launch_deflate<true, CfgB>(a, st) : launch_deflate<false, CfgB>(a, st); break;
-    case 3: rc = rden_ts ? launch_deflate<true, CfgC>(a, st) : launch_deflate<false, CfgC>(a, st); break;
-    case 4: rc = rden_ts ? launch_deflate<true, CfgD>(a, st) : launch_deflate<false, CfgD>(a, st); break;
-    default: break;
-  }
-  if (rc != MBPLS_OK) return rc;
-  MBPLS_RETURN_LAST();
+  if (pl.deflate_cl) return rden_ts ? dispatch_deflate<true, true>(pl.deflate, a, st) : dispatch_deflate<false, true>(pl.deflate, a, st);
+  return rden_ts ? dispatch_deflate<true, false>(pl.deflate, a, st) : dispatch_deflate<false, false>(pl.deflate, a, st);
 }
 
 int mbpls_fused_deflate_rec_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0u0,
@@ -724,19 +915,18 @@ int mbpls_fused_deflate_rec_f64(double* Xt, long ld, int n, const double* ts, co
   if (gdef && (!u0u0 || !tsu0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && (!rden_u0 || !tsu0_masked))))
     return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
+  const Plan pl = plan_of(ld);
+  if (!pl.trip || pl.trip_cl || nsplit > pl.workers) return MBPLS_ERR_SIZE;  // single-CTA configurations only
   FusedArgs a{nullptr, Xt, ld, n, nullptr, u0u0, ts, rden_ts, rden_u0, tsu0_masked, tsu0, gdef, split_f0, split_f1, split_block, nsplit, B,
-              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr};
+              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = MBPLS_ERR_SIZE;
-  switch (config_of(ld)) {
-    case 1: rc = rden_ts ? launch_deflate3<true, CfgA>(a, st) : launch_deflate3<false, CfgA>(a, st); break;
-    case 2: rc = rden_ts ? launch_deflate3<true, CfgB>(a, st) : launch_deflate3<false, CfgB>(a, st); break;
-    case 3: rc = rden_ts ? launch_deflate3<true, CfgC>(a, st) : launch_deflate3<false, CfgC>(a, st); break;
-    case 4: rc = rden_ts ? launch_deflate3<true, CfgD>(a, st) : launch_deflate3<false, CfgD>(a, st); break;
-    default: break;
+  switch (pl.trip) {
+    case 1: return rden_ts ? launch_deflate3<true, CfgA>(a, st) : launch_deflate3<false, CfgA>(a, st);
+    case 2: return rden_ts ? launch_deflate3<true, CfgB>(a, st) : launch_deflate3<false, CfgB>(a, st);
+    case 3: return rden_ts ? launch_deflate3<true, CfgC>(a, st) : launch_deflate3<false, CfgC>(a, st);
+    case 4: return rden_ts ? launch_deflate3<true, CfgD>(a, st) : launch_deflate3<false, CfgD>(a, st);
+    default: return MBPLS_ERR_SIZE;
   }
-  if (rc != MBPLS_OK) return rc;
-  MBPLS_RETURN_LAST();
 }
 
 }  // extern "C"

@@ -397,17 +397,18 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
 
     # one-pass kernels (csrc/fused.cu): a trip reads X once; they need the score accumulators of a whole feature in
-    # registers, i.e. ld <= 10240.  Their "workers" own one split each: size the split table to one persistent CTA per SM.
+    # registers, i.e. ld <= 20480 (beyond 10240 a feature is split over the CTA pair of a cluster).  Their "workers" own one
+    # split each: the library says how many workers one wave of persistent CTAs holds on this device.
     # NaN-masked data runs through the same kernels with NaN read as zero; every masked denominator is derived from the
     # NaN bit matrix (csrc/nanmask.cu), which needs the per-feature NaN counts of the census (col_nan).
     want_op = one_pass is not False and (not nan or col_nan is not None)
-    wpc = call("mbpls_fused_workers_per_cta", ld) if (want_op and p > 0) else 0
-    use_op = wpc > 0
+    nworkers = call("mbpls_fused_total_workers", ld) if (want_op and p > 0) else 0
+    use_op = nworkers > 0
     if one_pass is True and not use_op and p > 0:
-        raise ValueError("one_pass=True needs a leading dimension of at most 10240 samples (and, for NaN data, the census)")
+        raise ValueError("one_pass=True needs a leading dimension of at most 20480 samples (and, for NaN data, the census)")
     use_opd = use_op and one_pass_deflate is not False and deflate_mode == 0
     if use_op:
-        of0, of1, obso = make_splits(block_off, 1, sm_count(dev), ctas_per_sm=wpc, min_feats=16)
+        of0, of1, obso = make_splits(block_off, 1, nworkers, ctas_per_sm=1, min_feats=16)
         nsplit_o = len(of0)
         oblk = [b for b in range(B) for _ in range(obso[b + 1] - obso[b])]
         osf0, osf1, osbso, osblk = _i32(of0, dev), _i32(of1, dev), _i32(obso, dev), _i32(oblk, dev)
@@ -436,7 +437,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
     bits = rden_u = rden_ts = rden_u0 = tsu0_m = tsu0 = None
     # recurrence deflation (fused_deflate3_kernel): x_j . u0 is carried per feature instead of keeping u0 in shared memory
-    use_rec = use_opd and fuse_next_xtu and (deflate_rec is True or (deflate_rec is None and _DEFLATE_REC_DEFAULT))
+    use_rec = use_opd and fuse_next_xtu and (deflate_rec is True or (deflate_rec is None and _DEFLATE_REC_DEFAULT)) \
+        and not (call("mbpls_fused_uses_clusters", ld) & 1)
     gdef = buf(p) if use_rec else None
     if use_rec and tsu0 is None:
         tsu0 = buf(1)

@@ -11,11 +11,15 @@ warnings.simplefilter("ignore")
 dev = torch.device("cuda:0")
 args = sys.argv[1:]
 scale = float(args[0]) if args and args[0].replace(".", "").isdigit() else 1.0
+only = [a[2:] for a in args if a.startswith("v=")]  # v=<variant name>: run only these variants
+args = [a for a in args if not a.startswith("v=")]
 which = set(a for a in args if not a.replace(".", "").isdigit()) or {"dense", "nan", "c3"}
 
 VARIANTS = (("two-pass", dict(one_pass=False)), ("one-pass trip", dict(one_pass=True, one_pass_deflate=False)),
             ("one-pass trip+deflate", dict(one_pass=True, deflate_rec=False)),
             ("one-pass trip+deflate(rec)", dict(one_pass=True, deflate_rec=True)))
+if only:
+    VARIANTS = tuple(v for v in VARIANTS if v[0] in only)
 MULT = {"colden": 1.0 / 64, "rowden": 1.0 / 64, "trip": 1.0, "xtu": 1.0, "xw": 1.0, "deflate": 2.0, "loadings": 1.0, "standardize": 2.0}
 
 
@@ -65,6 +69,9 @@ if "c3nan" in which:
     S8 = [int(s * scale) for s in (20000, 35000, 60000, 95000, 140000, 180000, 220000, 450000)]
     run("C3 8 blocks n=2000 q=1 10% NaN", 2000, S8, 20, 1, 0.10)
     run("n=4000 p=500k q=1 10% NaN", 4000, [int(500_000 * scale)], 10, 1, 0.10)
+if "n20k" in which:  # features split over CTA pairs for both passes
+    run("n=20000 p=500k q=1", 20_000, [int(500_000 * scale)], 10, 1, 0.0)
+    run("n=16000 p=500k q=1", 16_000, [int(500_000 * scale)], 10, 1, 0.0)
 if "mid" in which:
     run("n=4000 p=500k q=1", 4000, [int(500_000 * scale)], 10, 1, 0.0)
     run("n=1000 p=2M q=1", 1000, [int(2_000_000 * scale)], 10, 1, 0.0)

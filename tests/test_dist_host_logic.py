@@ -65,7 +65,7 @@ def test_split_tables_cover_every_feature_inside_one_block():
 def test_one_pass_configuration_tables():
     """Pure host entry points of the C ABI: workers per CTA by feature length, NaN bit-matrix row length."""
     from mbpls_b200._cabi import call
-    assert [call("mbpls_fused_workers_per_cta", ld) for ld in (16, 1280, 1296, 2560, 2576, 5120, 5136, 10240, 10256)] == \
-        [8, 8, 4, 4, 2, 2, 1, 1, 0]
-    assert call("mbpls_fused_workers_per_cta", 1000) == 0  # leading dimensions are multiples of 16
+    lds = (16, 1280, 1296, 2560, 2576, 5120, 5136, 10240, 10256, 20480, 20496)
+    assert [call("mbpls_fused_workers_per_sm_pair", ld) for ld in lds] == [16, 16, 8, 8, 4, 4, 2, 2, 1, 1, 0]
+    assert call("mbpls_fused_workers_per_sm_pair", 1000) == 0  # leading dimensions are multiples of 16
     assert [call("mbpls_nan_bitmask_ldw", n) for n in (1, 32, 33, 128, 129, 10_000)] == [4, 4, 4, 4, 8, 316]

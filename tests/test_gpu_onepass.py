@@ -1,7 +1,7 @@
 """GPU: the one-pass NIPALS kernels (csrc/fused.cu: one read of X per trip; loadings + deflation + the next
 component's first trip in one read + write) against the live numpy oracle, for every worker configuration
-(feature lengths up to 640 / 1280 / 2560 / 5120 16-byte units), dense and NaN-masked, and against the two-pass
-kernels they replace."""
+(feature lengths up to 640 / 1280 / 2560 / 5120 16-byte units per CTA, and features split over the CTA pair of a
+thread-block cluster up to 20,480 samples), dense and NaN-masked, and against the two-pass kernels they replace."""
 import warnings
 
 import numpy as np
@@ -33,7 +33,9 @@ def _check(m, o, X, Y, kw, what):
 # n chosen so that ld = round_up(n, 16) lands in each configuration, including its upper edge and ragged tails
 @pytest.mark.parametrize("n,sizes", [(37, (21, 40)), (640, (90, 33)), (1277, (70, 50)), (1300, (64, 48, 9)),
                                      (2560, (80, 41)), (2570, (75, 30)), (5117, (60, 37)), (5200, (50, 45)),
-                                     (10000, (40, 56)), (10240, (33, 31))])
+                                     (10000, (40, 56)), (10240, (33, 31)),
+                                     # features split over the CTA pair of a cluster (both passes): 10,240 < n <= 20,480
+                                     (10250, (35, 22)), (15001, (21, 30)), (20480, (18, 25))])
 def test_one_pass_dense_matches_oracle(n, sizes):
     from oracle.cases import latent_blocks
     X, Y = latent_blocks(n, sizes, 2, 3, seed=n % 97)
@@ -42,7 +44,8 @@ def test_one_pass_dense_matches_oracle(n, sizes):
     _check(m, o, X, Y, kw, f"one-pass dense n={n}")
 
 
-@pytest.mark.parametrize("n,sizes", [(45, (30, 17)), (1000, (60, 35)), (2000, (48, 40)), (4000, (40, 33)), (9000, (24, 30))])
+@pytest.mark.parametrize("n,sizes", [(45, (30, 17)), (1000, (60, 35)), (2000, (48, 40)), (4000, (40, 33)), (9000, (24, 30)),
+                                     (13000, (16, 12))])
 def test_one_pass_nan_matches_oracle(n, sizes):
     from oracle.cases import latent_blocks
     X, Y = latent_blocks(n, sizes, 2, 2, seed=5 + n % 89, nan_frac=0.1)
@@ -53,6 +56,19 @@ def test_one_pass_nan_matches_oracle(n, sizes):
     for b in range(2):
         for a, r in zip(m.sparse_X_info_[b], o.sparse_X_info_[b]):
             assert np.array_equal(a, r)
+
+
+@pytest.mark.parametrize("n,nan_frac", [(6000, 0.0), (10000, 0.0), (10000, 0.07), (12000, 0.0)])
+def test_cluster_deflation_long_splits(n, nan_frac):
+    """Enough features that every worker pair of the cluster deflation kernel walks a long split (ring wrap-around,
+    both exchange slots reused many times); PLS1 so the trip count must be exactly 2 per component."""
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(n, (3100, 2900), 1, 3, seed=n % 71, nan_frac=nan_frac)
+    kw = dict(n_components=3, method="NIPALS", sparse_data=nan_frac > 0)
+    m, o = _pair(kw, X, Y.ravel(), one_pass=True)
+    _check(m, o, X, Y.ravel(), kw, f"cluster deflation n={n} nan={nan_frac}")
+    if nan_frac == 0:
+        assert list(m.n_iter_) == [2, 2, 2] == list(o.n_iter_)
 
 
 def test_one_pass_pls1_many_blocks_single_features():
@@ -111,7 +127,7 @@ def test_one_pass_is_reproducible_bitwise():
 def test_one_pass_rejects_long_features():
     from mbpls_b200 import MBPLS
     rng = np.random.default_rng(0)
-    X, Y = rng.standard_normal((10300, 6)), rng.standard_normal(10300)
+    X, Y = rng.standard_normal((20500, 6)), rng.standard_normal(20500)
     with pytest.raises(ValueError):
         MBPLS(n_components=1).set_runtime(one_pass=True).fit(X, Y)
     m = MBPLS(n_components=1).fit(X, Y)  # auto: falls back to the two-pass kernels
