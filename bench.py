@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass NIPALS kernels (X'u and X w as separate reads)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-p", type=int, default=0, help="features of the CPU sample (0: auto)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity gate (GPU fit vs numpy oracle on a column slice)")
+    ap.add_argument("--parity-features", type=int, default=1024, help="features per block of the dense parity slice (NaN slice: a quarter)")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--verbose", action="store_true")
     return ap.parse_args()
@@ -77,40 +79,72 @@ def fit_bytes(n, p, K, trips):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the numpy oracle port of mbpls/mbpls.py on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, p_sample, repeats=1):
+CPU_P_DENSE = 20_000        # dense CPU sample at n=10,000 x p=20,000 ...
+CPU_P_SECOND = 10_000       # ... and a second width to show the time is linear in p
+CPU_NAN_SHAPE = (2_000, 4_000)  # NaN-mode CPU sample (Python-loop-bound on the host)
+
+
+def _host_threads():
+    """All host cores for BLAS, whatever OMP_NUM_THREADS said at import (torchrun exports OMP_NUM_THREADS=1)."""
+    import threadpoolctl
+    return threadpoolctl.threadpool_limits(limits=os.cpu_count())
+
+
+def cpu_sample(args, p_sample, repeats=1, n=None, nan_frac=None):
+    """One bounded CPU fit of the benchmark's workload shape: the reference's own MBPLS (unmodified, through the
+    check_array shim of oracle/refshim.py) when /root/reference is mounted, else the numpy port (oracle/mbpls_oracle.py)."""
     import numpy as np
     import threadpoolctl
-    from oracle import OracleMBPLS
+    from oracle import OracleMBPLS, refshim
     from oracle.cases import latent_blocks
-    n, K = args.n, args.components
+    n = args.n if n is None else n
+    nan_frac = args.nan_frac if nan_frac is None else nan_frac
+    K = args.components
     frac = [s / sum(SIZES_FULL) for s in SIZES_FULL]
     sizes = [max(8, int(round(p_sample * f))) for f in frac]
-    X, Y = latent_blocks(n, sizes, args.q, K, seed=args.seed % 100000, noise=args.noise, decay=args.decay,
-                         nan_frac=args.nan_frac)
-    best, trips = None, None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
+    X, Y = latent_blocks(n, sizes, args.q, K, seed=args.seed % 100000, noise=args.noise, decay=args.decay, nan_frac=nan_frac)
+    use_ref = refshim.available()
+    times, trips = [], None
+    with _host_threads():
+        info = threadpoolctl.threadpool_info()
+        threads = max([i.get("num_threads", 1) for i in info] or [1])
+        for _ in range(repeats):
+            Xc, Yc = [x.copy() for x in X], Y.copy()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                if use_ref:
+                    m = refshim.load()(n_components=K, method='NIPALS', sparse_data=nan_frac > 0)
+                    t0 = time.perf_counter()
+                    m.fit(Xc, Yc)
+                    dt = time.perf_counter() - t0
+                    trips = trips or [2] * K if args.q == 1 else None  # the reference does not expose its trip counts
+                else:
+                    m = OracleMBPLS(n_components=K, method="NIPALS", sparse_data=nan_frac > 0, max_iter=args.max_iter)
+                    t0 = time.perf_counter()
+                    m.fit(Xc, Yc)
+                    dt = time.perf_counter() - t0
+                    trips = list(m.n_iter_)
+            times.append(dt)
+    if trips is None:  # PLS2 through the real reference: count the trips once with the (untimed) port
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            m = OracleMBPLS(n_components=K, method="NIPALS", sparse_data=args.nan_frac > 0,
-                            max_iter=args.max_iter).fit([x.copy() for x in X], Y.copy())
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        trips = list(m.n_iter_)
-    info = threadpoolctl.threadpool_info()
-    threads = max([i.get("num_threads", 1) for i in info] or [1])
+            trips = list(OracleMBPLS(n_components=K, method="NIPALS", sparse_data=nan_frac > 0, max_iter=args.max_iter)
+                         .fit([x.copy() for x in X], Y.copy()).n_iter_)
     p = sum(sizes)
-    return dict(seconds=best, gbs=fit_bytes(n, p, K, trips) / best / 1e9, trips=trips, cores=threads,
-                sample=f"oracle numpy/OpenBLAS port of mbpls.py NIPALS, n={n}, p={p} in 4 blocks, q={args.q}, K={K}, "
+    best = min(times)
+    what = "mbpls/mbpls.py of the reference (unmodified, check_array shim)" if use_ref else "oracle numpy/OpenBLAS port of mbpls.py"
+    return dict(seconds=best, mean_seconds=sum(times) / len(times), gbs=fit_bytes(n, p, K, trips) / best / 1e9, trips=trips,
+                cores=threads, kind="reference" if use_ref else "port", p=p, n=n,
+                sample=f"{what}, NIPALS, n={n}, p={p} in 4 blocks, q={args.q}, K={K}, nan_frac={nan_frac}, "
                        f"{threads} BLAS threads of {os.cpu_count()} cpus, best of {repeats}")
 
 
-def auto_cpu_p(args, budget_s):
-    """Pick the CPU sample width so one fit takes roughly `budget_s` (about 3 GB/s measured on 8-16 cores)."""
+def cpu_p_for_budget(args, budget_s):
+    """The CPU sample is p = 20,000 features unless one fit at ~8 GB/s would not fit `budget_s`."""
     if args.cpu_p:
         return args.cpu_p
-    per_feature = 16.0 * args.n * (1 + args.components + (2 if args.q == 1 else 40) * args.components) / 3e9
-    return int(max(400, min(40_000, budget_s / per_feature)))
+    per_feature = 16.0 * args.n * (1 + args.components + (2 if args.q == 1 else 40) * args.components) / 8e9
+    return int(max(1_000, min(CPU_P_DENSE, budget_s / per_feature)))
 
 
 def run_reference(args):
@@ -118,8 +152,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    budget = max(3.0, 150.0 / (steps + warm))
-    p_sample = auto_cpu_p(args, budget)
+    p_sample = cpu_p_for_budget(args, max(4.0, 170.0 / (steps + warm)))
     for _ in range(warm):
         cpu_sample(args, p_sample)
     times, res = [], None
@@ -127,17 +160,27 @@ def run_reference(args):
         res = cpu_sample(args, p_sample)
         times.append(res["seconds"])
     sec = sum(times) / len(times)
-    p = p_sample
     gbs = res["gbs"] * res["seconds"] / sec
+    # a second width: the fit time is linear in p (so GB/s at the sample width stands for the full width), and the NaN-mode
+    # sample that goes with variants.nan_10pct of the GPU arm
+    second = cpu_sample(args, max(500, p_sample // 2))
+    extra = {"linear_in_p": {str(res["p"]): {"seconds": min(times), "gbs": res["gbs"] * res["seconds"] / min(times)},
+                             str(second["p"]): {"seconds": second["seconds"], "gbs": second["gbs"]}}}
+    if args.nan_frac == 0 and not args.no_nan_variant:
+        nn, pp = min(CPU_NAN_SHAPE[0], args.n), min(CPU_NAN_SHAPE[1], p_sample)
+        nan = cpu_sample(args, pp, n=nn, nan_frac=0.10)
+        extra["nan_10pct"] = {"value": nan["gbs"], "unit": "GB/s", "seconds": nan["seconds"], "cores": nan["cores"], "kind": nan["kind"],
+                              "sample": nan["sample"]}
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, note=f"bounded CPU sample: p={p} features instead of {int(sum(SIZES_FULL) * args.scale)}"),
-        "trips_per_component": res["trips"],
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "config": workload_config(args, note=f"bounded CPU sample: p={res['p']} features instead of {int(sum(SIZES_FULL) * args.scale)} "
+                                             "(fit time is linear in p, see linear_in_p); GB/s is size-normalised"),
+        "trips_per_component": res["trips"], "best_of_steps_s": min(times),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, **extra,
     }
     print(json.dumps(line), flush=True)
 
@@ -152,6 +195,99 @@ def workload_config(args, note=None):
     if note:
         cfg["note"] = note
     return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# parity gate (SURVEY.md 8d "parity gate run with every benchmark"; mbpls/tests/test_mbpls.py:66-117 is the model)
+# ------------------------------------------------------------------------------------------------
+def _col_err(o, r):
+    """max over components of the relative error after sign alignment (columns are components)."""
+    import numpy as np
+    o, r = np.asarray(o, float), np.asarray(r, float)
+    if o.shape != r.shape:
+        return float("inf")
+    worst = 0.0
+    for k in range(r.shape[1]):
+        den = np.linalg.norm(r[:, k]) or 1.0
+        worst = max(worst, min(np.linalg.norm(o[:, k] - r[:, k]), np.linalg.norm(o[:, k] + r[:, k])) / den)
+    return float(worst)
+
+
+def parity_gate(args, dev, group, rank, world, nan_frac, feats_per_block):
+    """The SAME device-generated data the timed fits use -- the first `feats_per_block` features of each of the 4 blocks,
+    all n samples, same Y -- fitted (a) by the GPU path, feature-sharded over the ranks of this run exactly like the timed
+    fit, and (b) on rank 0 by the numpy oracle (oracle/mbpls_oracle.py, the restatement of mbpls/mbpls.py pinned to the
+    reference's golden vectors).  Reports the worst per-component relative error after sign alignment over
+    Ts_, T_, W_, P_, U_, V_ and of beta_ / A_ (no alignment), whether the NIPALS trip counts are equal, and (NaN variant)
+    whether the NaN census and the scalers' observed counts are equal."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mbpls_b200 import MBPLS, synth
+    from mbpls_b200 import engine as E
+    n, K, q = args.n, args.components, args.q
+    full = [int(s * args.scale) for s in SIZES_FULL]
+    starts = [sum(full[:b]) for b in range(len(full))]
+    sizes = [min(feats_per_block, s) for s in full]
+    ld = E.round_ld(n)
+    shard = E.ShardMap.build(sizes, rank, world)
+    Yd = synth.response(n, q, K, dev, args.seed, decay=args.decay)
+
+    def gen(dst, b, c0, c1):  # features [c0, c1) of the slice of block b == global features starts[b] + [c0, c1)
+        synth.fill_feature_major(dst, n, starts[b] + c0, starts[b] + c1, K, args.seed, noise=args.noise, decay=args.decay,
+                                 nan_frac=nan_frac)
+
+    Xl = torch.zeros((max(shard.p_local, 1), ld), dtype=torch.float64, device=dev)
+    for b, (c0, c1) in enumerate(shard.local_ranges):
+        if c1 > c0:
+            gen(Xl[shard.block_off[b]:shard.block_off[b + 1]], b, c0, c1)
+    local = [Xl[shard.block_off[b]:shard.block_off[b + 1], :n].t() for b in range(len(sizes))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = MBPLS(n_components=K, method="NIPALS", standardize=True, calc_all=True, sparse_data=nan_frac > 0, copy=True)
+        m.set_runtime(device=dev, group=group, materialize=True, global_sizes=sizes if world > 1 else None, max_iter=args.max_iter,
+                      one_pass=False if args.two_pass else None)
+        m.fit(local, Yd)
+    out = None
+    if rank == 0:
+        import threadpoolctl
+        from oracle import OracleMBPLS
+        host = []
+        for b, pb in enumerate(sizes):
+            t = torch.zeros((pb, ld), dtype=torch.float64, device=dev)
+            gen(t, b, 0, pb)
+            host.append(np.ascontiguousarray(t[:, :n].t().cpu().numpy()))
+            del t
+        Yh = Yd.cpu().numpy()
+        t0 = time.perf_counter()
+        with warnings.catch_warnings(), threadpoolctl.threadpool_limits(limits=os.cpu_count()):
+            warnings.simplefilter("ignore")
+            o = OracleMBPLS(n_components=K, method="NIPALS", sparse_data=nan_frac > 0, max_iter=args.max_iter).fit(
+                [x.copy() for x in host], Yh.copy())
+        oracle_s = time.perf_counter() - t0
+        errs = {"Ts_": _col_err(m.Ts_, o.Ts_), "U_": _col_err(m.U_, o.U_), "V_": _col_err(m.V_, o.V_),
+                "T_": max(_col_err(a, b_) for a, b_ in zip(m.T_, o.T_)), "W_": max(_col_err(a, b_) for a, b_ in zip(m.W_, o.W_)),
+                "P_": max(_col_err(a, b_) for a, b_ in zip(m.P_, o.P_)),
+                "beta_": float(np.linalg.norm(m.beta_ - o.beta_) / np.linalg.norm(o.beta_)),
+                "A_": float(np.linalg.norm(m.A_ - o.A_) / np.linalg.norm(o.A_))}
+        census_equal = None
+        if nan_frac > 0:
+            census_equal = all(np.array_equal(a, b_) for blk in range(len(sizes))
+                               for a, b_ in zip(m.sparse_X_info_[blk], o.sparse_X_info_[blk]))
+            census_equal = bool(census_equal and all(
+                np.array_equal(np.asarray(a.n_samples_seen_), np.asarray(b_.n_samples_seen_)) for a, b_ in zip(m.x_scalers_, o.x_scalers_)))
+        worst = max(errs.values())
+        out = {"max_rel_err": worst, "per_attribute": errs, "trips_equal": list(m.n_iter_) == list(o.n_iter_),
+               "trips_gpu": list(m.n_iter_), "trips_oracle": list(o.n_iter_), "census_equal": census_equal,
+               "tolerance": 1e-8, "ok": bool(worst <= 1e-8 and list(m.n_iter_) == list(o.n_iter_) and census_equal is not False),
+               "oracle_seconds": oracle_s,
+               "slice": f"first {sizes} features of the 4 blocks of the benchmark's device-generated data (global starts {starts}), "
+                        f"all n={n} samples, K={K}, q={q}, nan_frac={nan_frac}; GPU fit feature-sharded over {world} rank(s); "
+                        "oracle = oracle/mbpls_oracle.py (numpy restatement of mbpls/mbpls.py) on rank 0"}
+    del m, Xl
+    if world > 1:
+        dist.barrier(group=group)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,6 +492,20 @@ def run_ours(args):
                     "frac": kern[dominant]["gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes"], "per_kernel": kern}
 
+    # ---- parity gate: the timed configuration's own data (a column slice of it) through the GPU path and the oracle
+    parity = None
+    if not args.no_parity:
+        log("parity gate (dense)")
+        parity = {"dense" if args.nan_frac == 0 else "nan": parity_gate(args, dev, group, rank, world, args.nan_frac, args.parity_features)}
+        if args.nan_frac == 0 and not args.no_nan_variant:
+            log("parity gate (10 % NaN)")
+            parity["nan_10pct"] = parity_gate(args, dev, group, rank, world, 0.10, max(16, args.parity_features // 4))
+        if rank == 0:
+            parity["ok"] = all(v["ok"] for v in parity.values())
+            parity["max_rel_err"] = max(v["max_rel_err"] for k, v in parity.items() if isinstance(v, dict))
+            parity["trips_equal"] = all(v["trips_equal"] for k, v in parity.items() if isinstance(v, dict))
+        log("parity", parity)
+
     # ---- end to end through the public API with HOST buffers (pinned, row-major like the reference's inputs)
     e2e = None
     del model
@@ -410,11 +560,17 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        log("cpu baseline sample p", auto_cpu_p(args, 15.0))
-        r = cpu_sample(args, auto_cpu_p(args, 15.0))
+        p_cpu = cpu_p_for_budget(args, 30.0)
+        log("cpu baseline sample p", p_cpu)
+        r = cpu_sample(args, p_cpu)
         log("cpu baseline done", r["seconds"])
-        cpu = {"value": r["gbs"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+        cpu = {"value": r["gbs"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "seconds": r["seconds"], "trips_per_component": r["trips"]}
+        if "nan_10pct" in variants:
+            nn, pp = min(CPU_NAN_SHAPE[0], args.n), min(CPU_NAN_SHAPE[1], p_cpu)
+            rn = cpu_sample(args, pp, n=nn, nan_frac=0.10)
+            variants["nan_10pct"]["cpu_baseline"] = {"value": rn["gbs"], "unit": "GB/s", "cores": rn["cores"], "kind": rn["kind"],
+                                                     "sample": rn["sample"], "seconds": rn["seconds"]}
 
     if rank == 0:
         line = {
@@ -424,7 +580,7 @@ def run_ours(args):
             "config": workload_config(args), "trips_per_component": trips, "algorithmic_bytes_per_step": fit_bytes(n, p, K, trips),
             "frac_of_hbm_peak": value / (peak_gbs * world),
             "frac_of_hbm_peak_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9 / (peak_gbs * world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
+            "parity": parity, "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
             "passes_over_X_per_step": passes, "hbm_gbs_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9,
         }
         print(json.dumps(line), flush=True)
@@ -436,6 +592,11 @@ def main():
     global VERBOSE
     args = parse()
     VERBOSE = args.verbose
+    # torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline, the parity gate's oracle) run on rank 0 and
+    # should see the host's cores (numpy / torch are imported after this point; threadpoolctl raises the limit again at use)
+    if int(os.environ.get("RANK", "0")) == 0:
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(os.cpu_count() or 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -120,6 +120,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive and return the barrier state from BEFORE this arrival; mbar_pending_count(state) == 1 means this was the
+// last pending arrival, i.e. the phase is now complete
+__device__ __forceinline__ uint64_t mbar_arrive_state(uint64_t* bar) {
+  uint64_t st;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(bar)) : "memory");
+  return st;
+}
+__device__ __forceinline__ uint32_t mbar_pending_count(uint64_t state) {
+  uint32_t c;
+  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(c) : "l"(state));
+  return c;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

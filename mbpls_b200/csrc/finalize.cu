@@ -102,6 +102,7 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       x[k] = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j + k) * ld));
+      if (last_is_pad) x[k].y = 0.0;  // element n of an odd-length feature is not a sample (an adopted view may hold anything there)
       bad |= !isfinite(x[k].x) | !isfinite(x[k].y);
       if (mean) {  // StandardScaler.transform fused into the product (mbpls.py:1097,:1369): z = (x - mean) / scale
         const double m = __ldg(mean + j + k), sc = __ldg(scale + j + k);
@@ -125,6 +126,7 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
   }
   for (; j < f1; ++j) {
     double2 x = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j) * ld));
+    if (last_is_pad) x.y = 0.0;
     bad |= !isfinite(x.x) | !isfinite(x.y);
     if (mean) {
       const double m = __ldg(mean + j), sc = __ldg(scale + j);

@@ -179,11 +179,12 @@ __device__ __forceinline__ void issue_chunk(const double* __restrict__ X, long l
 }
 
 template <class C>
-__device__ __forceinline__ void init_sync(const Smem<C>& sm) {
+__device__ __forceinline__ void init_sync(const Smem<C>& sm, int sync_mode) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::G * C::S; ++i) {
       mbar_init(&sm.full[i], 1);
-      sm.cnt[2 * i] = 0;
+      if (sync_mode == 2) mbar_init(reinterpret_cast<uint64_t*>(&sm.cnt[2 * i]), C::NW);  // "empty": one arrival per warp
+      else sm.cnt[2 * i] = 0;
     }
     for (int i = 0; i < 2 * C::G; ++i) mbar_init(&sm.xbar[i], 1);
     fence_barrier_init();
@@ -201,30 +202,44 @@ __device__ __forceinline__ void prime_ring(const double* __restrict__ X, long ld
   }
 }
 
-// The calling warp is done reading stage (g, s).  Returns the number of warps that had said so before (lane 0 only).
-// Relaxed atomic: every shared-memory read of the stage feeds a dot-product FMA that precedes this call in program order,
-// and an instruction cannot issue before its operands have arrived, so the reads have completed when the counter moves.
+// The calling warp is done reading stage (g, s).  Returns (lane 0 only) whether it was the LAST warp of the worker to say so.
+// Three hand-off protocols (FusedArgs::sync_mode, MBPLS_FUSED_SYNC):
+//  0  relaxed shared-memory counter.  Every shared-memory read of the stage feeds a dot-product FMA that precedes this call in
+//     program order, and an instruction cannot issue before its operands have arrived, so the reads have completed when the
+//     counter moves -- an argument about the hardware, not the PTX memory model (racecheck reports the refill as a WAR hazard);
+//  1  acq_rel counter + generic->async proxy fence in front of the refill: ordered by the memory model, invisible to racecheck;
+//  2  an "empty" mbarrier per stage with one pending arrival per warp: mbarrier.arrive (release) returns the state before the
+//     arrival, pending_count == 1 identifies the last arriver, whose test_wait (acquire) on the completed phase orders every
+//     warp's reads before the bulk copy it then issues -- the consumer-release / producer-acquire of a TMA pipeline, with the
+//     producer role falling to whichever warp arrives last.
 template <class C>
-__device__ __forceinline__ unsigned arrive_stage(int g, int s, int lane, const Smem<C>& sm, int sync_mode) {
+__device__ __forceinline__ bool arrive_stage(int g, int s, int lane, const Smem<C>& sm, int sync_mode, uint32_t parity) {
   __syncwarp();
-  if (lane != 0) return 0u;
-  return sync_mode ? atom_inc_smem_acqrel(&sm.cnt[2 * (g * C::S + s)]) : atom_inc_smem(&sm.cnt[2 * (g * C::S + s)]);
+  if (lane != 0) return false;
+  unsigned* c = &sm.cnt[2 * (g * C::S + s)];
+  if (sync_mode == 2) {
+    uint64_t* eb = reinterpret_cast<uint64_t*>(c);
+    if (mbar_pending_count(mbar_arrive_state(eb)) != 1u) return false;
+    while (!mbar_test_wait(eb, parity)) {
+    }
+    return true;
+  }
+  const unsigned old = sync_mode ? atom_inc_smem_acqrel(c) : atom_inc_smem(c);
+  if (old != C::NW - 1) return false;
+  *reinterpret_cast<volatile unsigned*>(c) = 0;
+  if (sync_mode) fence_proxy_async_smem();
+  return true;
 }
 
 // The last warp of the worker to arrive on a stage (which held chunk c of feature j) refills it with the chunk S
-// positions further down the worker's stream, immediately (a free stage is lost ring depth).  -DMBPLS_FUSED_PROXY_FENCE adds
-// an explicit generic->async proxy fence in front of the bulk copy.
+// positions further down the worker's stream, immediately (a free stage is lost ring depth).
 template <class C>
-__device__ __forceinline__ void refill_if_last(unsigned old, const double* __restrict__ X, long ld, int units, int ncf, int g, int s,
-                                               int j, int c, int f1, int lane, const Smem<C>& sm, int sync_mode) {
-  if (lane == 0 && old == C::NW - 1) {
-    *reinterpret_cast<volatile unsigned*>(&sm.cnt[2 * (g * C::S + s)]) = 0;
+__device__ __forceinline__ void refill_if_last(bool last, const double* __restrict__ X, long ld, int units, int ncf, int g, int s,
+                                               int j, int c, int f1, const Smem<C>& sm) {
+  if (last) {
     int c2 = c + C::S, f2 = j;
     while (c2 >= ncf) { c2 -= ncf; ++f2; }
-    if (f2 < f1) {
-      if (sync_mode) fence_proxy_async_smem();
-      issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
-    }
+    if (f2 < f1) issue_chunk<C>(X, ld, units, g, s, f2, c2, sm);
   }
 }
 
@@ -320,6 +335,7 @@ __device__ __forceinline__ void fused_trip_body(const FusedArgs& a, const Smem<C
     const double rd = (NANMODE && load) ? a.rden[j] : inv_uu;  // 1 / (masked) u'u of this feature
     double numa = 0.0, numb = 0.0, numc = 0.0, numd = 0.0;
     int s_use = s;  // s: next stage to load from; s_use: stage of the chunk being consumed
+    uint32_t ph_use = ph;
 
     // previous feature's weight into the accumulators, then this feature's chunk c into the freed registers
     auto load_chunk = [&](const int c) {
@@ -358,8 +374,8 @@ __device__ __forceinline__ void fused_trip_body(const FusedArgs& a, const Smem<C
     // issuing chunk c+1's shared-memory loads before consuming chunk c changed nothing: profiles/r1_notes.md)
     auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode), X, ld, units, ncf, g, s_use, j, c, f1, lane, sm, sync_mode);
-      if (++s_use == C::S) s_use = 0;
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode, ph_use), X, ld, units, ncf, g, s_use, j, c, f1, sm);
+      if (++s_use == C::S) { s_use = 0; ph_use ^= 1u; }
     };
 #pragma unroll
     for (int c = 0; c < C::CPF; ++c) {
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(512, 1) fused_trip_kernel(const FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Geo ge = make_geo<C, CL>(a.ld, a.n);
   const Smem<C> sm(smem_raw, 2 * ge.units, 1);  // u (this CTA's share)
-  init_sync<C>(sm);
+  init_sync<C>(sm, a.sync_mode);
   for (int i = threadIdx.x; i < 2 * ge.units; i += blockDim.x) sm.vec0[i] = i < ge.nloc ? a.u[2 * ge.uoff + i] : 0.0;
   __syncthreads();
   if (CL) cluster_sync_all();  // the peer's exchange barriers are initialised before anything is sent to them
@@ -445,6 +461,7 @@ __device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Sme
     double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
     uint32_t mx = 0, my = 0;  // NaN mode: which of this thread's entries are NaN (they must be stored back as NaN)
     int s_use = s;
+    uint32_t ph_use = ph;
 
     auto load_chunk = [&](const int c) {
       const bool have = load && c < ncf;
@@ -480,8 +497,8 @@ __device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Sme
     };
     auto release_chunk = [&](const int c) {
       if (!(load && c < ncf)) return;
-      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode), X, ld, units, ncf, g, s_use, j, c, f1, lane, sm, sync_mode);
-      if (++s_use == C::S) s_use = 0;
+      refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode, ph_use), X, ld, units, ncf, g, s_use, j, c, f1, sm);
+      if (++s_use == C::S) { s_use = 0; ph_use ^= 1u; }
     };
 #pragma unroll
     for (int c = 0; c < C::CPF; ++c) {
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Geo ge = make_geo<C, CL>(a.ld, a.n);
   const Smem<C> sm(smem_raw, 2 * ge.units, 2);  // ts | u0 (this CTA's share)
-  init_sync<C>(sm);
+  init_sync<C>(sm, a.sync_mode);
   const bool next = a.u != nullptr;
   for (int i = threadIdx.x; i < 2 * ge.units; i += blockDim.x) {
     sm.vec0[i] = i < ge.nloc ? a.ts[2 * ge.uoff + i] : 0.0;
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs 
   const int units = static_cast<int>(ld >> 1);
   const int ncf = (units + C::UC - 1) / C::UC;
   const Smem<C> sm(smem_raw, ld, 1);  // ts
-  init_sync<C>(sm);
+  init_sync<C>(sm, a.sync_mode);
   const bool next = a.gdef != nullptr;
   for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.ts[i] : 0.0;
   const double c_dense = next ? *a.cscal : 0.0;  // ts . u0
@@ -668,7 +685,7 @@ __global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs 
         }
       }
       if (have) {
-        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm, a.sync_mode), a.Xw, ld, units, ncf, g, s, j, c, f1, lane, sm, a.sync_mode);
+        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm, a.sync_mode, ph), a.Xw, ld, units, ncf, g, s, j, c, f1, sm);
         if (++s == C::S) { s = 0; ph ^= 1u; }
       }
     }
@@ -725,7 +742,10 @@ bool cluster_enabled() {
 }
 int default_sync_mode() {
   static int v = -1;
-  if (v < 0) v = env_int("MBPLS_FUSED_SYNC", 0) != 0;
+  if (v < 0) {
+    v = env_int("MBPLS_FUSED_SYNC", 0);
+    if (v < 0 || v > 2) v = 0;
+  }
   return v;
 }
 

@@ -69,7 +69,23 @@ __global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __re
       }
     }
     miss = warp_sum(miss);
-    if (lane == 0) out[j] = mode == 2 ? vv - miss : 1.0 / (vv - miss);
+    double obs = vv - miss;
+    if (fabs(miss) > 0.5 * fabs(vv)) {
+      // most of the mass sits under the holes: "total minus missing" would cancel (and could reach 0 or change sign where
+      // the reference's direct sum over the observed samples, :849-852 / :923-925, is positive) -> sum the observed ones
+      double o = 0.0;
+      for (int w = lane; w < nwords; w += 32) {
+        unsigned m = ~row[w];
+        if ((w + 1) * 32 > n) m &= (n - w * 32 >= 32) ? 0xffffffffu : ((1u << (n - w * 32)) - 1u);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          o = fma(v[w * 32 + b], v2[w * 32 + b], o);
+        }
+      }
+      obs = warp_sum(o);
+    }
+    if (lane == 0) out[j] = mode == 2 ? obs : 1.0 / obs;
   }
 }
 

@@ -173,25 +173,38 @@ def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, dev
     main.synchronize()
 
 
-def try_adopt_feature_major(blocks, n: int):
+def try_adopt_feature_major(blocks, n: int, writable: bool):
     """Zero-copy path: the blocks are consecutive column-major CUDA views into one 128-byte aligned
-    buffer with a common leading dimension -> return that buffer as the p x ld feature-major matrix."""
+    buffer with a common leading dimension -> return that buffer as the p x ld feature-major matrix,
+    or None (-> the caller copies).  Nothing outside the n samples of the views is ever written:
+
+    * ``writable=False`` (predict / transform): the product kernels honour n, so any leading dimension
+      works, e.g. the row slice ``X_cm[:n_train]`` of a taller column-major matrix;
+    * ``writable=True`` (fit with copy=False, which standardises and deflates in place): the kernels
+      stream whole padded features and write them back, so the elements [n, ld) of every feature must be
+      padding the caller set aside: ``ld == round_ld(n)`` and already zero (they stay zero).  A view whose
+      stride runs over rows of a taller matrix is copied instead.
+    """
     if not blocks or not all(isinstance(b, torch.Tensor) and b.is_cuda and b.dtype == F64 and b.dim() == 2 for b in blocks):
         return None
     ld = blocks[0].stride(1)
     if ld % 16 != 0 or ld < n or blocks[0].data_ptr() % 128 != 0:
         return None
     nxt = blocks[0].data_ptr()
-    base_storage = blocks[0].untyped_storage().data_ptr()
+    storage = blocks[0].untyped_storage()
+    base_storage = storage.data_ptr()
     for b in blocks:
         if b.shape[0] != n or b.shape[1] < 1 or b.stride(0) != 1 or b.stride(1) != ld or b.data_ptr() != nxt \
                 or b.untyped_storage().data_ptr() != base_storage:
             return None
         nxt += b.shape[1] * ld * 8
     p = sum(int(b.shape[1]) for b in blocks)
+    if nxt - base_storage > storage.nbytes():  # the last feature's tail [n, ld) would lie outside the allocation
+        return None
     Xt = blocks[0].as_strided((p, ld), (ld, 1))
-    if ld > n:
-        Xt[:, n:].zero_()
+    if writable and ld > n:
+        if ld != round_ld(n) or bool((Xt[:, n:] != 0).any()):
+            return None
     return Xt
 
 
@@ -203,12 +216,14 @@ def alloc_feature_major(p: int, n: int, device) -> torch.Tensor:
     return t
 
 
-def ingest_blocks(blocks, n: int, shard: ShardMap, device, presharded: bool = False, adopt: bool = False) -> torch.Tensor:
+def ingest_blocks(blocks, n: int, shard: ShardMap, device, presharded: bool = False, adopt: bool = False,
+                  adopt_writable: bool = True) -> torch.Tensor:
     """blocks: the global blocks (every rank slices its own column range) or, when ``presharded``, this
-    rank's local column ranges of them.  ``adopt`` allows the zero-copy path (caller passed copy=False)."""
+    rank's local column ranges of them.  ``adopt`` allows the zero-copy path (fit: the caller passed copy=False and the
+    matrix is standardised / deflated in place, ``adopt_writable``; predict / transform: read-only)."""
     if adopt and (presharded or shard.world == 1):
         nonempty = [b for b in blocks if b is not None and b.shape[1] > 0]
-        Xt = try_adopt_feature_major(nonempty, n)
+        Xt = try_adopt_feature_major(nonempty, n, writable=adopt_writable)
         if Xt is not None and Xt.shape[0] == shard.p_local:
             return Xt
     Xt = alloc_feature_major(shard.p_local, n, device)
@@ -469,7 +484,15 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     if trips_per_sync is None:
         # trips enqueued per readback of the convergence flag; trips launched after convergence are no-ops
         # (a few microseconds each), so batching only removes host round-trips from the critical path
-        est_ms = 2.0 * p * ld * 8 / 5e12 * 1e3
+        # (the estimate must be the same on every rank -- shard widths differ -- or the ranks would enqueue different
+        # numbers of per-trip all-reduces before the readback: use the widest shard)
+        p_est = p
+        if group is not None:
+            import torch.distributed as dist
+            pw = torch.tensor([p], dtype=torch.int64, device=dev)
+            dist.all_reduce(pw, op=dist.ReduceOp.MAX, group=group)
+            p_est = int(pw.item())
+        est_ms = 2.0 * p_est * ld * 8 / 5e12 * 1e3
         trips_per_sync = 2 if est_ms > 1.0 else 4
     # what the closing pass of the previous component left behind for the first trip of the coming one:
     # None, "w" (its weights) or "scores" (weights, squared norms and partial block scores: no pass over X needed)

@@ -53,6 +53,26 @@ _RUNTIME_DEFAULTS = dict(
 )
 
 
+# Small dense steps (pinv(P'W), the q x q eigen-problems, the superlevel epilogue) run in single-CTA device kernels whose
+# shared-memory tiles are sized for 64 (csrc/smalllin.cu SL_MAX, csrc/nipals.cu EPI_MAXB / EPI_MAXQ).  The reference has no such
+# limits; they are checked before any data is uploaded or modified.
+MAX_COMPONENTS = MAX_RESPONSES = MAX_BLOCKS = 64
+
+
+def _check_limits(n_components, q: int, B: int) -> int:
+    try:
+        K = int(n_components)
+    except (TypeError, ValueError) as exc:
+        raise ValueError(f"n_components must be an integer, got {n_components!r}") from exc
+    if K < 1:
+        raise ValueError(f"n_components must be >= 1, got {K}")
+    for what, val, cap in (("n_components", K, MAX_COMPONENTS), ("Y columns", q, MAX_RESPONSES), ("X blocks", B, MAX_BLOCKS)):
+        if val > cap:
+            raise NotImplementedError(f"mbpls_b200 supports at most {cap} {what} (got {val}): the K x K / q x q / B-wide "
+                                      "steps of the fit run in fixed-size single-CTA kernels")
+    return K
+
+
 def _is_block_list(X) -> bool:
     return isinstance(X, list) and not isinstance(X[0], list)  # mbpls.py:301
 
@@ -207,7 +227,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         return (np.where(row_has)[0], np.where(col_has)[0], np.where(~row_has)[0], np.where(~col_has)[0])
 
     # ------------------------------------------------------------------ ingest shared by fit / predict / transform
-    def _ingest(self, X, n_expected: Optional[int], shard: Optional[ShardMap], device, what="X", adopt=False):
+    def _ingest(self, X, n_expected: Optional[int], shard: Optional[ShardMap], device, what="X", adopt=False,
+                adopt_writable=True):
         gs = self._runtime()["global_sizes"]
         blocks = X if _is_block_list(X) else [X]
         blocks = [_as_2d_source(b, what, allow_empty=gs is not None) for b in blocks]
@@ -231,7 +252,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             shard = ShardMap.build(sizes, rank, world)
         elif list(shard.sizes) != sizes:
             raise ValueError("X has %r features per block, but MBPLS was fitted with %r" % (sizes, list(shard.sizes)))
-        Xt = E.ingest_blocks(blocks, n, shard, device, presharded=gs is not None, adopt=adopt)
+        Xt = E.ingest_blocks(blocks, n, shard, device, presharded=gs is not None, adopt=adopt, adopt_writable=adopt_writable)
         return Xt, n, shard
 
     # ------------------------------------------------------------------ fit (mbpls.py:273-1050)
@@ -270,6 +291,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 Ysrc = Ysrc.reshape(-1, 1)
             Ysrc = _as_2d_source(Ysrc, "Y")
             n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
+            _check_limits(self.n_components, q, len(X) if _is_block_list(X) else 1)
             # ---- X blocks (mbpls.py:299-347)
             Xt, n_x, shard = self._ingest(X, n, None, device, adopt=not self.copy)
             B = len(shard.sizes)
@@ -332,6 +354,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             Ysrc = Ysrc.reshape(-1, 1)
         Ysrc = _as_2d_source(Ysrc, "Y")
         n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
+        _check_limits(self.n_components, q, len(blocks))
         for b in blocks:
             if int(b.shape[0]) != n:
                 raise ValueError("Found input variables with inconsistent numbers of samples: %r" % [int(b.shape[0]), n])
@@ -575,7 +598,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         scaled_copy=True: a private, standardised copy (needed by the sequential block-score deflation)."""
         dev = self._device_model(device)
         shard = dev["shard"]
-        Xt, m, _ = self._ingest(X, None, shard, device, adopt=not scaled_copy)
+        Xt, m, _ = self._ingest(X, None, shard, device, adopt=not scaled_copy, adopt_writable=False)
         mean = scale = None
         if self.standardize:
             mean, scale, _, _ = self._device_scalers(shard, device)

@@ -3,6 +3,7 @@ import os
 import socket
 import subprocess
 import sys
+import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -69,3 +70,17 @@ def test_one_pass_configuration_tables():
     assert [call("mbpls_fused_workers_per_sm_pair", ld) for ld in lds] == [16, 16, 8, 8, 4, 4, 2, 2, 1, 1, 0]
     assert call("mbpls_fused_workers_per_sm_pair", 1000) == 0  # leading dimensions are multiples of 16
     assert [call("mbpls_nan_bitmask_ldw", n) for n in (1, 32, 33, 128, 129, 10_000)] == [4, 4, 4, 4, 8, 316]
+
+
+def test_size_limits_are_checked_up_front():
+    """K, q and B are capped at 64 by the single-CTA small-matrix kernels; the cap is reported by name before any
+    data is uploaded, not as an opaque status after the NIPALS loop has run."""
+    from mbpls_b200.mbpls import _check_limits, MAX_COMPONENTS
+    assert _check_limits(3, 2, 4) == 3 and _check_limits(MAX_COMPONENTS, 64, 64) == 64
+    for bad in ((65, 1, 1), (2, 65, 1), (2, 1, 65)):
+        with pytest.raises(NotImplementedError, match="at most 64"):
+            _check_limits(*bad)
+    with pytest.raises(ValueError):
+        _check_limits(0, 1, 1)
+    with pytest.raises(ValueError):
+        _check_limits("three", 1, 1)

@@ -185,3 +185,39 @@ def test_plot_data_matches_reference_recipe(capsys):
     except ImportError:
         with pytest.raises(ImportError):
             m.plot(1)
+
+
+@pytest.mark.parametrize("n_train,N", [(112, 160), (101, 160), (96, 96)])
+def test_row_slice_views_of_a_taller_device_matrix_are_never_written(n_train, N):
+    """A row slice ``X_cm[:n_train]`` of a column-major CUDA matrix has the parent's row count as its column stride: the
+    elements [n_train, N) of every feature are the caller's held-out samples, not padding.  Neither predict / transform
+    (which adopt such views zero-copy) nor fit(copy=False) may touch them, and a slice that starts at a later row must take
+    the copy path instead of failing (engine.try_adopt_feature_major)."""
+    import torch
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(N, (24, 40), 2, 3, seed=9)
+    dev = torch.device("cuda:0")
+    buf = torch.zeros((64, N), dtype=torch.float64, device=dev)      # feature-major parent: 64 features x N samples
+    buf[:24] = torch.from_numpy(X[0].T.copy()).to(dev)
+    buf[24:] = torch.from_numpy(X[1].T.copy()).to(dev)
+    parent = buf.clone()
+    views = lambda r0, r1: [buf[:24, r0:r1].t(), buf[24:, r0:r1].t()]  # n x p_b views with strides (1, N)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(n_components=3).fit([x[:n_train].copy() for x in X], Y[:n_train].copy())
+        m = MBPLS(n_components=3).fit([x[:n_train].copy() for x in X], Y[:n_train].copy())
+        yh = m.predict(views(0, n_train))
+        assert torch.equal(buf, parent), "predict wrote into the caller's matrix"
+        assert rel_err(yh, o.predict([x[:n_train] for x in X])) < TOL
+        if N > n_train:
+            yh_tail = m.predict(views(n_train, N))                    # slice with a storage offset
+            assert torch.equal(buf, parent)
+            assert rel_err(yh_tail, o.predict([x[n_train:] for x in X])) < TOL
+        Ts = m.transform(views(0, n_train))
+        assert torch.equal(buf, parent)
+        assert rel_err(np.abs(Ts), np.abs(o.transform([x[:n_train] for x in X]))) < TOL
+        m2 = MBPLS(n_components=3, copy=False).fit(views(0, n_train), Y[:n_train].copy())
+        assert torch.equal(buf[:, n_train:], parent[:, n_train:]), "fit(copy=False) wrote beyond the n samples it was given"
+        assert rel_err(m2.beta_, o.beta_) < TOL
