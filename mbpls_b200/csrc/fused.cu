@@ -220,8 +220,7 @@ __device__ __forceinline__ bool arrive_stage(int g, int s, int lane, const Smem<
   if (sync_mode == 2) {
     uint64_t* eb = reinterpret_cast<uint64_t*>(c);
     if (mbar_pending_count(mbar_arrive_state(eb)) != 1u) return false;
-    while (!mbar_test_wait(eb, parity)) {
-    }
+    mbar_wait(eb, parity);  // already complete: returns at once, with acquire semantics
     return true;
   }
   const unsigned old = sync_mode ? atom_inc_smem_acqrel(c) : atom_inc_smem(c);
@@ -252,7 +251,9 @@ __device__ __forceinline__ double pair_sum(double own, int g, int tg, uint32_t p
     mbar_arrive_expect_tx(bar, 8);
     st_async_f64(mapa_shared(smem_u32(slot), peer), own, mapa_shared(smem_u32(bar), peer));
   }
-  mbar_wait_cluster(bar, (xp >> xs) & 1u);
+  // CTA-scope acquire: the value arrives through the mbarrier's transaction count (like a multicast bulk copy), and a
+  // cluster-scope acquire would invalidate L1 on every exchange (CCTL.IVALL: 8 % of the stall samples in ncu)
+  mbar_wait(bar, (xp >> xs) & 1u);
   const double other = *reinterpret_cast<volatile double*>(slot);
   xp ^= 1u << xs;
   xs ^= 1;
@@ -518,6 +519,7 @@ __device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Sme
       const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
       if (((k / C::EPTC) + 1 < ncf) || gi < units) {
         const double2 tv = ts2[gi];
+        const double2 uv = u2[gi];  // issued together with the ts load (zeros when there is no next component)
         double2 xn;
         xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
         xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
@@ -531,7 +533,6 @@ __device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Sme
         }
         x[k] = xn;
         if (next) {
-          const double2 uv = u2[gi];
           if (k & 1) {
             wc = fma(xn.x, uv.x, wc);
             wd = fma(xn.y, uv.y, wd);
