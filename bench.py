@@ -387,14 +387,14 @@ def run_ours(args):
 
     one_pass = False if args.two_pass else None
 
-    def make_model(profile=None, materialize=False, sparse=None, rec=None):
+    def make_model(profile=None, materialize=False, sparse=None):
         m = MBPLS(n_components=K, method="NIPALS", standardize=True, calc_all=True,
                   sparse_data=(args.nan_frac > 0) if sparse is None else sparse, copy=False)
         m.set_runtime(device=dev, group=group, materialize=materialize, global_sizes=sizes, profile=profile,
-                      max_iter=args.max_iter, one_pass=one_pass, deflate_rec=rec)
+                      max_iter=args.max_iter, one_pass=one_pass)
         return m
 
-    def one_fit(profile=None, nan_frac=None, rec=None):
+    def one_fit(profile=None, nan_frac=None):
         regenerate(nan_frac)
         barrier()
         log("regenerated")
@@ -402,7 +402,7 @@ def run_ours(args):
         e0.record()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            m = make_model(profile, sparse=None if nan_frac is None else nan_frac > 0, rec=rec).fit(local_blocks(), Yd)
+            m = make_model(profile, sparse=None if nan_frac is None else nan_frac > 0).fit(local_blocks(), Yd)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -432,14 +432,6 @@ def run_ours(args):
         variants["nan_10pct"] = {"fit_s": nan_ms / 1e3, "value": fit_bytes(n, p, K, nt) / (nan_ms / 1e3) / 1e9, "unit": "GB/s",
                                  "trips_per_component": nt, "kernels": "one-pass kernels with NaN read as zero + masked denominators from the NaN bit matrix (DESIGN.md 3a)"}
         del nan_model
-        # opt-in deflation that carries x_j . u0 per feature instead of keeping u0 in shared memory: faster,
-        # but its first-trip weights are noisier, so trip counts can exceed the reference's; reported for information only
-        one_fit(rec=True)
-        rec_ms, rec_model = one_fit(rec=True)
-        rt_ = list(rec_model.n_iter_)
-        variants["recurrence_deflation_opt_in"] = {"fit_s": rec_ms / 1e3, "value": fit_bytes(n, p, K, rt_) / (rec_ms / 1e3) / 1e9,
-                                                   "unit": "GB/s", "trips_per_component": rt_}
-        del rec_model
     trips = list(model.n_iter_)
     ms_step = sum(times) / len(times)
     value = fit_bytes(n, p, K, trips) / (ms_step / 1e3) / 1e9
@@ -532,20 +524,24 @@ def run_ours(args):
             del Xbuf
             torch.cuda.empty_cache()
             e_times, d2h = [], 0
-            for it in range(1 + max(1, args.e2e_steps)):
+            n_e2e = 1 + max(1, args.e2e_steps)   # one untimed warm-up repetition (pinned result buffers are cached after it)
+            for it in range(n_e2e + (1 if VERBOSE else 0)):  # --verbose: one more, untimed, with per-phase wall clocks
                 barrier()
                 t0 = time.perf_counter()
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
                     m = MBPLS(n_components=K, method="NIPALS", sparse_data=args.nan_frac > 0, copy=True)
-                    m.set_runtime(device=dev, group=group, materialize=True, global_sizes=sizes, max_iter=args.max_iter)
+                    phases = {} if it >= n_e2e else None
+                    m.set_runtime(device=dev, group=group, materialize=True, global_sizes=sizes, max_iter=args.max_iter, timings=phases)
                     m.fit(host, Yh)
+                    if phases is not None:
+                        log("e2e phases (s)", {k: round(v, 4) for k, v in phases.items()})
                 barrier()
                 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=group)
                 log("e2e fit s", float(dt.item()))
-                if it > 0:
+                if 0 < it < n_e2e:
                     e_times.append(float(dt.item()))
                 d2h = sum(a.nbytes for a in [m.Ts_, m.U_, m.V_, m.R_, m.beta_, m.A_] + m.T_ + m.W_ + m.P_ + m.W_non_normal_)
                 e_trips = list(m.n_iter_)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 7
+#define MBPLS_ABI_VERSION 8
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -166,8 +166,7 @@ int mbpls_fused_uses_clusters(long ld);
  * mbpls_masked_rowden_f64 afterwards. */
 int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
                                 const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* w,
-                                double* norm_part, double* Tnum, long ldt, double* dots_out, const int* done, void* stream);
-/* dots_out (optional): the raw (masked) numerators x_j . u, which seed the recurrence of mbpls_fused_deflate_rec_f64 when u = u0 */
+                                double* norm_part, double* Tnum, long ldt, const int* done, void* stream);
 /* Loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL -- the complete
  * first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0, its squared norms
  * and its partial block scores Tnum.  1 read + 1 write of X.  NaN mode (rden_ts != NULL): masked loadings / weights through
@@ -176,15 +175,6 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
                             const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream);
-
-/* Same pass without a resident u0: gdef[j] holds x_j . u0 of the current (deflated) matrix, seeded by the first trip of the
- * fit (dots_out, u = u0) and updated here, gdef[j] -= p_j * (ts . u0) (masked data: tsu0_masked[j] instead of *tsu0); the next
- * weights are gdef[j] / u0'u0.  Shared memory then holds ts and the ring only (40 KB chunks at n = 10,000).  gdef == NULL:
- * loadings + deflation only. */
-int mbpls_fused_deflate_rec_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0u0,
-                                const double* rden_u0, const double* tsu0, const double* tsu0_masked, double* gdef,
-                                const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
-                                double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream);
 
 /* ---- NaN bit matrix and the masked denominators derived from it (csrc/nanmask.cu; mbpls.py:848-852, :867-872, :923-925)
  * bits[j*ldw + (i >> 5)] bit (i & 31) = 1 iff x_ij is NaN; ldw = mbpls_nan_bitmask_ldw(n) 32-bit words per feature. */

@@ -140,7 +140,7 @@ def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=
     lazy = {
         "Ts_": lambda: model._gather_samples(Ts, n),
         "U_": lambda: model._gather_samples(U, n) if U is not None else np.empty((n, 0)),
-        "V_": lambda: np.ascontiguousarray(V.cpu().numpy().T),
+        "V_": lambda: E.to_host(V, transpose=True),
         "P_": lambda: model._features_T(P, shard, True),
         "R_": lambda: model._features_T(R, shard, False),
         "beta_": lambda: model._features_T(beta, shard, False),

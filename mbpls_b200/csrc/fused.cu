@@ -65,9 +65,6 @@ struct FusedArgs {
   const double* ts;  // deflate only
   const double* rden;   // NaN mode: per-feature reciprocal masked denominator for u (trip) / ts (deflate)
   const double* rden2;  // NaN mode, deflate: same for u0
-  const double* cmask;  // recurrence deflation, NaN mode: per-feature masked ts . u0
-  const double* cscal;  // recurrence deflation: device scalar ts . u0
-  double* gdef;         // recurrence deflation: running x_j(deflated) . u0 per feature (read, updated); trip: raw dot products out
   const int* split_f0;
   const int* split_f1;
   const int* split_block;
@@ -80,7 +77,7 @@ struct FusedArgs {
   double* P_k;  // deflate: loadings out
   double* pss;  // deflate: p_j^2 out
   const int* done;
-  int sync_mode;  // 0: relaxed stage counter (default); 1: acq_rel counter + generic->async proxy fence before the refill
+  int sync_mode;  // stage hand-off protocol, see arrive_stage(): 2 = "empty" mbarrier (default), 0 / 1 = shared-memory counters
 };
 
 // TG threads per worker, EPTC units per thread per chunk, at most CPF chunks per feature, S ring stages
@@ -221,6 +218,7 @@ __device__ __forceinline__ bool arrive_stage(int g, int s, int lane, const Smem<
     uint64_t* eb = reinterpret_cast<uint64_t*>(c);
     if (mbar_pending_count(mbar_arrive_state(eb)) != 1u) return false;
     mbar_wait(eb, parity);  // already complete: returns at once, with acquire semantics
+    fence_proxy_async_smem();  // the reads were generic-proxy accesses, the refill is an async-proxy write
     return true;
   }
   const unsigned old = sync_mode ? atom_inc_smem_acqrel(c) : atom_inc_smem(c);
@@ -389,10 +387,7 @@ __device__ __forceinline__ void fused_trip_body(const FusedArgs& a, const Smem<C
     flip ^= 1;
     if (CL) one[0] = pair_sum<C>(one[0], g, tg, ge.peer, xs, xp, sm);
     wj = one[0] * rd;
-    if (tg == 0 && ge.lead) {
-      a.w[j] = wj;
-      if (a.gdef) a.gdef[j] = one[0];  // x_j . u (numerator only): seeds the running x_j . u0 of the recurrence deflation
-    }
+    if (tg == 0 && ge.lead) a.w[j] = wj;
     normsq = fma(wj, wj, normsq);
   }
 
@@ -584,143 +579,6 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   if (CL) cluster_sync_all();
 }
 
-// ------------------------------------------------------------------------------------------
-// Recurrence deflation (opt-in, set_runtime(deflate_rec=True)): the same pass without a resident u0.
-//
-// With p_j = x_j . ts in hand, the dot product of the DEFLATED feature with u0 follows from that of the undeflated one:
-// x_j(deflated) . u0 = x_j . u0 - p_j (ts . u0)   (masked data: all sums over the observed samples of the feature).
-// So a_j = x_j . u0 obeys a recurrence over the components.  Keeping that scalar per feature in global memory (`gdef`,
-// seeded with the raw dot products of a first trip, whose u IS u0, and re-seeded the same way every few components so that
-// rounding cannot pile up) removes u0 from shared memory: the kernel then has the trip kernel's footprint -- one n-vector
-// and the ring -- i.e. 40 KB chunks instead of 16 KB at n = 10,000 (30.4 -> 26.6 ms for 160 GB, 6.0 TB/s read + write),
-// and the next weight is known right after the ONE reduction, so update, write-back and score accumulation of feature j-1
-// ride, unit by unit, on the load loop of feature j (each register is updated, stored, accumulated and reloaded in turn).
-// Not the default: the carried scalar is noisier than a fresh dot product by the ratio |x_j| / |x_j deflated|, which can
-// push diff_t of a late component's second trip over the reference's max_tol = 1e-14 and cost a third trip
-// (profiles/r1_notes.md).  A variant that keeps u0 resident and forms x_j . u0 afresh (one reduction, same footprint as
-// fused_deflate_kernel) measured 29.0 vs 30.0 ms and was dropped.
-// ------------------------------------------------------------------------------------------
-template <bool NANMODE, class C>
-__global__ void __launch_bounds__(512, 1) fused_deflate3_kernel(const FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const long ld = a.ld;
-  const int units = static_cast<int>(ld >> 1);
-  const int ncf = (units + C::UC - 1) / C::UC;
-  const Smem<C> sm(smem_raw, ld, 1);  // ts
-  init_sync<C>(sm, a.sync_mode);
-  const bool next = a.gdef != nullptr;
-  for (int i = threadIdx.x; i < ld; i += blockDim.x) sm.vec0[i] = i < a.n ? a.ts[i] : 0.0;
-  const double c_dense = next ? *a.cscal : 0.0;  // ts . u0
-  __syncthreads();
-
-  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
-  const int lane = threadIdx.x & 31, wig = tg >> 5;
-  const int wk = blockIdx.x * C::G + g;
-  if (wk >= a.nsplit) return;
-  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
-  if (tg == 0) prime_ring<C>(a.Xw, ld, units, ncf, g, f0, f1, sm);
-  const double inv_uu = next ? 1.0 / *a.uu : 1.0;
-  const double2* __restrict__ ts2 = reinterpret_cast<const double2*>(sm.vec0);
-  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-
-  double2 acc[C::EPT], x[C::EPT];
-#pragma unroll
-  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
-  double normsq = 0.0, wj = 0.0, pj = 0.0;
-  uint32_t mx = 0, my = 0;  // NaN mode: NaN positions of the feature held in x (written back as NaN)
-  int s = 0;
-  uint32_t ph = 0;
-  int flip = 0;
-
-  for (int j = f0; j <= f1; ++j) {
-    const bool load = j < f1, store = j > f0;
-    const double rdp = (NANMODE && load) ? a.rden[j] : 1.0;               // loadings: 1 / masked ts'ts (dense: not divided, :920)
-    const double rdw = (NANMODE && load && next) ? a.rden2[j] : inv_uu;   // next weights: 1 / masked u0'u0
-    const double cj = (NANMODE && load && next) ? a.cmask[j] : c_dense;   // (masked) ts . u0
-    double2* __restrict__ xg = reinterpret_cast<double2*>(a.Xw + static_cast<size_t>(j - 1) * ld);  // row of the feature held in x
-    const double gj = (load && next) ? a.gdef[j] : 0.0;  // x_j . u0 before this deflation
-    double pa = 0.0, pb = 0.0, pc = 0.0, pd = 0.0;
-    uint32_t nmx = 0, nmy = 0;
-#pragma unroll
-    for (int c = 0; c < C::CPF; ++c) {
-      const bool have = load && c < ncf;
-      const double2* __restrict__ xs = reinterpret_cast<const double2*>(sm.stage(g, s));
-      if (have) mbar_wait(&sm.full[g * C::S + s], ph);
-      const bool whole = c + 1 < ncf;
-#pragma unroll
-      for (int e = 0; e < C::EPTC; ++e) {
-        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
-        if (c < ncf && (whole || gi < units)) {
-          const double2 tv = ts2[gi];
-          if (store) {  // feature j-1: deflate, write back, accumulate the next component's score partials
-            double2 xn;
-            xn.x = __dsub_rn(x[k].x, __dmul_rn(tv.x, pj));  // the reference rounds ts*p before subtracting (:969)
-            xn.y = __dsub_rn(x[k].y, __dmul_rn(tv.y, pj));
-            if (NANMODE) {
-              double2 out = xn;
-              if ((mx >> k) & 1u) { out.x = qnan; xn.x = 0.0; }
-              if ((my >> k) & 1u) { out.y = qnan; xn.y = 0.0; }
-              st_stream(xg + gi, out);
-            } else {
-              st_stream(xg + gi, xn);
-            }
-            acc[k].x = fma(wj, xn.x, acc[k].x);
-            acc[k].y = fma(wj, xn.y, acc[k].y);
-          }
-          if (have) {  // feature j: into the freed registers, both dot products on the fly
-            double2 xv = xs[l];
-            if (NANMODE) {
-              if (isnan(xv.x)) { xv.x = 0.0; nmx |= 1u << k; }
-              if (isnan(xv.y)) { xv.y = 0.0; nmy |= 1u << k; }
-            }
-            if (e & 1) {
-              pc = fma(xv.x, tv.x, pc);
-              pd = fma(xv.y, tv.y, pd);
-            } else {
-              pa = fma(xv.x, tv.x, pa);
-              pb = fma(xv.y, tv.y, pb);
-            }
-            x[k] = xv;
-          }
-        }
-      }
-      if (have) {
-        refill_if_last<C>(arrive_stage<C>(g, s, lane, sm, a.sync_mode, ph), a.Xw, ld, units, ncf, g, s, j, c, f1, sm);
-        if (++s == C::S) { s = 0; ph ^= 1u; }
-      }
-    }
-    if (!load) break;
-    mx = nmx;
-    my = nmy;
-    double v[1] = {(pa + pb) + (pc + pd)};
-    worker_sum<1, C::kTG>(v, scratch + flip * 3 * C::NW, g, wig, lane);
-    flip ^= 1;
-    pj = v[0] * rdp;
-    const double gnew = gj - pj * cj;  // x_j(deflated) . u0
-    if (next) {
-      wj = gnew * rdw;
-      normsq = fma(wj, wj, normsq);
-    }
-    if (tg == 0) {
-      a.P_k[j] = pj;
-      a.pss[j] = pj * pj;
-      if (next) {
-        a.w[j] = wj;
-        a.gdef[j] = gnew;
-      }
-    }
-  }
-  if (!next) return;
-  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
-#pragma unroll
-  for (int k = 0; k < C::EPT; ++k) {
-    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
-    if (gi < units) tn[gi] = acc[k];
-  }
-  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
-}
-
 // Configurations by feature length (units = 16-byte units per feature handled by ONE CTA <= TG*EPTC*CPF).  Measured
 // (profiles/r1_notes.md): every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as
 // the ring allows: the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
@@ -731,7 +589,7 @@ using CfgC = Cfg<128, 5, 2, 4>;   // <= 1280 units: four workers, 10 KB chunks
 using CfgD = Cfg<64, 10, 1, 2>;   // <= 640 units: eight workers, one chunk per feature
 
 // MBPLS_FUSED_CLUSTER=0 keeps features of up to 10,240 samples on the single-CTA deflation kernel (A/B measurements);
-// MBPLS_FUSED_SYNC=1 selects the acq_rel stage counter + proxy fence (FusedArgs::sync_mode)
+// MBPLS_FUSED_SYNC=0 / 1 select the counter-based stage hand-offs instead of the default "empty" mbarrier (FusedArgs::sync_mode)
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -744,8 +602,8 @@ bool cluster_enabled() {
 int default_sync_mode() {
   static int v = -1;
   if (v < 0) {
-    v = env_int("MBPLS_FUSED_SYNC", 0);
-    if (v < 0 || v > 2) v = 0;
+    v = env_int("MBPLS_FUSED_SYNC", 2);
+    if (v < 0 || v > 2) v = 2;
   }
   return v;
 }
@@ -868,13 +726,6 @@ int dispatch_deflate(int cfg, const FusedArgs& a, cudaStream_t st) {
   }
 }
 
-template <bool NANMODE, class C>
-int launch_deflate3(const FusedArgs& a, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes<C>(a.ld, 1);
-  if ((a.ld >> 1) > C::MAX_UNITS) return MBPLS_ERR_SIZE;
-  return launch_fused(fused_deflate3_kernel<NANMODE, C>, a, C::G, smem, false, st);
-}
-
 }  // namespace
 
 extern "C" {
@@ -899,13 +750,13 @@ int mbpls_fused_uses_clusters(long ld) {
 
 int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* u, const double* uu, const double* rden,
                                 const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* w,
-                                double* norm_part, double* Tnum, long ldt, double* dots_out, const int* done, void* stream) {
+                                double* norm_part, double* Tnum, long ldt, const int* done, void* stream) {
   if (!Xt || !u || !uu || !split_f0 || !split_f1 || !split_block || !w || !norm_part || !Tnum || ld < n || ldt < ld || B < 1)
     return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
   const Plan pl = plan_of(ld);
   if (!pl.trip || nsplit > pl.workers) return MBPLS_ERR_SIZE;
-  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, nullptr, nullptr, dots_out, split_f0, split_f1, split_block, nsplit, B,
+  FusedArgs a{Xt, nullptr, ld, n, u, uu, nullptr, rden, nullptr, split_f0, split_f1, split_block, nsplit, B,
               w, norm_part, Tnum, ldt, nullptr, nullptr, done, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.trip_cl) return rden ? dispatch_trip<true, true>(pl.trip, a, st) : dispatch_trip<false, true>(pl.trip, a, st);
@@ -921,33 +772,11 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
   if (nsplit == 0) return MBPLS_OK;
   const Plan pl = plan_of(ld);
   if (!pl.deflate || nsplit > pl.workers) return MBPLS_ERR_SIZE;
-  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, nullptr, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, split_f0, split_f1, split_block, nsplit, B,
               w_next, norm_part, Tnum, ldt, P_k, pss, nullptr, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.deflate_cl) return rden_ts ? dispatch_deflate<true, true>(pl.deflate, a, st) : dispatch_deflate<false, true>(pl.deflate, a, st);
   return rden_ts ? dispatch_deflate<true, false>(pl.deflate, a, st) : dispatch_deflate<false, false>(pl.deflate, a, st);
-}
-
-int mbpls_fused_deflate_rec_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0u0,
-                                const double* rden_u0, const double* tsu0, const double* tsu0_masked, double* gdef,
-                                const int* split_f0, const int* split_f1, const int* split_block, int nsplit, int B, double* P_k,
-                                double* pss, double* w_next, double* norm_part, double* Tnum, long ldt, void* stream) {
-  if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
-  if (gdef && (!u0u0 || !tsu0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && (!rden_u0 || !tsu0_masked))))
-    return MBPLS_ERR_ARG;
-  if (nsplit == 0) return MBPLS_OK;
-  const Plan pl = plan_of(ld);
-  if (!pl.trip || pl.trip_cl || nsplit > pl.workers) return MBPLS_ERR_SIZE;  // single-CTA configurations only
-  FusedArgs a{nullptr, Xt, ld, n, nullptr, u0u0, ts, rden_ts, rden_u0, tsu0_masked, tsu0, gdef, split_f0, split_f1, split_block, nsplit, B,
-              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr, default_sync_mode()};
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (pl.trip) {
-    case 1: return rden_ts ? launch_deflate3<true, CfgA>(a, st) : launch_deflate3<false, CfgA>(a, st);
-    case 2: return rden_ts ? launch_deflate3<true, CfgB>(a, st) : launch_deflate3<false, CfgB>(a, st);
-    case 3: return rden_ts ? launch_deflate3<true, CfgC>(a, st) : launch_deflate3<false, CfgC>(a, st);
-    case 4: return rden_ts ? launch_deflate3<true, CfgD>(a, st) : launch_deflate3<false, CfgD>(a, st);
-    default: return MBPLS_ERR_SIZE;
-  }
 }
 
 }  // extern "C"

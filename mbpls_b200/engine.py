@@ -99,12 +99,6 @@ def _i32(vals, device):
 # ingest: host / device arrays -> feature-major device matrix
 # --------------------------------------------------------------------------------------------- #
 _STAGE_BYTES = 64 << 20
-# Recurrence deflation (csrc/fused.cu fused_deflate3_kernel) is 8 % faster at the headline size but opt-in
-# (set_runtime(deflate_rec=True)): the carried x_j . u0 is noisier than a fresh dot product by the ratio |x_j| / |x_j deflated|,
-# which can push diff_t of a late component's second trip over the reference's max_tol = 1e-14 and cost a third trip
-# (observed: component 11 of 19 on a 260 x 115 problem) -- results stay within 1e-8 but n_iter_ no longer matches.
-_DEFLATE_REC_DEFAULT = False
-_REC_REFRESH = 16             # the carried x_j . u0 is recomputed from X every so many components (bounds the drift)
 _COPY_STREAMS: dict = {}
 
 
@@ -206,6 +200,34 @@ def try_adopt_feature_major(blocks, n: int, writable: bool):
         if ld != round_ld(n) or bool((Xt[:, n:] != 0).any()):
             return None
     return Xt
+
+
+_PIN_MIN_BYTES = 1 << 20
+
+
+def to_host(t: torch.Tensor, transpose: bool = False) -> np.ndarray:
+    """Device tensor -> numpy array (its transpose when ``transpose``), contiguous in the returned orientation.
+
+    The transposition runs on the device and the copy lands in page-locked memory from PyTorch's caching host allocator,
+    so a result array costs one PCIe-rate DMA: no pageable staging inside the driver, no first-touch page faults of a
+    fresh allocation, no strided host transposes (657 MB of attributes at the headline size cost 0.3 s that way).  The array
+    keeps its pinned block alive; the block returns to the cache when the array is dropped.  Small results, and
+    allocations the host cannot pin, take the ordinary pageable copy."""
+    if transpose:
+        t = t.t()
+    t = t.contiguous()
+    if not t.is_cuda:
+        return t.numpy()
+    if t.numel() * t.element_size() >= _PIN_MIN_BYTES:
+        try:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        except RuntimeError:
+            h = None
+        if h is not None:
+            h.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return h.numpy()
+    return t.cpu().numpy()
 
 
 def alloc_feature_major(p: int, n: int, device) -> torch.Tensor:
@@ -388,8 +410,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
                deflate_last: bool = False, one_pass: Optional[bool] = None,
-               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None,
-               deflate_rec: Optional[bool] = None) -> NipalsResult:
+               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -450,13 +471,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     ctrl_h = torch.empty(_cabi.CTRL_COUNT, dtype=torch.int32).pin_memory()
     u0u0 = buf(1)
     call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), st)
-    bits = rden_u = rden_ts = rden_u0 = tsu0_m = tsu0 = None
-    # recurrence deflation (fused_deflate3_kernel): x_j . u0 is carried per feature instead of keeping u0 in shared memory
-    use_rec = use_opd and fuse_next_xtu and (deflate_rec is True or (deflate_rec is None and _DEFLATE_REC_DEFAULT)) \
-        and not (call("mbpls_fused_uses_clusters", ld) & 1)
-    gdef = buf(p) if use_rec else None
-    if use_rec and tsu0 is None:
-        tsu0 = buf(1)
+    bits = rden_u = rden_ts = rden_u0 = None
     ldw = 0
     if nan and use_op:
         # NaN bit matrix (the pattern never changes: deflation keeps NaN, mbpls.py:969) and the masked denominators
@@ -465,7 +480,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         bits = torch.empty((p, ldw), dtype=torch.int32, device=dev)
         call("mbpls_nan_bitmask_f64", ptr(Xt), ld, n, p, ptr(bits), ldw, st)
         col_nan = col_nan.to(torch.int32).contiguous()
-        rden_u, rden_ts, rden_u0, tsu0_m, tsu0 = buf(p), buf(p), buf(p), buf(p), buf(1)
+        rden_u, rden_ts, rden_u0 = buf(p), buf(p), buf(p)
         call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(u0), None, ptr(u0u0), 1, ptr(rden_u0), None, st)
 
     res = NipalsResult(Wt=buf(K, p), W=buf(K, p), P=buf(K, p), Ts=buf(K, ld, zero=True), U=buf(K, ld, zero=True),
@@ -516,9 +531,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         while True:
             for _ in range(trips_per_sync):
                 first = launched == 0
-                # recurrence deflation: every _REC_REFRESH components the first trip is recomputed from X (its u is u0), which
-                # re-seeds the carried x_j . u0 exactly; otherwise the deflation pass has already left the first trip's scores
-                have_scores = first and w_ready == "scores" and not (use_rec and k % _REC_REFRESH == 0)
+                have_scores = first and w_ready == "scores"  # the deflation pass has already left the first trip's scores
                 if have_scores or (use_op and not (first and w_ready == "w")):
                     if not have_scores:
                         if nan:  # 1 / sum over the observed samples of u^2, per feature (mbpls.py:848-852)
@@ -526,8 +539,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                                                          ptr(scal), 1, ptr(rden_u), done_p, st))
                         timed("trip", lambda: call("mbpls_nipals_fused_trip_f64", ptr(Xt), ld, n, ptr(u), ptr(scal), ptr(rden_u),
                                                    ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(w), ptr(norm_part_o),
-                                                   ptr(Tnum_o), ld, ptr(gdef) if (use_rec and first) else None,
-                                                   done_p, st))
+                                                   ptr(Tnum_o), ld, done_p, st))
                         if nan:  # sum over the observed features of w~^2, per sample and split (:867-872)
                             timed("rowden", lambda: call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1),
                                                          nsplit_o, ptr(Tden_o), ld, done_p, st))
@@ -577,26 +589,12 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
                 call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
                      ptr(rden_ts), None, st)
-                if fuse and use_rec:  # sum over the observed samples of ts u0 per feature
-                    call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
-                    call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), ptr(u0), ptr(tsu0), 2,
-                         ptr(tsu0_m), None, st)
-            elif fuse and use_rec:
-                call("mbpls_vec_dot_f64", ptr(ts), ptr(u0), n, ptr(tsu0), st)
-            if use_rec:
-                timed("deflate", lambda: call("mbpls_fused_deflate_rec_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
-                                              ptr(u0u0) if fuse else None, ptr(rden_u0) if fuse else None,
-                                              ptr(tsu0) if fuse else None, ptr(tsu0_m) if fuse else None,
-                                              ptr(gdef) if fuse else None, ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B,
-                                              ptr(res.P[k]), ptr(pss), ptr(w) if fuse else None,
-                                              ptr(norm_part_o) if fuse else None, ptr(Tnum_o) if fuse else None, ld, st))
-            else:
-                timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
-                                              ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
-                                              ptr(rden_u0) if fuse else None,
-                                              ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
-                                              ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
-                                              ptr(Tnum_o) if fuse else None, ld, st))
+            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
+                                          ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
+                                          ptr(rden_u0) if fuse else None,
+                                          ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
+                                          ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
+                                          ptr(Tnum_o) if fuse else None, ld, st))
             if nan and fuse:
                 call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1), nsplit_o, ptr(Tden_o), ld,
                      None, st)

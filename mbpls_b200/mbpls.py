@@ -47,9 +47,13 @@ _RUNTIME_DEFAULTS = dict(
     global_sizes=None,    # multi-GPU: the blocks passed in are this rank's column ranges of blocks of these sizes
     profile=None,         # dict collecting CUDA-event pairs per kernel (bench.py roofline)
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
-    one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 10240), False two-pass kernels
+    one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 20480), False two-pass kernels
     one_pass_deflate=None,  # loadings+deflation also runs the next component's whole first trip (None auto, False off)
-    deflate_rec=None,     # that pass without a resident u0: x_j.u0 carried per feature across components (csrc/fused.cu v3)
+    timings=None,         # dict: wall-clock seconds per phase of fit (ingest / standardize / solve / materialize), measured with a
+                          # device synchronisation at every phase boundary (diagnostics; bench.py --verbose)
+    gather=None,          # multi-GPU, per-feature attributes (W_, P_, R_, beta_, x_scalers_): "all" = every rank materialises the
+                          # full p x K arrays (all-gather), "local" = every rank its own rows, sharded like the input it passed.
+                          # None: "local" when the input was pre-sharded (global_sizes), else "all"
 )
 
 
@@ -162,10 +166,22 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         import torch.distributed as dist
         return group, dist.get_rank(group), dist.get_world_size(group)
 
-    def _gather_features_dev(self, t_local: torch.Tensor, shard: ShardMap) -> torch.Tensor:
-        """K x p_local device tensor -> K x p_global device tensor (same on every rank)."""
+    def _gather_mode(self) -> str:
+        rt = self._runtime()
+        mode = rt["gather"]
+        if mode is None:
+            mode = "local" if rt["global_sizes"] is not None else "all"
+        if mode not in ("all", "local"):
+            raise ValueError("runtime option gather must be 'all', 'local' or None")
+        return mode
+
+    def _gather_features_dev(self, t_local: torch.Tensor, shard: ShardMap, force_all: bool = False) -> torch.Tensor:
+        """K x p_local device tensor -> K x p_global device tensor (same on every rank); in "local" gather mode the
+        rank's own K x p_local rows (no collective: a rank that passed its column ranges gets their attributes back)."""
         group, rank, world = self._group_info()
         if world == 1 or shard.world == 1:  # single GPU, or feature axis replicated (row-sharded fit)
+            return t_local[:, :shard.p_local]
+        if not force_all and self._gather_mode() == "local":
             return t_local[:, :shard.p_local]
         import torch.distributed as dist
         per = -(-shard.p_global // world)
@@ -176,26 +192,37 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         dist.all_gather(parts, pad, group=group)
         return torch.cat(parts, dim=1)[:, :shard.p_global]
 
-    def _gather_features(self, t_local: torch.Tensor, shard: ShardMap) -> np.ndarray:
-        """K x p_local device tensor -> K x p_global numpy array (same on every rank)."""
-        return self._gather_features_dev(t_local, shard).cpu().numpy()
+    def _gather_features(self, t_local: torch.Tensor, shard: ShardMap, force_all: bool = False) -> np.ndarray:
+        """K x p_local device tensor -> K x p_global (or, "local" gather mode, K x p_local) numpy array."""
+        return E.to_host(self._gather_features_dev(t_local, shard, force_all))
+
+    def _local_attrs(self, shard: ShardMap) -> bool:
+        """True when per-feature attributes hold this rank's rows only ("local" gather mode of a feature-sharded fit)."""
+        _, _, world = self._group_info()
+        return world > 1 and shard.world > 1 and self._gather_mode() == "local"
+
+    def _feature_bounds(self, shard: ShardMap):
+        """Column boundaries of the blocks inside a gathered (global) or local per-feature result."""
+        if self._local_attrs(shard):
+            return np.asarray(shard.block_off)
+        return np.concatenate(([0], np.cumsum(shard.sizes)))
 
     def _features_T(self, t_local: torch.Tensor, shard: ShardMap, split: bool):
-        """Component-major K x p_local device result -> the reference's layout: one p_global x K numpy array, or (split)
-        the list of per-block p_b x K arrays.  The transposition runs on the device, so the host only receives
-        contiguous copies (the strided numpy transposes of five 160 MB arrays cost 0.4 s at the headline size)."""
+        """Component-major K x p_local device result -> the reference's layout: one p x K numpy array, or (split) the list
+        of per-block p_b x K arrays (p = all features, or this rank's in "local" gather mode).  The transposition runs on the
+        device and the copies land in pinned memory (engine.to_host)."""
         full = self._gather_features_dev(t_local, shard)
         if not split:
-            return full.t().contiguous().cpu().numpy()
-        bounds = np.concatenate(([0], np.cumsum(shard.sizes)))
-        return [full[:, int(bounds[b]):int(bounds[b + 1])].t().contiguous().cpu().numpy() for b in range(len(shard.sizes))]
+            return E.to_host(full, transpose=True)
+        bounds = self._feature_bounds(shard)
+        return [E.to_host(full[:, int(bounds[b]):int(bounds[b + 1])], transpose=True) for b in range(len(shard.sizes))]
 
     def _gather_samples(self, t: torch.Tensor, n_local: int) -> np.ndarray:
         """K x ld device tensor of per-sample results -> n x K numpy array; concatenates the row shards when the
         sample axis is sharded (row-sharded KERNEL fit), plain copy otherwise."""
         rows = self.__dict__.get("_rows")
         if rows is None:
-            return np.ascontiguousarray(t[:, :n_local].cpu().numpy().T)
+            return E.to_host(t[:, :n_local], transpose=True)
         import torch.distributed as dist
         group, counts = rows
         K, mx = t.shape[0], max(counts)
@@ -204,7 +231,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         parts = [torch.empty_like(pad) for _ in counts]
         dist.all_gather(parts, pad, group=group)
         full = torch.cat([pt[:, :c] for pt, c in zip(parts, counts)], dim=1)
-        return np.ascontiguousarray(full.cpu().numpy().T)
+        return E.to_host(full, transpose=True)
 
     # ------------------------------------------------------------------ NaN census (mbpls.py:255-271)
     def check_sparsity_level(self, data):
@@ -271,6 +298,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_dev"] = None
         self.__dict__["_dev_scalers"] = None
         self.__dict__["_rows"] = None
+        self.__dict__["_attrs_local_sizes"] = None
         for name in _LAZY_NAMES:  # results of an earlier fit must not shadow the lazily materialised ones of this fit
             self.__dict__.pop(name, None)
 
@@ -284,6 +312,16 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                     self._materialize_all()
                 return self
 
+        import time as _time
+        tm = rt["timings"]
+
+        def mark(name, _t=[_time.perf_counter()]):
+            if tm is not None:
+                torch.cuda.synchronize(device)
+                now = _time.perf_counter()
+                tm[name] = tm.get(name, 0.0) + now - _t[0]
+                _t[0] = now
+
         with torch.cuda.device(device):
             # ---- Y (mbpls.py:293-298)
             Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
@@ -296,9 +334,11 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             Xt, n_x, shard = self._ingest(X, n, None, device, adopt=not self.copy)
             B = len(shard.sizes)
             ld = Xt.shape[1]
+            self.__dict__["_attrs_local_sizes"] = tuple(shard.sizes) if self._local_attrs(shard) else None
             Yt = E.alloc_feature_major(q, n, device)
             E.ingest_feature_major(Ysrc, n, 0, q, Yt, device)
             boff_dev = E._i32(shard.block_off, device)
+            mark("ingest")
 
             row_flag = ycol_flag = None
             if sparse:
@@ -330,6 +370,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 zss = xs.zss
                 self.__dict__["_dev_scalers"] = (xs.mean[:shard.p_local], xs.scale[:shard.p_local], ys.mean[:q], ys.scale[:q])
             self.num_blocks_ = B
+            mark("standardize")
 
             if self.method == 'NIPALS':
                 self._fit_nipals(Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device)
@@ -338,8 +379,10 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 crossmethods.fit(self, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
             if pre_lazy:
                 self.__dict__["_lazy"].update(pre_lazy)
+            mark("solve")
         if rt["materialize"]:
             self._materialize_all()
+            mark("materialize")
         return self
 
     # ---- KERNEL with n >= p on several GPUs: shard the SAMPLE axis
@@ -437,7 +480,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         ycol_nan, yrow_flag, yinf = E.nan_census(Yt, n, one, 1)
         self._raise_if_any_rank(bool(xinf.item()) or bool(yinf.item()),
                                 "Input contains infinity or a value too large for dtype('float64').", group)
-        col_full = self._gather_features(col_nan.view(1, -1).to(F64), shard)[0] > 0
+        col_full = self._gather_features(col_nan.view(1, -1).to(F64), shard, force_all=True)[0] > 0  # census lists global columns
         rows = row_flag[:, :n].cpu().numpy().astype(bool)
         self.sparse_Y_info_ = {'Y': self._census_from_flags(yrow_flag[0, :n].cpu().numpy().astype(bool),
                                                             (ycol_nan[:q] > 0).cpu().numpy())}
@@ -461,11 +504,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 var = self._gather_features(xs.var.view(1, -1), shard)[0]
                 scale = self._gather_features(xs.scale.view(1, -1), shard)[0]
                 seen = self._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
-                xsc, g0 = [], 0
-                for pb in shard.sizes:
-                    xsc.append(_make_scaler(mean[g0:g0 + pb], var[g0:g0 + pb], scale[g0:g0 + pb], seen[g0:g0 + pb]))
-                    g0 += pb
-                box["x"] = xsc
+                bounds = self._feature_bounds(shard)
+                box["x"] = [_make_scaler(mean[a:b], var[a:b], scale[a:b], seen[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
                 box["y"] = _make_scaler(ys.mean[:q].cpu().numpy(), ys.var[:q].cpu().numpy(), ys.scale[:q].cpu().numpy(),
                                         ys.seen[:q].cpu().numpy())
             return box
@@ -507,7 +547,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
-                           one_pass_deflate=rt["one_pass_deflate"], deflate_rec=rt["deflate_rec"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
+                           one_pass_deflate=rt["one_pass_deflate"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
         self.n_iter_ = list(res.n_iter)
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
@@ -540,10 +580,10 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.W_concat_ = np.empty((shard.p_global, 0))
 
         lazy = {
-            "Ts_": lambda: np.ascontiguousarray(res.Ts[:, :n].cpu().numpy().T),
-            "U_": lambda: np.ascontiguousarray(res.U[:, :n].cpu().numpy().T),
-            "V_": lambda: np.ascontiguousarray(res.V[:, :q].cpu().numpy().T),
-            "T_": lambda: [np.ascontiguousarray(res.Tb[b, :, :n].cpu().numpy().T) for b in range(B)],
+            "Ts_": lambda: E.to_host(res.Ts[:, :n], transpose=True),
+            "U_": lambda: E.to_host(res.U[:, :n], transpose=True),
+            "V_": lambda: E.to_host(res.V[:, :q], transpose=True),
+            "T_": lambda: [E.to_host(res.Tb[b, :, :n], transpose=True) for b in range(B)],
             "W_": lambda: self._features_T(res.W, shard, True),
             "W_non_normal_": lambda: self._features_T(res.Wt, shard, True),
             "P_": lambda: self._features_T(res.P, shard, True),
@@ -568,11 +608,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         if self.__dict__.get("_rows") is not None:
             rank, world = 0, 1
         P_ = self.P_
-        sizes = [int(pb.shape[0]) for pb in P_]
-        shard = ShardMap.build(sizes, rank, world)
+        local = self.__dict__.get("_attrs_local_sizes")  # attributes hold this rank's rows only: (global block sizes)
+        if local is not None:
+            shard = ShardMap.build(list(local), rank, world)
+            if [int(pb.shape[0]) for pb in P_] != [c1 - c0 for c0, c1 in shard.local_ranges]:
+                raise ValueError("this model holds rank-local attributes of a different rank / world size")
+        else:
+            shard = ShardMap.build([int(pb.shape[0]) for pb in P_], rank, world)
 
-        def up(full_pk):  # p_global x K numpy -> K x p_local device
-            return torch.from_numpy(np.ascontiguousarray(full_pk[shard.lo:shard.hi].T)).to(device)
+        def up(full_pk):  # p x K numpy (global, or already this rank's rows) -> K x p_local device
+            rows = full_pk if local is not None else full_pk[shard.lo:shard.hi]
+            return torch.from_numpy(np.ascontiguousarray(rows.T)).to(device)
 
         dev = dict(shard=shard, R=up(self.R_), beta=up(self.beta_), P=up(np.concatenate(P_, axis=0)),
                    V=torch.from_numpy(np.ascontiguousarray(self.V_.T)).to(device))
@@ -585,8 +631,10 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         sc = self.__dict__.get("_dev_scalers")
         if sc is not None and sc[0].device == device:
             return sc
-        mean = np.concatenate([np.atleast_1d(s.mean_) for s in self.x_scalers_])[shard.lo:shard.hi]
-        scale = np.concatenate([np.atleast_1d(s.scale_) for s in self.x_scalers_])[shard.lo:shard.hi]
+        mean = np.concatenate([np.atleast_1d(s.mean_) for s in self.x_scalers_])
+        scale = np.concatenate([np.atleast_1d(s.scale_) for s in self.x_scalers_])
+        if self.__dict__.get("_attrs_local_sizes") is None:
+            mean, scale = mean[shard.lo:shard.hi], scale[shard.lo:shard.hi]
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
         sc = (t(mean), t(scale), t(np.atleast_1d(self.y_scaler_.mean_)), t(np.atleast_1d(self.y_scaler_.scale_)))
         self.__dict__["_dev_scalers"] = sc
@@ -630,7 +678,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             if self.standardize:
                 _, _, ymean, yscale = self._device_scalers(shard, device)
                 call("mbpls_scaler_inverse_f64", ptr(Yh), Yh.shape[1], m, q, ptr(ymean), ptr(yscale), stream_ptr(device))
-            return np.ascontiguousarray(Yh[:, :m].cpu().numpy().T)
+            return E.to_host(Yh[:, :m], transpose=True)
 
     def transform(self, X, Y=None, return_block_scores=False, copy=True):
         """Superscores (and block scores / Y scores) of new data (mbpls.py:1052-1335)."""
@@ -649,7 +697,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             flag = torch.zeros(1, dtype=torch.int32, device=device)
             Ts_dev = E.skinny_gemm(Xt, m, dev["R"], shard.block_off, group, mean, scale, flag)  # K x ld   (:1110-1117)
             self._check_flag(flag, group)
-            Ts = np.ascontiguousarray(Ts_dev[:, :m].cpu().numpy().T)
+            Ts = E.to_host(Ts_dev[:, :m], transpose=True)
             out = [Ts]
             if want_blocks and not self.sparse_data:
                 # Dense data: the K sequential deflations of :1131-1155 collapse to one product and a K x K
@@ -665,7 +713,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                     Cb = torch.triu(E.gram(Pb, Wb, o1 - o0, group), diagonal=1).contiguous()  # striu(P_b' W_b)
                     cols = [CM.lincomb_sub(full[k].contiguous(), Ts_dev, k, Cb[:k, k].contiguous(), m)[:m] if k > 0
                             else full[0, :m] for k in range(K)]
-                    T.append(np.ascontiguousarray(torch.stack(cols, dim=1).cpu().numpy()))
+                    T.append(E.to_host(torch.stack(cols, dim=1)))
                 out.append(T)
             elif want_blocks:  # NaN mode: sequential deflation, NaNs stay NaN and count as zero (:1126-1155)
                 B = len(shard.sizes)
@@ -680,7 +728,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                                  ptr(dev["P"][k - 1, o0:o1]), stream_ptr(device))
                         tk = E.skinny_gemm(Xb, m, dev["W"][k:k + 1, o0:o1], [0, o1 - o0], group)
                         cols.append(tk[0, :m])
-                    T.append(np.ascontiguousarray(torch.stack(cols, dim=1).cpu().numpy()))
+                    T.append(E.to_host(torch.stack(cols, dim=1)))
                 out.append(T)
             if Y is not None:  # :1119-1125, :1156-1166
                 Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
@@ -698,7 +746,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                 self._check_flag(yflag, None)
                 nrm = torch.sqrt(E.rows_sumsq(Ur, m))
                 call("mbpls_rows_scale_f64", ptr(Ur), Ur.shape[1], K, m, ptr(nrm), 1, stream_ptr(device))
-                out.append(np.ascontiguousarray(Ur[:, :m].cpu().numpy().T))
+                out.append(E.to_host(Ur[:, :m], transpose=True))
         return out[0] if len(out) == 1 else tuple(out)
 
     # ------------------------------------------------------------------ convenience (mbpls.py:1412-1437)

@@ -16,8 +16,7 @@ args = [a for a in args if not a.startswith("v=")]
 which = set(a for a in args if not a.replace(".", "").isdigit()) or {"dense", "nan", "c3"}
 
 VARIANTS = (("two-pass", dict(one_pass=False)), ("one-pass trip", dict(one_pass=True, one_pass_deflate=False)),
-            ("one-pass trip+deflate", dict(one_pass=True, deflate_rec=False)),
-            ("one-pass trip+deflate(rec)", dict(one_pass=True, deflate_rec=True)))
+            ("one-pass trip+deflate", dict(one_pass=True)))
 if only:
     VARIANTS = tuple(v for v in VARIANTS if v[0] in only)
 MULT = {"colden": 1.0 / 64, "rowden": 1.0 / 64, "trip": 1.0, "xtu": 1.0, "xw": 1.0, "deflate": 2.0, "loadings": 1.0, "standardize": 2.0}

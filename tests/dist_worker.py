@@ -39,7 +39,19 @@ def gpu_checks(group, rank, world, dev):
             warnings.simplefilter("ignore")
             m2 = MBPLS(**kw).set_runtime(group=group, device=dev, global_sizes=list(sizes))
             m2.fit(local, Y.copy())
-        assert np.allclose(m2.beta_, m.beta_, rtol=1e-11, atol=1e-14), "pre-sharded fit differs"
+        # a rank that passed its own column ranges gets their per-feature attributes back ("local" gather: no all-gather of
+        # p x K matrices, no redundant device->host copies); per-sample attributes are complete on every rank
+        assert m2.beta_.shape[0] == sh.p_local and np.allclose(m2.beta_, m.beta_[sh.lo:sh.hi], rtol=1e-11, atol=1e-14)
+        for b, (c0, c1) in enumerate(sh.local_ranges):
+            assert m2.P_[b].shape == (c1 - c0, 4) and np.allclose(m2.P_[b], m.P_[b][c0:c1], rtol=1e-10, atol=1e-13)
+            assert np.allclose(m2.x_scalers_[b].mean_, m.x_scalers_[b].mean_[c0:c1], rtol=1e-13, atol=1e-15)
+        assert np.allclose(m2.Ts_, m.Ts_, rtol=1e-10, atol=1e-13)
+        assert np.allclose(m2.predict([xt[:, c0:c1] for xt, (c0, c1) in zip(Xt, sh.local_ranges)]), m.predict(Xt), rtol=1e-9, atol=1e-12)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m3 = MBPLS(**kw).set_runtime(group=group, device=dev, global_sizes=list(sizes), gather="all")
+            m3.fit(local, Y.copy())
+        assert np.allclose(m3.beta_, m.beta_, rtol=1e-11, atol=1e-14), "pre-sharded fit with gather='all' differs"
         print(f"rank {rank}: world={world} nan={nan_frac} n={n} trips={m.n_iter_} worst={worst}", flush=True)
     # the other methods under the same feature sharding (KERNEL: the p > n branch; n >= p needs row sharding)
     # KERNEL n=1201 >= p=800 takes the row-sharded path (samples split over the ranks, p x p all-reduce)

@@ -91,12 +91,11 @@ def test_one_pass_agrees_with_two_pass_kernels(nan_frac):
     fits = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        for name, rt in (("one", dict(one_pass=True, deflate_rec=False)), ("two", dict(one_pass=False)),
-                         ("trip_only", dict(one_pass=True, one_pass_deflate=False)),
-                         ("rec", dict(one_pass=True, deflate_rec=True))):
+        for name, rt in (("one", dict(one_pass=True)), ("two", dict(one_pass=False)),
+                         ("trip_only", dict(one_pass=True, one_pass_deflate=False))):
             fits[name] = MBPLS(**kw).set_runtime(**rt).fit([x.copy() for x in X], Y.copy())
     ref = fits["two"]
-    for name in ("one", "trip_only", "rec"):
+    for name in ("one", "trip_only"):
         m = fits[name]
         assert list(m.n_iter_) == list(ref.n_iter_), (name, m.n_iter_, ref.n_iter_)
         assert rel_err(m.beta_, ref.beta_) < 1e-10
@@ -134,31 +133,13 @@ def test_one_pass_rejects_long_features():
     assert m.beta_.shape == (6, 1)
 
 
-@pytest.mark.parametrize("n,sizes,nan_frac", [(37, (21, 40), 0.0), (1300, (64, 48, 9), 0.0), (2570, (75, 30), 0.0),
-                                              (5200, (50, 45), 0.0), (10000, (40, 56), 0.0), (2000, (48, 40), 0.1),
-                                              (9000, (24, 30), 0.1)])
-def test_recurrence_deflation_matches_oracle(n, sizes, nan_frac):
-    """Deflation pass that carries x_j . u0 per feature across the components instead of keeping u0 resident."""
+def test_deep_pls1_fit_keeps_two_trips_per_component():
+    """19 components of a PLS1 fit: the exact deflation (next weights from the rounded, deflated feature, like the
+    reference) takes exactly the reference's two trips per component all the way down."""
     from oracle.cases import latent_blocks
-    X, Y = latent_blocks(n, sizes, 2, 4, seed=3 + n % 83, nan_frac=nan_frac)
-    kw = dict(n_components=4, method="NIPALS", sparse_data=nan_frac > 0)
-    m, o = _pair(kw, X, Y, one_pass=True, deflate_rec=True)
-    _check(m, o, X, Y, kw, f"recurrence deflation n={n} nan={nan_frac}")
-
-
-def test_recurrence_deflation_on_long_fits():
-    """More components than the refresh period of the carried x_j . u0 (engine._REC_REFRESH).  The default (exact) deflation
-    takes exactly the reference's two trips per PLS1 component; the opt-in recurrence variant matches every attribute to 1e-8
-    but may need one more trip in late components (its first-trip weights are noisier, see engine._DEFLATE_REC_DEFAULT)."""
-    from oracle.cases import latent_blocks
-    from mbpls_b200 import engine
-    K = engine._REC_REFRESH + 3
+    K = 19
     X, Y = latent_blocks(260, (70, 45), 1, K, seed=17, decay=0.9)
     kw = dict(n_components=K, method="NIPALS")
     m, o = _pair(kw, X, Y.ravel(), one_pass=True)
     _check(m, o, X, Y.ravel(), kw, "exact deflation, long fit")
     assert list(m.n_iter_) == [2] * K == list(o.n_iter_)
-    r, _ = _pair(kw, X, Y.ravel(), one_pass=True, deflate_rec=True)
-    ref, ours = snapshot_model(o, [x.copy() for x in X], Y.ravel().copy()), snapshot_model(r, [x.copy() for x in X], Y.ravel().copy())
-    compare(ours, ref, TOL, "recurrence deflation, long fit")
-    assert all(2 <= t <= 3 for t in r.n_iter_), r.n_iter_
