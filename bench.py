@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--two-pass", action="store_true", help="force the two-pass NIPALS kernels (X'u and X w as separate reads)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-p", type=int, default=0, help="features of the CPU sample (0: auto)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (C2 / C3 q=10 / C5) reported under `configs`")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity gate (GPU fit vs numpy oracle on a column slice)")
     ap.add_argument("--parity-features", type=int, default=1024, help="features per block of the dense parity slice (NaN slice: a quarter)")
     ap.add_argument("--seed", type=int, default=20261017)
@@ -287,6 +288,216 @@ def parity_gate(args, dev, group, rank, world, nan_frac, feats_per_block):
     del m, Xl
     if world > 1:
         dist.barrier(group=group)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, measured in the same run (reported under `configs`)
+# ------------------------------------------------------------------------------------------------
+def fp64_peaks(dev):
+    """cuBLAS DGEMM and DSYRK rates on this GPU (8192^3, best of 3): the FP64 roofline SURVEY.md 8(d) asks to measure once
+    per box.  DSYRK is credited n^2 k flops (the executed half)."""
+    import ctypes
+    import glob
+    import torch
+    N = 8192
+    A = torch.randn((N, N), dtype=torch.float64, device=dev)
+    out = {}
+
+    def best(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    ms = best(lambda: torch.matmul(A, A.t()))
+    out["dgemm_tflops"] = 2.0 * N ** 3 / ms / 1e9
+    try:
+        libs = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cublas", "lib", "libcublas.so*")) + \
+            glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcublas.so*")) + ["libcublas.so.12"]
+        lib = None
+        for path in libs:
+            try:
+                lib = ctypes.CDLL(path)
+                break
+            except OSError:
+                continue
+        Cm = torch.zeros((N, N), dtype=torch.float64, device=dev)
+        one, zero = ctypes.c_double(1.0), ctypes.c_double(0.0)
+        handle = ctypes.c_void_p(torch.cuda.current_blas_handle())
+        lib.cublasDsyrk_v2.restype = ctypes.c_int
+        lib.cublasDsyrk_v2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+
+        def syrk():  # C = A A' (column-major view of the same buffer), upper triangle
+            rc = lib.cublasDsyrk_v2(handle, 1, 0, N, N, ctypes.byref(one), ctypes.c_void_p(A.data_ptr()), N, ctypes.byref(zero),
+                                    ctypes.c_void_p(Cm.data_ptr()), N)
+            if rc != 0:
+                raise RuntimeError(f"cublasDsyrk status {rc}")
+        ms = best(syrk)
+        out["dsyrk_tflops_executed"] = 1.0 * N ** 3 / ms / 1e9
+    except Exception as exc:  # the probe must never take the benchmark line down
+        out["dsyrk_error"] = repr(exc)[:160]
+    return out
+
+
+def run_configs(args, dev, group, rank, world, peak_gbs):
+    """BASELINE.json configs 2, 3 and 5 on device-generated data of their full size (fp64, same generator as the headline):
+    time, algorithmic bytes or flops, and the fraction of the measured HBM / FP64 peak.  N > 1: C3 and C2-SIMPLS shard the
+    feature axis, C5 KERNEL / UNIPALS shard the sample axis (p x p, resp. per-component p-vector all-reduces)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mbpls_b200 import MBPLS, synth
+    from mbpls_b200 import engine as E
+    out = {}
+    sc = args.scale
+
+    def sync_max(seconds):
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, reps=2):
+        best, res = None, None
+        for _ in range(reps):
+            prep = fn(None)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = fn(prep)
+            e1.record()
+            barrier()
+            dt = sync_max(e0.elapsed_time(e1) / 1e3)
+            best = dt if best is None else min(best, dt)
+        return best, res
+
+    peaks = fp64_peaks(dev) if rank == 0 else {}
+    out["fp64_peaks"] = peaks
+    fp64_peak = max(peaks.get("dgemm_tflops", 0.0), 1e-9)
+
+    # ---- C3: 8 uneven blocks, n = 2,000, Y n x 10 (the reference paper's own q, runtime_analysis_rowincrease.py:58), K = 20
+    n, K, q = 2000, 20, 10
+    sizes = [int(s * sc) for s in (20000, 35000, 60000, 95000, 140000, 180000, 220000, 450000)]
+    shard = E.ShardMap.build(sizes, rank, world)
+    ld = E.round_ld(n)
+    Xb = torch.empty((max(shard.p_local, 1), ld), dtype=torch.float64, device=dev)
+    Yd = synth.response(n, q, K, dev, args.seed + 3, decay=args.decay)
+
+    def c3(prep):
+        if prep is None:
+            synth.fill_feature_major(Xb, n, shard.lo, shard.hi, K, args.seed + 3, noise=args.noise, decay=args.decay)
+            return True
+        blocks = [Xb[shard.block_off[b]:shard.block_off[b + 1], :n].t() for b in range(len(sizes))]
+        prof = {}
+        m = MBPLS(n_components=K, method="NIPALS", copy=False).set_runtime(device=dev, group=group, materialize=False,
+                                                                           global_sizes=sizes, max_iter=2000, profile=prof).fit(blocks, Yd)
+        return m, prof
+
+    dt, (m, prof) = timed(c3)
+    trips = list(m.n_iter_)
+    p = sum(sizes)
+    passes = sum(len(prof.get(k, [])) * w for k, w in (("trip", 1), ("xtu", 1), ("xw", 1), ("deflate", 2), ("loadings", 1), ("standardize", 2)))
+    out["c3_pls2_q10_nipals"] = {
+        "workload": f"NIPALS n={n} p={p} blocks={sizes} q={q} K={K}", "fit_s": dt, "trips_per_component": trips, "trips_total": sum(trips),
+        "value": fit_bytes(n, p, K, trips) / dt / 1e9, "unit": "GB/s (canonical two-pass bytes)",
+        "hbm_gbs_actual_traffic": passes * 8.0 * n * p / dt / 1e9, "frac_of_hbm_peak_actual_traffic": passes * 8.0 * n * p / dt / 1e9 / (peak_gbs * world),
+        "ms_per_trip": dt / max(sum(trips), 1) * 1e3}
+    del m, Xb
+
+    # ---- C2: single-block PLS1, n = 5,000 x p = 50,000, K = 10: KERNEL (P > N: XX' on the FP64 tensor cores) and SIMPLS
+    n, K, q = 5000, 10, 1
+    sizes = [int(50000 * sc)]
+    p = sizes[0]
+    shard = E.ShardMap.build(sizes, rank, world)
+    ld = E.round_ld(n)
+    Xb = torch.empty((max(shard.p_local, 1), ld), dtype=torch.float64, device=dev)
+    Yd = synth.response(n, q, K, dev, args.seed + 2, decay=args.decay)
+    for method in ("KERNEL", "SIMPLS"):
+        def c2(prep, method=method):
+            if prep is None:
+                synth.fill_feature_major(Xb, n, shard.lo, shard.hi, K, args.seed + 2, noise=args.noise, decay=args.decay)
+                return True
+            blocks = [Xb[:shard.p_local, :n].t()]
+            return MBPLS(n_components=K, method=method, copy=False, full_svd=True).set_runtime(
+                device=dev, group=group, materialize=False, global_sizes=sizes).fit(blocks, Yd)
+        dt, m = timed(c2)
+        ent = {"workload": f"{method} PLS1 n={n} p={p} K={K} calc_all=True", "fit_s": dt}
+        if method == "KERNEL":
+            flops = 2.0 * n * n * p  # XX' as a GEMM; the symmetric kernel executes half
+            ent.update({"crossproduct_flops_as_gemm": flops, "tflops_whole_fit_as_gemm": flops / dt / 1e12,
+                        "frac_of_measured_dgemm_whole_fit": flops / dt / 1e12 / (fp64_peak * world) if peaks else None,
+                        "note": "whole fit (cross product + K rank-2 deflations of the n x n matrix + calc_all passes) over the GEMM-credited flops"})
+        else:
+            bts = 8.0 * n * p * (1 + 2 * K)
+            ent.update({"algorithmic_bytes": bts, "value": bts / dt / 1e9, "unit": "GB/s", "frac_of_hbm_peak": bts / dt / 1e9 / (peak_gbs * world)})
+        out[f"c2_pls1_{method.lower()}"] = ent
+        del m
+    del Xb
+
+    # ---- C5: tall n = 1,000,000 x p = 2,000 (2 blocks), q = 4, K = 30: KERNEL and UNIPALS (n >> p), then batched predict
+    n, K, q = int(1_000_000 * sc), 30, 4
+    sizes = [1000, 1000]
+    p = sum(sizes)
+    ld = E.round_ld(n)
+    Xb = torch.empty((p, ld), dtype=torch.float64, device=dev)  # N > 1: every rank generates the matrix and ingests its rows
+    Yd = synth.response(n, q, K, dev, args.seed + 5, decay=0.9)
+    model = None
+    for method in ("KERNEL", "UNIPALS"):
+        def c5(prep, method=method):
+            if prep is None:
+                synth.fill_feature_major(Xb, n, 0, p, K, args.seed + 5, noise=args.noise, decay=0.9)
+                return True
+            blocks = [Xb[:1000, :n].t(), Xb[1000:, :n].t()]
+            return MBPLS(n_components=K, method=method, copy=world > 1, full_svd=True, calc_all=False).set_runtime(
+                device=dev, group=group, materialize=False).fit(blocks, Yd)
+        dt, m = timed(c5, reps=2 if method == "KERNEL" else 1)
+        ent = {"workload": f"{method} n={n} p={p} (2 blocks) q={q} K={K} calc_all=False; " +
+                           ("sample axis sharded over the ranks" if world > 1 else "one GPU"), "fit_s": dt}
+        if method == "KERNEL":
+            flops = 2.0 * n * p * p
+            ent.update({"crossproduct_flops_as_gemm": flops, "tflops_whole_fit_as_gemm": flops / dt / 1e12,
+                        "frac_of_measured_dgemm_whole_fit": flops / dt / 1e12 / (fp64_peak * world) if peaks else None})
+            model = m
+        else:
+            bts = 8.0 * n * p * (1 + 4 * K)  # standardise + per component: X'Y, X w, X'ts (reads) and the deflation (R+W) ~ 5, fused: 4
+            ent.update({"x_bytes": 8.0 * n * p, "seconds_per_component": dt / K,
+                        "x_passes_per_component_equivalent": dt / K / (8.0 * n * p / (peak_gbs * 1e9 * world)),
+                        "note": "x_passes_per_component_equivalent = time per component / time of one read of X at the measured HBM peak"})
+        out[f"c5_tall_{method.lower()}"] = ent
+        if method != "KERNEL":
+            del m
+    # batched predict on a fresh tall batch (device-resident feature-major input, numpy output)
+    synth.fill_feature_major(Xb, n, 0, p, K, args.seed + 6, noise=args.noise, decay=0.9)
+    blocks = [Xb[:1000, :n].t(), Xb[1000:, :n].t()]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.predict(blocks)
+        barrier()
+        t0 = time.perf_counter()
+        yh = model.predict(blocks)
+        torch.cuda.synchronize(dev)
+        dt = sync_max(time.perf_counter() - t0)
+    out["c5_predict"] = {"workload": f"predict {n} x {p} -> {tuple(yh.shape)} (replicated model, every rank predicts the whole batch)",
+                         "predict_s": dt, "rows_per_s": n / dt, "value": 8.0 * n * p / dt / 1e9, "unit": "GB/s",
+                         "frac_of_hbm_peak": 8.0 * n * p / dt / 1e9 / peak_gbs}
+    del model, Xb, yh
+    torch.cuda.empty_cache()
     return out
 
 
@@ -554,6 +765,20 @@ def run_ours(args):
         else:
             e2e = {"value": None, "unit": "GB/s", "skipped": "host RAM too small for the full-size input"}
 
+    configs = None
+    if not args.no_configs:
+        try:
+            del Xbuf
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        log("other BASELINE configurations")
+        try:
+            configs = run_configs(args, dev, group, rank, world, peak_gbs)
+        except Exception as exc:  # secondary measurements must not take the headline line down
+            configs = {"error": repr(exc)[:300]}
+        log("configs", configs)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         p_cpu = cpu_p_for_budget(args, 30.0)
@@ -576,7 +801,7 @@ def run_ours(args):
             "config": workload_config(args), "trips_per_component": trips, "algorithmic_bytes_per_step": fit_bytes(n, p, K, trips),
             "frac_of_hbm_peak": value / (peak_gbs * world),
             "frac_of_hbm_peak_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9 / (peak_gbs * world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "parity": parity, "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
+            "parity": parity, "configs": configs, "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
             "passes_over_X_per_step": passes, "hbm_gbs_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9,
         }
         print(json.dumps(line), flush=True)

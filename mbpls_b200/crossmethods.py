@@ -215,15 +215,33 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
 
 
 # ---- UNIPALS (mbpls.py:384-574) ------------------------------------------------------------------
-def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
+def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_group=None, n_global=None):
+    """group: the FEATURE axis is sharded over it (contractions over p are all-reduced).  rows_group: the SAMPLE axis is
+    sharded instead (n >= p): Xt / Yt hold this rank's n rows of all features; per component the sums
+    over samples -- X'Y (p x q), Y'ts (q), X'ts (p) and the two squared norms -- are all-reduced, everything indexed by
+    features is replicated and everything indexed by samples (block scores, ts, u, the deflation) stays row-local."""
     K, B = int(model.n_components), len(shard.sizes)
     p, ld = Xt.shape
     pg = shard.p_global
+    rg = rows_group
+    ng = n if n_global is None else n_global
+    if rg is not None and (group is not None or ng < pg):
+        raise NotImplementedError("row-sharded UNIPALS covers n >= p with a replicated feature axis")
+
+    def normalize_rows_(t):  # unit norm over the *global* sample axis
+        if rg is None:
+            return normalize_(t, n)
+        nrm = torch.sqrt(E.rows_sumsq(t.view(1, -1), n, rg))
+        scale_rows_(t.view(1, -1), n, nrm, True)
+        return nrm
+
     blockprod = BlockProducts(Xt, n, shard.block_off, group)
     if zss is None:
         zss = E.feature_sumsq(Xt, n)
-    varxb = model._block_sums(zss, boff_dev, B, group)
-    vary = float(E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).item())
+    varxb = model._block_sums(zss, boff_dev, B, group if rg is None else rg)
+    vary_t = E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).clone()
+    E.allreduce_(vary_t, rg)
+    vary = float(vary_t.item())
     Wc = torch.zeros((K, max(p, 1)), dtype=F64, device=device)   # eigenv columns ("weights")
     Wb = torch.zeros((K, max(p, 1)), dtype=F64, device=device)   # block-normalised
     P = torch.zeros((K, max(p, 1)), dtype=F64, device=device)
@@ -238,18 +256,19 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
     vv_dev = torch.zeros(K, dtype=F64, device=device)
     for k in range(K):
         Ct = xt_multi(Xt, n, Yt).contiguous()  # (X'Y)' from the *deflated* X (:396 / :489)
-        if n >= pg:  # :388-424
+        E.allreduce_(Ct, rg)
+        if ng >= pg:  # :388-424
             c = E.small_top_eigvec(E.gram(Ct, Ct, p, group))
             w = E.right_multiply(Ct, p, None, c.view(q, 1))[0].contiguous()
             normalize_over_features_(w, p, group)
             raw = blockprod(w)  # X_b w (un-normalised block part)
             ts = sum_rows(raw, ld)  # X w (:416)
-            normalize_(ts, n)
-            tt = E.rows_sumsq(ts.view(1, -1), n)
-            v = E.gram(Yt, ts.view(1, -1), n)[:, 0].contiguous()
+            normalize_rows_(ts)
+            tt = E.rows_sumsq(ts.view(1, -1), n, rg)
+            v = E.gram(Yt, ts.view(1, -1), n, rg)[:, 0].contiguous()
             scale_rows_(v.view(1, -1), q, tt, True)  # v = Y'ts / ts'ts (:420)
             u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # :423-424
-            normalize_(u, n)
+            normalize_rows_(u)
         else:  # :481-517
             At = E.skinny_gemm(Xt, n, Ct, shard.block_off, group)  # (X X'Y)' : q x ld
             c = E.small_top_sv_product(GY, E.gram(At, At, n))
@@ -268,6 +287,9 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
         tb = raw.clone()
         scale_rows_(tb, n, torch.sqrt(a), True)  # t_b = X_b w_b (:410-413)
         pv = xt_vec(Xt, n, ts, boff_dev, B, uu=tt)  # p = X'ts / ts'ts (:427)
+        if rg is not None:
+            pv = pv.contiguous()
+            E.allreduce_(pv, rg)
         pss_dev[k] = block_sumsq(pv, boff_dev, B, group)
         tt_dev[k:k + 1] = tt
         vv_dev[k:k + 1] = E.rows_sumsq(v.view(1, -1), q)

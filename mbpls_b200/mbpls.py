@@ -302,7 +302,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         for name in _LAZY_NAMES:  # results of an earlier fit must not shadow the lazily materialised ones of this fit
             self.__dict__.pop(name, None)
 
-        if self.method == 'KERNEL' and world > 1:
+        if self.method in ('KERNEL', 'UNIPALS') and world > 1:
             blocks0 = X if _is_block_list(X) else [X]
             n0, p0 = int(_shape2(blocks0[0])[0]), sum(int(_shape2(b)[1]) for b in blocks0)
             if n0 >= p0 and rt["global_sizes"] is None:
@@ -385,10 +385,11 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             mark("materialize")
         return self
 
-    # ---- KERNEL with n >= p on several GPUs: shard the SAMPLE axis
+    # ---- KERNEL / UNIPALS with n >= p on several GPUs: shard the SAMPLE axis
     def _fit_kernel_row_sharded(self, X, Y, group, rank, world, device):
-        """Every rank ingests its contiguous range of samples of all blocks; column statistics and the p x p / p x q
-        cross-products are all-reduced; the per-component p x p loop runs replicated; scores stay row-local."""
+        """Every rank ingests its contiguous range of samples of all blocks; column statistics and the sums over samples
+        (KERNEL: the p x p / p x q cross-products, once; UNIPALS: X'Y, X'ts and Y'ts per component) are all-reduced;
+        everything indexed by features runs replicated; scores stay row-local."""
         from . import crossmethods as CM
         blocks = X if _is_block_list(X) else [X]
         blocks = [_as_2d_source(b, "X") for b in blocks]
@@ -451,7 +452,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             self.y_scaler_ = _make_scaler(ym.cpu().numpy(), yv.cpu().numpy(), ys.cpu().numpy(), np.full(q, n, dtype=np.int64))
             self.__dict__["_dev_scalers"] = (xm, xs, ym, ys)
         self.num_blocks_ = B
-        CM._fit_kernel(self, Xt, Yt, nl, q, shard, boff_dev, zss, None, device, rows_group=group, n_global=n)
+        fit_rows = CM._fit_kernel if self.method == 'KERNEL' else CM._fit_unipals
+        fit_rows(self, Xt, Yt, nl, q, shard, boff_dev, zss, None, device, rows_group=group, n_global=n)
 
     # ---- helpers of fit
     def _raise_if_any_rank(self, bad: bool, msg: str, group):

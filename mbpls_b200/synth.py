@@ -43,17 +43,19 @@ def fill_feature_major(Xt: torch.Tensor, n: int, g_lo: int, g_hi: int, K: int, s
     r = Z.shape[1]
     s = decay ** torch.arange(r, dtype=torch.float64, device=device)
     Zs_t = (Z * s).t().contiguous()  # r x n
-    c = (g_lo // CHUNK) * CHUNK
+    # features per generator chunk: 4096, fewer for very long features so that a chunk's temporaries stay near 1 GB
+    chunk = CHUNK if n <= 32768 else max(64, CHUNK * 32768 // n)
+    c = (g_lo // chunk) * chunk
     while c < g_hi:
-        g = _gen(device, seed * 1000003 + 17 + c // CHUNK)
-        L = torch.randn((CHUNK, r), dtype=torch.float64, device=device, generator=g)
-        E = torch.randn((CHUNK, n), dtype=torch.float64, device=device, generator=g)
-        blk = torch.addmm(E, L, Zs_t, beta=noise)  # CHUNK x n
+        g = _gen(device, seed * 1000003 + 17 + c // chunk)
+        L = torch.randn((chunk, r), dtype=torch.float64, device=device, generator=g)
+        E = torch.randn((chunk, n), dtype=torch.float64, device=device, generator=g)
+        blk = torch.addmm(E, L, Zs_t, beta=noise)  # chunk x n
         if nan_frac > 0:
-            m = torch.rand((CHUNK, n), dtype=torch.float32, device=device, generator=g) < nan_frac
+            m = torch.rand((chunk, n), dtype=torch.float32, device=device, generator=g) < nan_frac
             blk[m] = float("nan")
-        a, b = max(c, g_lo), min(c + CHUNK, g_hi)
+        a, b = max(c, g_lo), min(c + chunk, g_hi)
         Xt[a - g_lo:b - g_lo, :n] = blk[a - c:b - c]
-        c += CHUNK
+        c += chunk
     if Xt.shape[1] > n:
         Xt[:g_hi - g_lo, n:] = 0.0
