@@ -644,6 +644,7 @@ def run_ours(args):
                                  "trips_per_component": nt, "kernels": "one-pass kernels with NaN read as zero + masked denominators from the NaN bit matrix (DESIGN.md 3a)"}
         del nan_model
     trips = list(model.n_iter_)
+    exchange = model.__dict__.get("_exchange")
     ms_step = sum(times) / len(times)
     value = fit_bytes(n, p, K, trips) / (ms_step / 1e3) / 1e9
 
@@ -801,7 +802,7 @@ def run_ours(args):
             "config": workload_config(args), "trips_per_component": trips, "algorithmic_bytes_per_step": fit_bytes(n, p, K, trips),
             "frac_of_hbm_peak": value / (peak_gbs * world),
             "frac_of_hbm_peak_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9 / (peak_gbs * world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "parity": parity, "configs": configs, "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
+            "exchange": exchange, "parity": parity, "configs": configs, "gpu_launches": launches, "clocks": clk, "step_ms": times, "variants": variants, "rank_skew": rank_skew,
             "passes_over_X_per_step": passes, "hbm_gbs_actual_traffic": passes * 8.0 * n * p / (ms_step / 1e3) / 1e9,
         }
         print(json.dumps(line), flush=True)

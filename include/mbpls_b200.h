@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 8
+#define MBPLS_ABI_VERSION 9
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -36,6 +36,7 @@ extern "C" {
 #define MBPLS_SCAL_COUNT 8
 #define MBPLS_CTRL_DONE 0  /* 1 once diff_t <= max_tol (mbpls.py:841) */
 #define MBPLS_CTRL_TRIPS 1 /* completed trips of the while loop for this component */
+#define MBPLS_CTRL_ERROR 2 /* sticky: a peer GPU did not arrive at an in-kernel exchange (mbpls_nipals_xchg_epilogue_f64) */
 #define MBPLS_CTRL_COUNT 4
 
 /* nipals_convergence_norm: matrix-norm semantics of np.linalg.norm on an n x 1 array (mbpls.py:887) */
@@ -126,6 +127,30 @@ typedef struct mbpls_epilogue_args {
 } mbpls_epilogue_args;
 /* `args` is a HOST pointer; the struct is passed to the kernel by value. */
 int mbpls_nipals_epilogue_f64(const mbpls_epilogue_args* args_host, void* stream);
+
+/* reduce_partials + exchange between the GPUs + epilogue as ONE kernel (csrc/nipals.cu xchg_epilogue_kernel).
+ * world == 1: the split partials are summed straight into epi.red and the last CTA runs the epilogue.
+ * world > 1 (features sharded): peer_bufs is a DEVICE array of `world` addresses, entry r = rank r's symmetric buffer as
+ * mapped into this process (peer memory over NVLink; torch.distributed._symmetric_memory hands out such arrays).  A buffer
+ * holds 2 slots of slot_elems doubles followed, at flags_off doubles, by `world` 8-byte flag words (zero before the first
+ * call).  seq > 0 must grow by one per call and be the same on every rank; every rank must make the same calls.  The sums
+ * over the GPUs are formed in rank order on every GPU, i.e. bit-identical everywhere (replaces ncclAllReduce of epi.red,
+ * SURVEY.md 8e).  counters: 2 zeroed unsigned ints in local memory.  On a peer timeout ctrl[MBPLS_CTRL_ERROR] is set. */
+typedef struct mbpls_xchg_args {
+  mbpls_epilogue_args epi;
+  const double* Tnum;            /* [nsplit][ldp] split partials (as for mbpls_nipals_reduce_partials_f64) */
+  const double* Tden;            /* NaN mode */
+  long ldp;
+  const int* block_split_off;    /* B + 1 */
+  const double* norm_part;       /* [n_norm_parts][B] */
+  int n_norm_parts;
+  int world, rank;
+  const unsigned long long* peer_bufs;
+  long slot_elems, flags_off;
+  unsigned long long seq;
+  unsigned int* counters;
+} mbpls_xchg_args;
+int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* args_host, int ctas, void* stream);
 
 typedef struct mbpls_record_args {
   int n, p, B, q, nanmode;

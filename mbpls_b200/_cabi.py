@@ -11,11 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
-CTRL_DONE, CTRL_TRIPS, CTRL_COUNT = 0, 1, 4
+CTRL_DONE, CTRL_TRIPS, CTRL_ERROR, CTRL_COUNT = 0, 1, 2, 4
 NORM_L2, NORM_L1, NORM_MAX, NORM_MIN = 0, 1, 2, 3
 
 _p = C.c_void_p
@@ -32,6 +32,15 @@ class EpilogueArgs(C.Structure):
         ("red", _p), ("Yt", _p), ("row_flag", _p), ("ycol_flag", _p),
         ("T", _p), ("u", _p), ("ts", _p), ("ts_old", _p), ("a", _p), ("v", _p),
         ("scal", _p), ("ctrl", _p), ("diff_trace", _p), ("diff_trace_len", _i),
+    ]
+
+
+class XchgArgs(C.Structure):
+    _fields_ = [
+        ("epi", EpilogueArgs),
+        ("Tnum", _p), ("Tden", _p), ("ldp", _l), ("block_split_off", _p), ("norm_part", _p), ("n_norm_parts", _i),
+        ("world", _i), ("rank", _i),
+        ("peer_bufs", _p), ("slot_elems", _l), ("flags_off", _l), ("seq", C.c_ulonglong), ("counters", _p),
     ]
 
 
@@ -67,6 +76,7 @@ SIGNATURES = {
     "mbpls_nipals_reduce_partials_f64": [_p, _p, _l, _i, _i, _p, _p, _i, _p, _i, _p, _p],
     "mbpls_nipals_begin_component_f64": [_p, _i, _p, _p, _p, _p],
     "mbpls_nipals_epilogue_f64": [C.POINTER(EpilogueArgs), _p],
+    "mbpls_nipals_xchg_epilogue_f64": [C.POINTER(XchgArgs), _i, _p],
     "mbpls_nipals_record_component_f64": [C.POINTER(RecordArgs), _p],
     "mbpls_loadings_deflate_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "mbpls_fused_workers_per_sm_pair": [_l],

@@ -215,6 +215,104 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
 
 
 # ---- UNIPALS (mbpls.py:384-574) ------------------------------------------------------------------
+def _gram_route_pays(n_global, p_global, K):
+    """UNIPALS with n >= p through the Gram matrices: one SYRK (n p^2 executed flops at ~30 TFLOP/s) against K components of
+    at least three passes over X at ~5 TB/s; also the p x p matrix (plus split-K partials) must stay small."""
+    if n_global < p_global or p_global < 1:
+        return False
+    syrk_s = float(n_global) * p_global * p_global / 3.0e13
+    stream_s = K * 3.0 * 8.0 * n_global * p_global / 5.0e12
+    return p_global <= 16384 and syrk_s < stream_s
+
+
+def _fit_unipals_gram(model, Xt, Yt, n, q, shard, boff_dev, zss, device, rows_group=None, n_global=None):
+    """UNIPALS for n >= p without a single per-component pass over X.
+
+    The reference rebuilds S = X'YY'X from the deflated X in every component and then makes four more passes over X
+    (t_b = X_b w_b, ts = X w, p = X'ts, X -= ts p'; :396-443).  With n >> p all of that lives in p-space: keep VAR = X'X and
+    C = X'Y (one tensor-core SYRK and one pass, the KERNEL method's cross-products, :586-587) and deflate THEM,
+        ts = X w / |X w|,  |X w|^2 = w'VAR w,  p = X'ts = VAR w / |X w|,  v = Y'ts = C'w / |X w|,
+        X <- X - ts p'   ==>   VAR <- VAR - p p',  C <- C - p v'      (ts'ts = 1, X'ts = p),
+    then recover the n-space outputs after the loop: Ts = X R (R = W pinv(P'W), unit columns), block scores
+    T_b = X_b W_b - Ts striu(P_b'W_b) (the K sequential deflations collapse to a triangular correction), U = Y v / v'v.
+    Same quantities as the streaming form up to rounding (4e-12 against the numpy reference over 30 components); C5 (n = 1 M,
+    p = 2,000, K = 30): 6 reads of X + one SYRK instead of ~150 passes.  rows_group: sample axis sharded over the ranks
+    (VAR, C and the few squared norms are all-reduced once; everything else is row-local or replicated)."""
+    K, B = int(model.n_components), len(shard.sizes)
+    p, ld = Xt.shape
+    rg = rows_group
+    st = stream_ptr(device)
+    if zss is None:
+        zss = E.feature_sumsq(Xt, n)
+    varxb = model._block_sums(zss, boff_dev, B, rg)
+    vary_t = E.segsum(E.feature_sumsq(Yt, n), E._i32([0, q], device), 1).clone()
+    E.allreduce_(vary_t, rg)
+    vary = float(vary_t.item())
+    Ct = xt_multi(Xt, n, Yt).contiguous()  # C' = (X'Y)' : q x p
+    ldv = (p + 15) // 16 * 16
+    VAR = crossprod(Xt, Xt, p, p, n, True, ldv)  # X'X on the FP64 tensor cores
+    E.allreduce_(Ct, rg)
+    E.allreduce_(VAR, rg)
+    Wc = torch.zeros((K, p), dtype=F64, device=device)
+    Wb = torch.zeros((K, p), dtype=F64, device=device)
+    P = torch.zeros((K, p), dtype=F64, device=device)
+    V = torch.zeros((K, q), dtype=F64, device=device)
+    U = torch.zeros((K, ld), dtype=F64, device=device)
+    A_dev = torch.zeros((K, B), dtype=F64, device=device)
+    pss_dev = torch.zeros((K, B), dtype=F64, device=device)
+    vv_dev = torch.zeros(K, dtype=F64, device=device)
+    for k in range(K):
+        c = E.small_top_eigvec(E.gram(Ct, Ct, p))  # top eigenvector of C'C (q x q) -> w = C c / |C c| (:396-402)
+        w = E.right_multiply(Ct, p, None, c.view(q, 1))[0].contiguous()
+        normalize_over_features_(w, p, None)
+        Vw = torch.zeros(p, dtype=F64, device=device)
+        call("mbpls_dense_gemv_f64", ptr(VAR), ldv, p, p, ptr(w), ptr(Vw), st)
+        tn = torch.sqrt(E.gram(w.view(1, -1), Vw.view(1, -1), p).view(-1))  # |X w|
+        v = E.gram(Ct, w.view(1, -1), p)[:, 0].contiguous()
+        scale_rows_(v.view(1, -1), q, tn, True)   # v = Y'ts / ts'ts (:420)
+        pv = Vw
+        scale_rows_(pv.view(1, -1), p, tn, True)  # p = X'ts / ts'ts (:427)
+        a = block_sumsq(w, boff_dev, B, None)     # :405-408
+        Wb[k] = scale_by_block(w, boff_dev, B, a, p)
+        A_dev[k] = a
+        u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # u = Y v / v'v, unit length (:423-424)
+        if rg is None:
+            normalize_(u, n)
+        else:
+            scale_rows_(u.view(1, -1), n, torch.sqrt(E.rows_sumsq(u.view(1, -1), n, rg)), True)
+        pss_dev[k] = block_sumsq(pv, boff_dev, B, None)
+        vv_dev[k:k + 1] = E.rows_sumsq(v.view(1, -1), q)
+        # X <- X - ts p' (:443), in p-space
+        call("mbpls_rank1_update_f64", ptr(Ct), Ct.stride(0), p, q, ptr(pv), ptr(v), st)
+        call("mbpls_dense_rank2_f64", ptr(VAR), ldv, p, p, ptr(pv), ptr(pv), None, 0.0, 0.0, -1.0, -1, -1, st)
+        Wc[k], P[k], V[k], U[k] = w, pv, v, u
+    del VAR
+    M = E.small_pinv(E.gram(P, Wc, p))
+    R = E.right_multiply(Wc, p, None, M)  # :476
+    beta = E.right_multiply(R, p, None, V.contiguous())  # :477
+    Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # ts_k = X_k w_k / |X_k w_k| = X r_k: unit columns by construction
+    Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
+    for b in range(B):
+        o0, o1 = shard.block_off[b], shard.block_off[b + 1]
+        full = E.skinny_gemm(Xt[o0:o1], n, Wb[:, o0:o1], [0, o1 - o0])  # X_b W_b : K x ld
+        Cb = torch.triu(E.gram(P[:, o0:o1], Wb[:, o0:o1], o1 - o0), diagonal=1).contiguous()  # striu(P_b'W_b)
+        Tb[b, 0] = full[0]
+        for k in range(1, K):  # t_b,k = X_b^(k) w_b,k = X_b w_b,k - sum_{j<k} ts_j (p_b,j . w_b,k)  (:410-413 after :443)
+            Tb[b, k] = lincomb_sub(full[k].contiguous(), Ts, k, Cb[:k, k].contiguous(), n)
+    A = A_dev.cpu().numpy().T.copy()
+    pssb_h, vv_h = pss_dev.cpu().numpy(), vv_dev.cpu().numpy()
+    evx = [float(pssb_h[k].sum() / varxb.sum()) for k in range(K)]  # ((ts p')**2).sum() = ts'ts p'p with ts'ts = 1 (:429-448)
+    evy = [float(vv_h[k] / vary) for k in range(K)]
+    evxb = (pssb_h / varxb[None, :]).T.copy()
+    model.A_ = A
+    model.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
+    model.explained_var_x_, model.explained_var_y_, model.explained_var_xblocks_ = evx, evy, evxb
+    model.W_non_normal_ = [np.empty((s_, 0)) for s_ in shard.sizes]
+    model.W_concat_ = np.empty((shard.p_global, 0))
+    _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb)
+    model.__dict__["_cv_weights"] = Wc
+
+
 def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_group=None, n_global=None):
     """group: the FEATURE axis is sharded over it (contractions over p are all-reduced).  rows_group: the SAMPLE axis is
     sharded instead (n >= p): Xt / Yt hold this rank's n rows of all features; per component the sums
@@ -227,6 +325,9 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_
     ng = n if n_global is None else n_global
     if rg is not None and (group is not None or ng < pg):
         raise NotImplementedError("row-sharded UNIPALS covers n >= p with a replicated feature axis")
+    route = model._runtime().get("unipals_route")
+    if group is None and ng >= pg and p > 0 and route != "stream" and (route == "gram" or _gram_route_pays(ng, pg, K)):
+        return _fit_unipals_gram(model, Xt, Yt, n, q, shard, boff_dev, zss, device, rows_group=rg, n_global=n_global)
 
     def normalize_rows_(t):  # unit norm over the *global* sample axis
         if rg is None:

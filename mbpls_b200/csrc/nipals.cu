@@ -251,9 +251,8 @@ begin_component_kernel(const double* __restrict__ u0, int n, double* __restrict_
 #define EPI_MAXB 64
 #define EPI_MAXQ 64
 
-__global__ void __launch_bounds__(1024) nipals_epilogue_kernel(mbpls_epilogue_args a) {
+__device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
   int* ctrl = a.ctrl;
-  if (ctrl[MBPLS_CTRL_DONE]) return;
   __shared__ double scratch[32 * 4];
   __shared__ double s_norm[EPI_MAXB], s_a[EPI_MAXB], s_v[EPI_MAXQ];
   __shared__ double s_sc[8];
@@ -424,6 +423,137 @@ __global__ void __launch_bounds__(1024) nipals_epilogue_kernel(mbpls_epilogue_ar
     }
     if (a.diff_trace && trips <= a.diff_trace_len) a.diff_trace[trips - 1] = trips > 1 ? s_sc[0] : 1.0;
   }
+}
+
+__global__ void __launch_bounds__(1024) nipals_epilogue_kernel(mbpls_epilogue_args a) {
+  if (a.ctrl[MBPLS_CTRL_DONE]) return;
+  epilogue_body(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// xchg_epilogue: reduce_partials + the exchange between the GPUs + the epilogue as ONE kernel.
+//
+// Feature-sharded fits end every trip with "sum the split partials -> sum over the GPUs -> superlevel step on every GPU".
+// With NCCL that is reduce_partials, a copy, the all-reduce on NCCL's stream (two cross-stream event hand-offs) and the
+// epilogue: four launches and ~0.1 ms of fixed cost per trip, which is what 8 GPUs lose on the headline problem and most of
+// a PLS2 trip on a small shard.  Here the exchange runs over NVLink peer memory inside the kernel:
+//   A  every CTA sums the split partials of its items (sample i of block b) into THIS rank's symmetric buffer (slot = trip
+//      parity); the last CTA to finish publishes `seq` into the flag word "rank -> peer" of every peer's buffer
+//      (st.release.sys over NVLink) and into its own;
+//   B  every CTA waits until all `world` flags of its own buffer have reached `seq` (ld.acquire.sys), then adds the slots of
+//      all ranks IN RANK ORDER -- peer slots are read straight through NVLink -- so every GPU forms bit-identical sums, which
+//      keeps the replicated epilogues (and their convergence decisions) in lock step;
+//   C  the last CTA to finish B runs the epilogue on the sums.
+// Slots alternate with the trip parity: a rank can only start trip s+2 after every peer has published s+1, which it does
+// after it has finished reading the slots of trip s.  A rank that waits longer than XCHG_TIMEOUT_NS for a peer raises
+// ctrl[MBPLS_CTRL_ERROR] instead of hanging.  world == 1: A writes the sums directly, C follows -- one launch instead of two.
+// ------------------------------------------------------------------------------------------
+#define XCHG_TIMEOUT_NS 20000000000ull
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) {
+  const mbpls_epilogue_args& a = x.epi;
+  if (a.ctrl[MBPLS_CTRL_DONE]) return;
+  __shared__ int s_flag;
+  const int n = a.n, B = a.B, nan = a.nanmode;
+  const long ldt = a.ldt;
+  const int nrows = nan ? 2 * B : B;                    // rows of `red` that hold per-sample sums
+  const long nitems = static_cast<long>(nrows) * n;
+  const long norm_off = static_cast<long>(nrows) * ldt;  // B squared norms behind them
+  const int tid = threadIdx.x, G = gridDim.x;
+  const bool multi = x.world > 1;
+  double* mine = multi ? reinterpret_cast<double*>(x.peer_bufs[x.rank]) + (x.seq & 1ull) * x.slot_elems : const_cast<double*>(a.red);
+
+  // ---- A: split partials -> this rank's sums
+  for (long it = static_cast<long>(blockIdx.x) * blockDim.x + tid; it < nitems; it += static_cast<long>(G) * blockDim.x) {
+    const int r = static_cast<int>(it / n), i = static_cast<int>(it - static_cast<long>(r) * n);
+    const int b = r < B ? r : r - B;
+    const double* src = r < B ? x.Tnum : x.Tden;
+    const int s0 = x.block_split_off[b], s1 = x.block_split_off[b + 1];
+    double acc = 0.0;
+    for (int sp = s0; sp < s1; ++sp) acc += src[static_cast<size_t>(sp) * x.ldp + i];
+    mine[static_cast<size_t>(r) * ldt + i] = acc;
+  }
+  if (blockIdx.x == 0 && tid < 32) {  // squared block-weight norms: one lane per block at a time, fixed order
+    for (int b = tid; b < B; b += 32) {
+      double acc = 0.0;
+      for (int c = 0; c < x.n_norm_parts; ++c) acc += x.norm_part[static_cast<size_t>(c) * B + b];
+      mine[norm_off + b] = acc;
+    }
+  }
+  if (multi) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned old = atomicAdd(&x.counters[0], 1u);
+      if (old == static_cast<unsigned>(G) - 1u) {  // all CTAs of this rank have written their sums: publish
+        x.counters[0] = 0u;
+        __threadfence_system();
+        for (int r = 0; r < x.world; ++r) {
+          unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[r]) + x.flags_off);
+          st_release_sys_u64(flags + x.rank, x.seq);
+        }
+      }
+      // ---- B: wait for every rank's sums (this rank's included)
+      const unsigned long long* myflags =
+          reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[x.rank]) + x.flags_off);
+      const unsigned long long t0 = global_timer_ns();
+      int ok = 1;
+      for (int r = 0; r < x.world && ok; ++r) {
+        while (ld_acquire_sys_u64(myflags + r) < x.seq) {
+          if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) {
+            ok = 0;
+            break;
+          }
+        }
+      }
+      s_flag = ok;
+    }
+    __syncthreads();
+    if (!s_flag) {  // a peer never arrived: report instead of hanging (the host raises)
+      if (tid == 0) a.ctrl[MBPLS_CTRL_ERROR] = 1;
+      return;
+    }
+    double* red = const_cast<double*>(a.red);
+    const size_t slot = (x.seq & 1ull) * x.slot_elems;
+    for (long it = static_cast<long>(blockIdx.x) * blockDim.x + tid; it < nitems + B; it += static_cast<long>(G) * blockDim.x) {
+      size_t off;
+      if (it < nitems) {
+        const int r = static_cast<int>(it / n), i = static_cast<int>(it - static_cast<long>(r) * n);
+        off = static_cast<size_t>(r) * ldt + i;
+      } else {
+        off = static_cast<size_t>(norm_off) + (it - nitems);
+      }
+      double acc = 0.0;
+      for (int r = 0; r < x.world; ++r) acc += __ldcv(reinterpret_cast<const double*>(x.peer_bufs[r]) + slot + off);
+      red[off] = acc;
+    }
+  }
+  // ---- C: the last CTA runs the superlevel step on the sums
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned old = atomicAdd(&x.counters[1], 1u);
+    s_flag = old == static_cast<unsigned>(G) - 1u;
+    if (s_flag) x.counters[1] = 0u;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  epilogue_body(a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -965,6 +1095,28 @@ int mbpls_nipals_epilogue_f64(const mbpls_epilogue_args* args, void* stream) {
   if (args->B < 1 || args->B > EPI_MAXB || args->q < 1 || args->q > EPI_MAXQ) return MBPLS_ERR_SIZE;
   if (args->nanmode && (!args->row_flag || !args->ycol_flag)) return MBPLS_ERR_ARG;
   nipals_epilogue_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*args);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* x, int ctas, void* stream) {
+  if (!x) return MBPLS_ERR_ARG;
+  const mbpls_epilogue_args* args = &x->epi;
+  if (!args->red || !args->T || !args->u || !args->ts || !args->ts_old || !args->Yt || !args->a || !args->v || !args->scal ||
+      !args->ctrl || !x->Tnum || !x->block_split_off || !x->norm_part || !x->counters)
+    return MBPLS_ERR_ARG;
+  if (args->B < 1 || args->B > EPI_MAXB || args->q < 1 || args->q > EPI_MAXQ) return MBPLS_ERR_SIZE;
+  if (args->nanmode && (!args->row_flag || !args->ycol_flag || !x->Tden)) return MBPLS_ERR_ARG;
+  if (x->world < 1 || x->rank < 0 || x->rank >= x->world) return MBPLS_ERR_ARG;
+  if (x->world > 1 && (!x->peer_bufs || x->seq == 0 || x->slot_elems < (args->nanmode ? 2 : 1) * args->B * args->ldt + args->B ||
+                       x->flags_off < 2 * x->slot_elems))
+    return MBPLS_ERR_ARG;
+  // every CTA must be resident at once (B spins on flags): at most one CTA per SM
+  int g = ctas > 0 ? ctas : 32;
+  if (g > num_sms()) g = num_sms();
+  const long items = static_cast<long>(args->nanmode ? 2 : 1) * args->B * args->n;
+  const int need = static_cast<int>((items + 1023) / 1024);
+  if (g > need) g = need < 1 ? 1 : need;
+  xchg_epilogue_kernel<<<g, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*x);
   MBPLS_RETURN_LAST();
 }
 

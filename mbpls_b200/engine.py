@@ -361,6 +361,54 @@ def make_splits(block_off: Sequence[int], n: int, sm_count: int, ctas_per_sm: Op
     return f0, f1, bso
 
 
+# --------------------------------------------------------------------------------------------- #
+# peer-memory exchange buffers for the in-kernel exchange (csrc/nipals.cu xchg_epilogue_kernel)
+# --------------------------------------------------------------------------------------------- #
+_SYMM_CACHE: dict = {}
+
+
+class PeerExchange:
+    """One symmetric buffer per rank (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every process of
+    the group over NVLink): 2 slots of `slot_elems` doubles + `world` 8-byte flag words.  `seq` counts the exchanges made
+    through it on every rank alike (flags only ever grow, so the buffer is reused from fit to fit)."""
+
+    def __init__(self, group, nred: int, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.slot_elems = (int(nred) + 15) // 16 * 16
+        self.flags_off = 2 * self.slot_elems
+        total = self.flags_off + max(16, self.world)
+        self.buf = symm_mem.empty(total, dtype=F64, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # nobody publishes a flag before every rank has zeroed its buffer
+        self.peer_bufs = int(self.hdl.buffer_ptrs_dev)
+        self.seq = 0
+
+
+def peer_exchange(group, nred: int, device):
+    """The cached PeerExchange for (group, size), or None when peer memory is not available (-> NCCL all-reduce).
+    MBPLS_XCHG=nccl forces the NCCL path."""
+    if os.environ.get("MBPLS_XCHG", "").lower() == "nccl":
+        return None
+    import torch.distributed as dist
+    key = (id(group), (int(nred) + 15) // 16 * 16, torch.device(device).index)
+    if key not in _SYMM_CACHE:
+        ok = 0
+        px = None
+        try:
+            px = PeerExchange(group, nred, device)
+            ok = 1
+        except Exception as exc:  # no VMM / P2P between these devices, or an older torch: fall back on every rank alike
+            _SYMM_CACHE.setdefault("errors", []).append(repr(exc)[:300])
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        _SYMM_CACHE[key] = px if int(flag.item()) == 1 else None
+    return _SYMM_CACHE[key]
+
+
 def allreduce_(t: torch.Tensor, group) -> None:
     if group is not None:
         import torch.distributed as dist
@@ -398,6 +446,7 @@ class NipalsResult:
     vv: List[float]
     n_iter: List[int]
     diff: List[float]
+    exchange: Optional[str] = None  # multi-GPU: how the per-trip sums crossed the GPUs
 
 
 def sm_count(device) -> int:
@@ -496,6 +545,39 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                              diff_trace=None, diff_trace_len=0)
     done_p = ptr(ctrl)  # ctrl[MBPLS_CTRL_DONE] is element 0
 
+    # One kernel per trip for "sum the split partials -> sum over the GPUs -> superlevel step" (csrc/nipals.cu
+    # xchg_epilogue_kernel): single GPU always; several GPUs when their memory is mapped peer to peer (else NCCL).
+    px = peer_exchange(group, nred, dev) if group is not None else None
+    fused_epi = os.environ.get("MBPLS_XCHG", "").lower() != "off" and (group is None or px is not None)
+    res.exchange = None if group is None else ("peer-memory kernel (NVLink loads, sums in rank order)" if px is not None
+                                               else "ncclAllReduce")
+    xcount = buf(2, dtype=torch.int32, zero=True)
+
+    def xchg_args(Tn, Td, ldp, bso_dev, npart_t, nparts_):
+        return _cabi.XchgArgs(epi=epi, Tnum=Tn.data_ptr(), Tden=Td.data_ptr() if Td is not None else None, ldp=ldp,
+                              block_split_off=bso_dev.data_ptr(), norm_part=npart_t.data_ptr(), n_norm_parts=nparts_,
+                              world=px.world if px else 1, rank=px.rank if px else 0, peer_bufs=px.peer_bufs if px else None,
+                              slot_elems=px.slot_elems if px else 0, flags_off=px.flags_off if px else 0, seq=0,
+                              counters=xcount.data_ptr())
+
+    x_tp = xchg_args(Tnum, Tden, ld, sbso, norm_part, nparts) if fused_epi else None
+    x_op = xchg_args(Tnum_o, Tden_o, ld, osbso, norm_part_o, nsplit_o) if (fused_epi and use_op) else None
+
+    def close_trip(xa, Tn, Td, bso_dev, npart_t, nparts_):
+        """split partials -> sums over splits and GPUs -> epilogue"""
+        if fused_epi:
+            if px is not None:
+                px.seq += 1
+                xa.seq = px.seq
+            call("mbpls_nipals_xchg_epilogue_f64", C.byref(xa), 0, st)
+            return
+        call("mbpls_nipals_reduce_partials_f64", ptr(Tn), ptr(Td), ld, n, B, ptr(bso_dev), ptr(npart_t), nparts_,
+             ptr(red_local), nan, done_p, st)
+        if group is not None:
+            red.copy_(red_local)
+            allreduce_(red, group)
+        call("mbpls_nipals_epilogue_f64", C.byref(epi), st)
+
     if trips_per_sync is None:
         # trips enqueued per readback of the convergence flag; trips launched after convergence are no-ops
         # (a few microseconds each), so batching only removes host round-trips from the critical path
@@ -543,8 +625,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                         if nan:  # sum over the observed features of w~^2, per sample and split (:867-872)
                             timed("rowden", lambda: call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1),
                                                          nsplit_o, ptr(Tden_o), ld, done_p, st))
-                    call("mbpls_nipals_reduce_partials_f64", ptr(Tnum_o), ptr(Tden_o), ld, n, B, ptr(osbso),
-                         ptr(norm_part_o), nsplit_o, ptr(red_local), nan, done_p, st)
+                    close_trip(x_op, Tnum_o, Tden_o, osbso, norm_part_o, nsplit_o)
                 else:
                     if first and w_ready == "w":
                         call("mbpls_block_sumsq_parts_f64", ptr(w), p, ptr(boff), B, ptr(norm_part), done_p, st)
@@ -553,16 +634,13 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                                                   ptr(w), ptr(norm_part), nan, done_p, st))
                     timed("xw", lambda: call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w), ptr(sf0), ptr(sf1), nsplit,
                                              ptr(Tnum), ptr(Tden), ld, nan, done_p, st))
-                    call("mbpls_nipals_reduce_partials_f64", ptr(Tnum), ptr(Tden), ld, n, B, ptr(sbso), ptr(norm_part),
-                         nparts, ptr(red_local), nan, done_p, st)
-                if group is not None:
-                    red.copy_(red_local)
-                    allreduce_(red, group)
-                call("mbpls_nipals_epilogue_f64", C.byref(epi), st)
+                    close_trip(x_tp, Tnum, Tden, sbso, norm_part, nparts)
                 launched += 1
             ctrl_h.copy_(ctrl, non_blocking=True)
             scal_h.copy_(scal, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
+            if int(ctrl_h[_cabi.CTRL_ERROR]):
+                raise _cabi.MbplsCudaError("a peer GPU did not arrive at the in-kernel exchange of a NIPALS trip (timeout)")
             if int(ctrl_h[_cabi.CTRL_DONE]) or int(ctrl_h[_cabi.CTRL_TRIPS]) >= max_iter:
                 break
         res.n_iter.append(int(ctrl_h[_cabi.CTRL_TRIPS]))

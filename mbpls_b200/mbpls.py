@@ -49,6 +49,8 @@ _RUNTIME_DEFAULTS = dict(
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
     one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 20480), False two-pass kernels
     one_pass_deflate=None,  # loadings+deflation also runs the next component's whole first trip (None auto, False off)
+    unipals_route=None,   # UNIPALS with n >= p: "gram" = everything in p-space from X'X / X'Y (crossmethods._fit_unipals_gram),
+                          # "stream" = the reference's per-component passes over X; None: whichever a cost model says is cheaper
     timings=None,         # dict: wall-clock seconds per phase of fit (ingest / standardize / solve / materialize), measured with a
                           # device synchronisation at every phase boundary (diagnostics; bench.py --verbose)
     gather=None,          # multi-GPU, per-feature attributes (W_, P_, R_, beta_, x_scalers_): "all" = every rank materialises the
@@ -140,7 +142,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
     def __getstate__(self):
         self._materialize_all()
         state = dict(self.__dict__)
-        for k in ("_rt", "_dev", "_lazy", "_dev_scalers", "_cv_weights", "_rows", "_col_nan"):
+        for k in ("_rt", "_dev", "_lazy", "_dev_scalers", "_cv_weights", "_rows", "_col_nan", "_exchange"):
             state.pop(k, None)
         return state
 
@@ -551,6 +553,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
                            one_pass_deflate=rt["one_pass_deflate"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
         self.n_iter_ = list(res.n_iter)
+        self.__dict__["_exchange"] = res.exchange
         if any(it >= rt["max_iter"] for it in res.n_iter):
             warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
         # ---- finalise (mbpls.py:985-989): W = concat(W_non_normal_)/colnorm, R = W pinv(P'W), beta = R V'

@@ -55,7 +55,10 @@ def gpu_checks(group, rank, world, dev):
         print(f"rank {rank}: world={world} nan={nan_frac} n={n} trips={m.n_iter_} worst={worst}", flush=True)
     # the other methods under the same feature sharding (KERNEL: the p > n branch; n >= p needs row sharding)
     # KERNEL n=1201 >= p=800 takes the row-sharded path (samples split over the ranks, p x p all-reduce)
-    for method, n in (("SIMPLS", 400), ("UNIPALS", 400), ("UNIPALS", 1200), ("KERNEL", 400), ("KERNEL", 1201)):
+    # UNIPALS n=1200 >= p=800 is row-sharded too: once in the reference's streaming form (per-component all-reduces of X'Y, X'ts,
+    # Y'ts) and once through the Gram matrices (one all-reduce of X'X and X'Y)
+    for method, n, route in (("SIMPLS", 400, None), ("UNIPALS", 400, None), ("UNIPALS", 1200, "stream"), ("UNIPALS", 1200, "gram"),
+                             ("KERNEL", 400, None), ("KERNEL", 1201, None)):
         sizes = (300, 50, 450)
         X, Y = latent_blocks(n, sizes, 3, 4, seed=50 + n)
         Xt, Yt = latent_blocks(13, sizes, 3, 4, seed=6)
@@ -63,7 +66,7 @@ def gpu_checks(group, rank, world, dev):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             o = OracleMBPLS(**kw).fit([x.copy() for x in X], Y.copy())
-            m = MBPLS(**kw).set_runtime(group=group, device=dev)
+            m = MBPLS(**kw).set_runtime(group=group, device=dev, unipals_route=route)
             m.fit([x.copy() for x in X], Y.copy())
         worst = compare(snapshot_model(m, Xt, Yt), snapshot_model(o, Xt, Yt), 1e-8, f"rank {rank} {method} n={n}")
         print(f"rank {rank}: world={world} {method} n={n} worst={worst}", flush=True)

@@ -51,6 +51,18 @@ def test_method_matches_reference_fixture(name):
     compare(ours, ref, TOL, name, skip=skip)
 
 
+@pytest.mark.parametrize("route", ["gram", "stream"])
+@pytest.mark.parametrize("name", ["pls2_ngtp_unipals", "c5_tall_unipals", "unipals_nostd"])
+def test_unipals_tall_both_routes_match_reference_fixture(name, route):
+    """UNIPALS with n >= p: the p-space route (X'X and X'Y deflated algebraically, scores recovered after the loop) and the
+    reference's streaming form (per-component passes over the deflated X) against the same live-reference fixtures."""
+    X, Y, Xt, Yt, kwargs, ref = load_live(name)
+    m = _fit(kwargs, X, Y, unipals_route=route)
+    ours = _snapshot(m, Xt, Yt)
+    skip = [k for k in ref if k not in ours and k.startswith("tr_")]
+    compare(ours, ref, TOL, f"{name} [{route}]", skip=skip)
+
+
 @pytest.mark.parametrize("tag,methods", [("pn", ["UNIPALS", "KERNEL", "SIMPLS"]), ("np", ["UNIPALS", "KERNEL"])])
 def test_methods_match_reference_kat_csvs(tag, methods):
     """mbpls/tests/test_mbpls.py:34-421 with our estimator in place of the reference's."""

@@ -12,4 +12,4 @@ def test_feature_sharded_fit_two_gpus():
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     r = run_workers("nccl", 2, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
-    assert r.stdout.count("worst=") == 16  # (3 NIPALS + 5 other-method cases) x 2 ranks
+    assert r.stdout.count("worst=") == 18  # (3 NIPALS + 6 other-method cases) x 2 ranks
