@@ -247,7 +247,7 @@ def parity_gate(args, dev, group, rank, world, nan_frac, feats_per_block):
         warnings.simplefilter("ignore")
         m = MBPLS(n_components=K, method="NIPALS", standardize=True, calc_all=True, sparse_data=nan_frac > 0, copy=True)
         m.set_runtime(device=dev, group=group, materialize=True, global_sizes=sizes if world > 1 else None, max_iter=args.max_iter,
-                      one_pass=False if args.two_pass else None)
+                      one_pass=False if args.two_pass else None, gather="all")  # rank 0 compares the complete attributes
         m.fit(local, Yd)
     out = None
     if rank == 0:

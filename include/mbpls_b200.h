@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 9
+#define MBPLS_ABI_VERSION 10
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -200,6 +200,56 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
                             const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream);
+
+/* ---- whole dense NIPALS fits in one kernel (csrc/smallfit.cu): one persistent CTA per fit, device-side while loop -----
+ * For problems that are launch-latency bound through the streaming kernels (README quickstart, the leave-one-out loops of
+ * the reference's notebooks).  Fit f uses the samples train_idx[f*ld_idx .. + train_cnt[f]) of the shared feature-major
+ * source (Xsrc p x ldx, Ysrc q x ldx, raw values): gather + StandardScaler (mbpls.py:303-326), the NIPALS loop :821-983,
+ * results per fit (component-major, sample vectors with leading dimension ldw >= max train_cnt):
+ *   stats  [4p + 4q]  x mean | x var | x scale | x sum z^2 | y mean | y var | y scale | y sum z^2
+ *   Wt, W, P  [K][p]   un-normalised weights, block-normalised weights, loadings
+ *   Ts, U  [K][ldw],  Tb [B][K][ldw]
+ *   small  [K(q + 2B + 4) + B + 2]  V (K x q) | A (K x B) | sum p_j^2 per block (K x B) | ts'ts (K) | v'v (K) | diff_t (K) |
+ *                                   trips (K) | varx per block (B) | vary | singular
+ *   R [K][p], beta [q][p]   R = W (P'W)^-1 by substitution (P'W is upper triangular for NIPALS) and beta = R V' (:986-989);
+ *                           singular = 1 flags a (near-)singular P'W: apply the pseudo-inverse on the host side instead
+ * Xw [nfits][p*ldw] / Yw [nfits][q*ldw] receive the standardised (then deflated) copies; scratch holds
+ * mbpls_smallfit_scratch_doubles(...) doubles per fit (scratch_stride).  With preds != NULL the CTA also predicts the
+ * samples test_idx[f*ld_tidx .. + test_cnt[f]) for every prefix of its model: preds[k][sample][c], k+1 components
+ * (the leading blocks of P'W, :1386).  Dense data only. */
+typedef struct mbpls_smallfit_args {
+  int n_src, p, B, q, K, nfits;
+  long ldx;
+  const double* Xsrc;
+  const double* Ysrc;
+  const int* block_off;
+  int standardize, norm_kind, max_iter;
+  double max_tol;
+  const int* train_idx;
+  const int* train_cnt;
+  long ld_idx;
+  const int* test_idx;
+  const int* test_cnt;
+  long ld_tidx;
+  long ldw;
+  double* Xw;
+  double* Yw;
+  double* stats;
+  double* Wt;
+  double* W;
+  double* P;
+  double* Ts;
+  double* U;
+  double* Tb;
+  double* small;
+  double* R;
+  double* beta;
+  double* preds;
+  double* scratch;
+  long scratch_stride;
+} mbpls_smallfit_args;
+int mbpls_smallfit_scratch_doubles(int p, int B, long ldw);
+int mbpls_smallfit_nipals_f64(const mbpls_smallfit_args* args_host, void* stream);
 
 /* ---- NaN bit matrix and the masked denominators derived from it (csrc/nanmask.cu; mbpls.py:848-852, :867-872, :923-925)
  * bits[j*ldw + (i >> 5)] bit (i & 31) = 1 iff x_ij is NaN; ldw = mbpls_nan_bitmask_ldw(n) 32-bit words per feature. */

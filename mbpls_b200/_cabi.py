@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -41,6 +41,19 @@ class XchgArgs(C.Structure):
         ("Tnum", _p), ("Tden", _p), ("ldp", _l), ("block_split_off", _p), ("norm_part", _p), ("n_norm_parts", _i),
         ("world", _i), ("rank", _i),
         ("peer_bufs", _p), ("slot_elems", _l), ("flags_off", _l), ("seq", C.c_ulonglong), ("counters", _p),
+    ]
+
+
+class SmallFitArgs(C.Structure):
+    _fields_ = [
+        ("n_src", _i), ("p", _i), ("B", _i), ("q", _i), ("K", _i), ("nfits", _i),
+        ("ldx", _l), ("Xsrc", _p), ("Ysrc", _p), ("block_off", _p),
+        ("standardize", _i), ("norm_kind", _i), ("max_iter", _i), ("max_tol", _d),
+        ("train_idx", _p), ("train_cnt", _p), ("ld_idx", _l),
+        ("test_idx", _p), ("test_cnt", _p), ("ld_tidx", _l),
+        ("ldw", _l),
+        ("Xw", _p), ("Yw", _p), ("stats", _p), ("Wt", _p), ("W", _p), ("P", _p), ("Ts", _p), ("U", _p), ("Tb", _p),
+        ("small", _p), ("R", _p), ("beta", _p), ("preds", _p), ("scratch", _p), ("scratch_stride", _l),
     ]
 
 
@@ -78,6 +91,8 @@ SIGNATURES = {
     "mbpls_nipals_epilogue_f64": [C.POINTER(EpilogueArgs), _p],
     "mbpls_nipals_xchg_epilogue_f64": [C.POINTER(XchgArgs), _i, _p],
     "mbpls_nipals_record_component_f64": [C.POINTER(RecordArgs), _p],
+    "mbpls_smallfit_scratch_doubles": [_i, _i, _l],
+    "mbpls_smallfit_nipals_f64": [C.POINTER(SmallFitArgs), _p],
     "mbpls_loadings_deflate_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "mbpls_fused_workers_per_sm_pair": [_l],
     "mbpls_fused_total_workers": [_l],
@@ -113,7 +128,7 @@ SIGNATURES = {
 }
 
 # functions whose int return value is a plain number, not a status
-_PLAIN = {"mbpls_abi_version", "mbpls_fused_workers_per_sm_pair", "mbpls_fused_total_workers", "mbpls_fused_uses_clusters", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
+_PLAIN = {"mbpls_abi_version", "mbpls_smallfit_scratch_doubles", "mbpls_fused_workers_per_sm_pair", "mbpls_fused_total_workers", "mbpls_fused_uses_clusters", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
           "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits"}
 
 

@@ -49,6 +49,8 @@ _RUNTIME_DEFAULTS = dict(
     deflate_last=False,   # also deflate X after the last component (the reference does; the result is never read)
     one_pass=None,        # NIPALS trip as ONE read of X (csrc/fused.cu): None auto (n <= 20480), False two-pass kernels
     one_pass_deflate=None,  # loadings+deflation also runs the next component's whole first trip (None auto, False off)
+    small_path=None,      # dense single-GPU NIPALS: the whole fit as ONE kernel launch (csrc/smallfit.cu).  None: when the matrix has
+                          # at most smallfit.SMALL_ELEMS elements; True / False force it on / off
     unipals_route=None,   # UNIPALS with n >= p: "gram" = everything in p-space from X'X / X'Y (crossmethods._fit_unipals_gram),
                           # "stream" = the reference's per-component passes over X; None: whichever a cost model says is cheaper
     timings=None,         # dict: wall-clock seconds per phase of fit (ingest / standardize / solve / materialize), measured with a
@@ -304,6 +306,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         for name in _LAZY_NAMES:  # results of an earlier fit must not shadow the lazily materialised ones of this fit
             self.__dict__.pop(name, None)
 
+        # (explicit choices among the streaming kernels keep the fit on them)
+        tuned = any(rt[k] != _RUNTIME_DEFAULTS[k] for k in ("one_pass", "one_pass_deflate", "deflate_mode", "standardize_mode",
+                                                            "fuse_next_xtu", "trips_per_sync", "deflate_last"))
+        if self.method == 'NIPALS' and not sparse and group is None and rt["global_sizes"] is None and rt["small_path"] is not False \
+                and rt["profile"] is None and (rt["small_path"] is True or not tuned):
+            with torch.cuda.device(device):
+                if self._try_fit_small(X, Y, device):
+                    if rt["materialize"]:
+                        self._materialize_all()
+                    return self
+
         if self.method in ('KERNEL', 'UNIPALS') and world > 1:
             blocks0 = X if _is_block_list(X) else [X]
             n0, p0 = int(_shape2(blocks0[0])[0]), sum(int(_shape2(b)[1]) for b in blocks0)
@@ -456,6 +469,97 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.num_blocks_ = B
         fit_rows = CM._fit_kernel if self.method == 'KERNEL' else CM._fit_unipals
         fit_rows(self, Xt, Yt, nl, q, shard, boff_dev, zss, None, device, rows_group=group, n_global=n)
+
+    # ---- small problems: the whole NIPALS fit in one kernel launch (csrc/smallfit.cu)
+    def _try_fit_small(self, X, Y, device) -> bool:
+        """Dense NIPALS on a matrix of at most smallfit.SMALL_ELEMS elements (README quickstart, CV folds): one packed
+        host->device copy, ONE kernel that runs mbpls.py:303-326 and :821-989 with the while loop on the device, one packed
+        device->host copy.  Returns False (nothing done) when the problem is not eligible."""
+        from . import smallfit as SF
+        rt = self._runtime()
+        blocks = X if _is_block_list(X) else [X]
+        shapes = [_shape2(b) for b in blocks]
+        if any(len(sh) != 2 for sh in shapes):
+            return False  # let the general path raise the reference's error
+        n, p = int(shapes[0][0]), sum(int(sh[1]) for sh in shapes)
+        if not SF.eligible(self.method, bool(self.sparse_data), rt["group"], n, p, rt["small_path"]):
+            return False
+        Ysrc = Y if isinstance(Y, torch.Tensor) else np.asarray(Y)
+        if Ysrc.ndim == 1:
+            Ysrc = Ysrc.reshape(-1, 1)
+        Ysrc = _as_2d_source(Ysrc, "Y")
+        blocks = [_as_2d_source(b, "X") for b in blocks]
+        q = int(Ysrc.shape[1])
+        for b in blocks:
+            if int(b.shape[0]) != int(Ysrc.shape[0]):  # check_consistent_length, mbpls.py:309,322
+                raise ValueError("Found input variables with inconsistent numbers of samples: %r" % [int(b.shape[0]), int(Ysrc.shape[0])])
+        B = len(blocks)
+        K = _check_limits(self.n_components, q, B)
+        for a in blocks + [Ysrc]:  # check_array(force_all_finite=True), :293,:310
+            ok = bool(torch.isfinite(a).all()) if isinstance(a, torch.Tensor) else bool(np.isfinite(a).all())
+            if not ok:
+                raise ValueError("Input contains NaN or infinity.")
+        D, n, sizes, p, q, ldx = SF.pack_source(blocks, Ysrc, device)
+        shard = ShardMap.build(sizes, 0, 1)
+        lay, out, _, keep = SF.launch(D, n, p, q, ldx, shard.block_off, K, bool(self.standardize),
+                                      E.norm_kind_of(self.nipals_convergence_norm), self.max_tol, rt["max_iter"],
+                                      [np.arange(n, dtype=np.int32)])
+        host = E.to_host(out)  # one copy: every result of the fit
+        ldw = lay.ldw
+        sm = SF.unpack_small(lay.view(host, "small"), K, q, B)
+        trips = [int(t) for t in sm["trips"]]
+        self.n_iter_ = trips
+        if any(t >= rt["max_iter"] for t in trips):
+            warnings.warn("NIPALS hit the max_iter safety cap before diff_t <= max_tol")
+        dv = lambda name, *shape: lay.view(out, name).view(*shape)   # device views (kept for predict / transform / CV)
+        hv = lambda name, *shape: lay.view(host, name).reshape(*shape)
+        Wt_d, W_d, P_d, V_d = dv("Wt", K, p), dv("W", K, p), dv("P", K, p), lay.view(out, "small")[:K * q].view(K, q)
+        if sm["singular"]:  # more components than the data has rank: R = W pinv(P'W) exactly like the reference (:988)
+            colnorm = torch.sqrt(E.rows_sumsq(Wt_d, p))
+            M = E.small_pinv(E.gram(P_d, Wt_d, p) / colnorm.view(1, -1))
+            R_d = E.right_multiply(Wt_d, p, 1.0 / colnorm, M)
+            beta_d = E.right_multiply(R_d, p, None, V_d.contiguous())
+            R_h, beta_h = E.to_host(R_d, transpose=True), E.to_host(beta_d, transpose=True)
+        else:
+            R_d, beta_d = dv("R", K, p), dv("beta", q, p)
+            R_h, beta_h = np.ascontiguousarray(hv("R", K, p).T), np.ascontiguousarray(hv("beta", q, p).T)
+        self.num_blocks_ = B
+        self.__dict__["_exchange"] = None
+        self.__dict__["_dev"] = dict(shard=shard, R=R_d, beta=beta_d, W=W_d, P=P_d, V=V_d, _keep=(out, keep))
+        self.__dict__["_cv_weights"] = Wt_d
+        st_d, st_h = lay.view(out, "stats"), lay.view(host, "stats")
+        if self.standardize:
+            self.__dict__["_dev_scalers"] = (st_d[0:p], st_d[2 * p:3 * p], st_d[4 * p:4 * p + q], st_d[4 * p + 2 * q:4 * p + 3 * q])
+            seen = np.full(p, n, dtype=np.int64)
+            off = shard.block_off
+            self.x_scalers_ = [_make_scaler(st_h[off[b]:off[b + 1]], st_h[p + off[b]:p + off[b + 1]],
+                                            st_h[2 * p + off[b]:2 * p + off[b + 1]], seen[off[b]:off[b + 1]]) for b in range(B)]
+            self.y_scaler_ = _make_scaler(st_h[4 * p:4 * p + q], st_h[4 * p + q:4 * p + 2 * q], st_h[4 * p + 2 * q:4 * p + 3 * q],
+                                          np.full(q, n, dtype=np.int64))
+        A = np.ascontiguousarray(sm["A"].T)
+        self.A_ = A
+        if self.calc_all:  # mbpls.py:932-964 from the reduced scalars
+            tt, vv, pssb, varxb = sm["tt"], sm["vv"], sm["pssb"], sm["varxb"]
+            self.explained_var_x_ = [float(tt[k] * pssb[k].sum() / varxb.sum()) for k in range(K)]
+            self.explained_var_y_ = [float(tt[k] * vv[k] / sm["vary"]) for k in range(K)]
+            self.explained_var_xblocks_ = (tt[None, :] * pssb.T) / varxb[:, None]
+            self.A_corrected_ = np.stack([_bip_corrected(A[:, k], shard.sizes) for k in range(K)], axis=1)
+        else:
+            self.explained_var_x_, self.explained_var_y_ = [], []
+            self.explained_var_xblocks_ = np.empty((B, 0))
+            self.A_corrected_ = np.empty((B, 0))
+        self.W_concat_ = np.empty((p, 0))
+        off = shard.block_off
+        split = lambda M_: [np.ascontiguousarray(M_[:, off[b]:off[b + 1]].T) for b in range(B)]
+        Tb = hv("Tb", B, K, ldw)
+        self.Ts_ = np.ascontiguousarray(hv("Ts", K, ldw)[:, :n].T)
+        self.U_ = np.ascontiguousarray(hv("U", K, ldw)[:, :n].T)
+        self.V_ = np.ascontiguousarray(sm["V"].T)
+        self.T_ = [np.ascontiguousarray(Tb[b][:, :n].T) for b in range(B)]
+        self.W_, self.W_non_normal_, self.P_ = split(hv("W", K, p)), split(hv("Wt", K, p)), split(hv("P", K, p))
+        self.R_, self.beta_ = R_h, beta_h
+        self.__dict__["_lazy"] = None
+        return True
 
     # ---- helpers of fit
     def _raise_if_any_rank(self, bad: bool, msg: str, group):

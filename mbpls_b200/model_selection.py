@@ -61,6 +61,41 @@ def _prefix_betas(model: MBPLS, ks: Sequence[int], device) -> list:
     return out
 
 
+def _batched_small_cv(estimator, blocks, Ysrc, n, q, sizes, shard, K, ks, folds, device):
+    """All folds of a dense NIPALS cross-validation in ONE kernel launch (csrc/smallfit.cu): one CTA per fold gathers its
+    training samples from the shared source, fits K components with the loop on the device, and predicts its held-out samples
+    for every prefix 1..K of the model.  Returns {k: (n, q) array}, or None when the problem is not eligible (-> fold loop)."""
+    from . import smallfit as SF
+    rt = estimator._runtime()
+    p = sum(sizes)
+    force = rt["small_path"]
+    if force is False or estimator.method != 'NIPALS' or estimator.sparse_data or not folds:
+        return None
+    ntr_max = max(len(tr) for tr, _ in folds)
+    if force is None:
+        import os
+        if os.environ.get("MBPLS_SMALL_PATH", "1") == "0":
+            return None
+        if ntr_max * p > 8 * SF.SMALL_ELEMS or len(folds) * (p + q) * ntr_max * 8 > SF.CV_WORKSPACE_BYTES:
+            return None
+    from .mbpls import _check_limits
+    _check_limits(K, q, len(sizes))
+    for a in blocks + [Ysrc]:
+        ok = bool(torch.isfinite(a).all()) if isinstance(a, torch.Tensor) else bool(np.isfinite(a).all())
+        if not ok:
+            raise ValueError("Input contains NaN or infinity.")
+    D, n, sizes, p, q, ldx = SF.pack_source(blocks, Ysrc, device)
+    lay, out, preds_d, keep = SF.launch(D, n, p, q, ldx, shard.block_off, K, bool(estimator.standardize),
+                                        E.norm_kind_of(estimator.nipals_convergence_norm), estimator.max_tol, rt["max_iter"],
+                                        [np.asarray(tr, dtype=np.int32) for tr, _ in folds],
+                                        [np.asarray(te, dtype=np.int32) for _, te in folds])
+    sm_all = E.to_host(out[lay.off["small"]:lay.off["small"] + lay.sizes["small"] * len(folds)]).reshape(len(folds), -1)
+    if np.any(sm_all[:, -1] != 0.0):  # some fold has more components than rank: the fold loop applies the pseudo-inverse
+        return None
+    Pm = E.to_host(preds_d)  # K x n x q
+    return {k: np.ascontiguousarray(Pm[k - 1]) for k in (ks or [K])}
+
+
 def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[Iterable[int]] = None):
     """Out-of-fold predictions of ``estimator`` (an unfitted ``mbpls_b200.MBPLS``) with the data kept on the GPU.
 
@@ -89,6 +124,11 @@ def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[
 
     with torch.cuda.device(device):
         shard = E.ShardMap.build(sizes, 0, 1)
+        batched = _batched_small_cv(estimator, blocks, Ysrc, n, q, sizes, shard, K, ks, folds, device)
+        if batched is not None:
+            if ks is None:
+                return batched[K].ravel() if y1d else batched[K]
+            return {k: (v.ravel() if y1d else v) for k, v in batched.items()}
         Xraw = E.ingest_blocks(blocks, n, shard, device)          # p x ld, uploaded once
         Yraw = E.alloc_feature_major(q, n, device)
         E.ingest_feature_major(Ysrc, n, 0, q, Yraw, device)

@@ -65,9 +65,13 @@ def test_cluster_deflation_long_splits(n, nan_frac):
     from oracle.cases import latent_blocks
     X, Y = latent_blocks(n, (3100, 2900), 1, 3, seed=n % 71, nan_frac=nan_frac)
     kw = dict(n_components=3, method="NIPALS", sparse_data=nan_frac > 0)
+    if n > 10000:
+        # a PLS1 second-trip diff_t is pure rounding noise; at n = 12,000 x p = 6,000 that noise sits AT the default 1e-14 (the
+        # numpy oracle itself took 2 trips on one host and 5 on another), so this case is pinned a decade above the floor
+        kw["max_tol"] = 1e-12
     m, o = _pair(kw, X, Y.ravel(), one_pass=True)
     _check(m, o, X, Y.ravel(), kw, f"cluster deflation n={n} nan={nan_frac}")
-    if nan_frac == 0 and n <= 10000:  # (at n = 12,000 the oracle's own second-trip diff_t grazes 1e-14; _check allows for that)
+    if nan_frac == 0:
         assert list(m.n_iter_) == [2, 2, 2] == list(o.n_iter_)
 
 

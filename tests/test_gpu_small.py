@@ -1,0 +1,161 @@
+"""GPU: whole dense NIPALS fits in ONE kernel launch (csrc/smallfit.cu, mbpls_b200/smallfit.py) -- the README quickstart
+and the leave-one-out regime of the reference's notebooks -- against the live-reference fixtures, the numpy oracle and the
+streaming kernels; and the batched cross-validation (every fold a CTA of the same launch, every prefix model from one fit)
+against an explicit refit loop.  (conftest.py switches the automatic small path off so that the rest of the suite keeps
+exercising the streaming kernels; here it is requested with small_path=True or the environment switch is lifted.)"""
+import os
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import assert_fixture_trips, assert_trips, compare, live_cases, load_live, rel_err, snapshot_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+DENSE_NIPALS = [c for c in live_cases() if "nipals" in c and "unipals" not in c and "nan" not in c]
+
+
+def _launches():
+    from mbpls_b200 import _cabi
+    return _cabi.launch_count
+
+
+@pytest.mark.parametrize("name", DENSE_NIPALS)
+def test_one_kernel_fit_matches_reference_fixture(name):
+    from mbpls_b200 import MBPLS
+    X, Y, Xt, Yt, kwargs, ref = load_live(name)
+    cp = (lambda a: [x.copy() for x in a] if isinstance(a, list) else a.copy())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = _launches()
+        m = MBPLS(**kwargs).set_runtime(small_path=True).fit(cp(X), cp(Y))
+        used = _launches() - c0
+    assert used == 1, f"the whole fit must be one kernel launch, counted {used}"
+    ours = snapshot_model(m, Xt, Yt)
+    compare(ours, ref, TOL, name + " [one kernel]")
+    assert_fixture_trips(ours["n_iter_"], name, ref)
+
+
+def test_readme_quickstart_takes_the_one_kernel_path_by_default(monkeypatch):
+    """BASELINE config 1 (README.rst:82-95): 40 x (200 + 250), y 40 x 1, 3 components."""
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    from oracle.cases import readme_quickstart
+    monkeypatch.delenv("MBPLS_SMALL_PATH", raising=False)
+    X, y = readme_quickstart(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = _launches()
+        m = MBPLS(n_components=3, method="NIPALS").fit([x.copy() for x in X], y.copy())
+        assert _launches() - c0 == 1
+        o = OracleMBPLS(n_components=3, method="NIPALS").fit([x.copy() for x in X], y.copy())
+    ref, ours = snapshot_model(o, [x[:9] for x in X], y[:9]), snapshot_model(m, [x[:9] for x in X], y[:9])
+    compare(ours, ref, TOL, "README quickstart")
+    assert list(m.n_iter_) == list(o.n_iter_) == [2, 2, 2]
+    # an explicit choice among the streaming kernels keeps the fit on them
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = _launches()
+        m2 = MBPLS(n_components=3).set_runtime(one_pass=True).fit([x.copy() for x in X], y.copy())
+        assert _launches() - c0 > 10
+    assert rel_err(m2.beta_, m.beta_) < 1e-10
+    m3 = pickle.loads(pickle.dumps(m))
+    assert np.allclose(m3.predict(X), m.predict(X), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,sizes,q,K", [(7, (3, 2), 1, 2), (33, (1, 17, 1), 2, 3), (100, (200, 250), 1, 15), (1500, (40, 30), 3, 4),
+                                         (300, (64,), 10, 6)])
+def test_one_kernel_fit_matches_oracle_and_streaming_kernels(n, sizes, q, K):
+    from mbpls_b200 import MBPLS
+    from oracle import OracleMBPLS
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(n, sizes, q, K, seed=n + K)
+    Xt, Yt = latent_blocks(11, sizes, q, K, seed=3)
+    kw = dict(n_components=K, method="NIPALS")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(**kw).fit([x.copy() for x in X], Y.copy())
+        m = MBPLS(**kw).set_runtime(small_path=True).fit([x.copy() for x in X], Y.copy())
+        s = MBPLS(**kw).set_runtime(small_path=False).fit([x.copy() for x in X], Y.copy())
+    ref, ours = snapshot_model(o, Xt, Yt), snapshot_model(m, Xt, Yt)
+    compare(ours, ref, TOL, f"one kernel n={n}")
+    assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, 1e-14, f"one kernel n={n}")
+    assert rel_err(m.beta_, s.beta_) < 1e-9
+
+
+def test_one_kernel_fit_with_more_components_than_rank_uses_the_pseudo_inverse():
+    """P'W singular (K beyond the rank of the centred data): R = W pinv(P'W) like the reference (:988), not a division."""
+    from mbpls_b200 import MBPLS
+    rng = np.random.default_rng(5)
+    Z = rng.standard_normal((6, 2))
+    X = Z @ rng.standard_normal((2, 9))          # rank 2 exactly (rank <= 2 after centring)
+    y = Z @ np.array([1.0, -0.5])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = MBPLS(n_components=4).set_runtime(small_path=True).fit(X.copy(), y.copy())
+        b = MBPLS(n_components=4).set_runtime(small_path=False).fit(X.copy(), y.copy())
+    assert np.all(np.isfinite(a.beta_)) and np.all(np.isfinite(a.predict(X)))
+    assert rel_err(a.predict(X), b.predict(X)) < 1e-6
+
+
+def test_nan_input_is_rejected_and_nan_mode_stays_on_the_streaming_kernels():
+    from mbpls_b200 import MBPLS
+    rng = np.random.default_rng(6)
+    X, y = rng.standard_normal((30, 8)), rng.standard_normal(30)
+    X[3, 2] = np.nan
+    with pytest.raises(ValueError):
+        MBPLS(n_components=1).set_runtime(small_path=True).fit(X.copy(), y.copy())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = _launches()
+        MBPLS(n_components=1, sparse_data=True).set_runtime(small_path=True).fit(X.copy(), y.reshape(-1, 1).copy())
+        assert _launches() - c0 > 5
+
+
+def _oracle_cv(kw, X, Y, folds):
+    from oracle import OracleMBPLS
+    out = np.full((Y.shape[0], Y.shape[1] if Y.ndim == 2 else 1), np.nan)
+    for tr, te in folds:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = OracleMBPLS(**kw).fit([x[tr] for x in X], Y[tr])
+            out[te] = m.predict([x[te] for x in X])
+    return out
+
+
+def test_leave_one_out_over_a_component_range_in_one_launch():
+    """The notebooks' model selection (Carbohydrate_Microarray_PLS.ipynb: cross_val_predict(..., cv=len(X)) for 15 component
+    counts): 60 folds x 6 prefix models from ONE kernel launch, against 6 x 60 oracle refits."""
+    from sklearn.model_selection import LeaveOneOut
+    from mbpls_b200 import MBPLS
+    from mbpls_b200.model_selection import cross_val_predict
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(60, (40, 55), 1, 6, seed=41)
+    y = Y.ravel()
+    folds = list(LeaveOneOut().split(np.arange(60)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = _launches()
+        path = cross_val_predict(MBPLS(n_components=2).set_runtime(small_path=True), X, y, cv=LeaveOneOut(),
+                                 n_components_list=range(1, 7))
+        assert _launches() - c0 == 1
+    for k in range(1, 7):
+        want = _oracle_cv(dict(n_components=k), X, Y, folds).ravel()
+        assert path[k].shape == y.shape and rel_err(path[k], want) < 1e-9, k
+
+
+@pytest.mark.parametrize("q,cv", [(2, 5), (1, 7)])
+def test_kfold_batched_matches_fold_loop(q, cv):
+    from sklearn.model_selection import KFold
+    from mbpls_b200 import MBPLS
+    from mbpls_b200.model_selection import cross_val_predict
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(45, (20, 12, 9), q, 3, seed=43)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = cross_val_predict(MBPLS(n_components=3).set_runtime(small_path=True), X, Y, cv=cv)
+        b = cross_val_predict(MBPLS(n_components=3).set_runtime(small_path=False), X, Y, cv=cv)
+    want = _oracle_cv(dict(n_components=3), X, Y, list(KFold(n_splits=cv).split(np.arange(45))))
+    assert rel_err(a, want) < 1e-9 and rel_err(b, want) < 1e-9
