@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 10
+#define MBPLS_ABI_VERSION 11
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -50,6 +50,9 @@ int mbpls_abi_version(void);
 /* ---- ingest (mbpls.py:301-323 check_array copies, :379 hstack) ---------------------------------- */
 /* row-major chunk (rows x cols, leading dim lds) -> feature-major dst[c*ld + row0 + r] */
 int mbpls_transpose_in_f64(const double* src, long lds, int rows, int cols, double* dst, long ld, int row0, void* stream);
+/* same from a single-precision row-major source: check_array(dtype=float64) (mbpls.py:310) widens float32 inputs on the
+ * host; here they cross PCIe at half the size and are widened inside the transposition */
+int mbpls_transpose_in_f32(const float* src, long lds, int rows, int cols, double* dst, long ld, int row0, void* stream);
 /* feature-major -> row-major */
 int mbpls_transpose_out_f64(const double* src, long ld, int rows, int cols, double* dst, long ldd, int row0, void* stream);
 
@@ -213,6 +216,7 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
  *                                   trips (K) | varx per block (B) | vary | singular
  *   R [K][p], beta [q][p]   R = W (P'W)^-1 by substitution (P'W is upper triangular for NIPALS) and beta = R V' (:986-989);
  *                           singular = 1 flags a (near-)singular P'W: apply the pseudo-inverse on the host side instead
+ * train_idx == NULL (nfits == 1): the fit uses every sample of the source, in order.
  * Xw [nfits][p*ldw] / Yw [nfits][q*ldw] receive the standardised (then deflated) copies; scratch holds
  * mbpls_smallfit_scratch_doubles(...) doubles per fit (scratch_stride).  With preds != NULL the CTA also predicts the
  * samples test_idx[f*ld_tidx .. + test_cnt[f]) for every prefix of its model: preds[k][sample][c], k+1 components
@@ -279,8 +283,10 @@ int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const do
                              double* out, long ldout, void* stream);
 /* out_part[s][c][i] = sum_{j in split s} nan0(z_ij) * Bm[c][j]   (X.dot(beta_), X.dot(R_), X_b.dot(W_b));
  * z_ij = Xt[j][i], or (Xt[j][i] - mean[j]) / scale[j] when mean/scale are given (x_scalers_[b].transform fused
- * into the product, mbpls.py:1097,:1369, so predict reads new data exactly once).  nonfinite_flag (optional) is
- * set to 1 if any raw element is NaN or inf (check_array's finiteness test, :1368, without an extra pass). */
+ * into the product, mbpls.py:1097,:1369, so predict reads new data exactly once); with mean given and scale == NULL
+ * only the centring is applied -- the caller has folded 1 / scale[j] into Bm, which takes the fp64 division out of the
+ * streaming loop.  nonfinite_flag (optional) is set to 1 if any raw element is NaN or inf (check_array's finiteness
+ * test, :1368, without an extra pass). */
 int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
                           const int* split_f1, int nsplit, double* out_part, long ldo, const double* mean,
                           const double* scale, int* nonfinite_flag, void* stream);

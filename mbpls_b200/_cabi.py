@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -72,6 +72,7 @@ class RecordArgs(C.Structure):
 SIGNATURES = {
     "mbpls_abi_version": [],
     "mbpls_transpose_in_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
+    "mbpls_transpose_in_f32": [_p, _l, _i, _i, _p, _l, _i, _p],
     "mbpls_transpose_out_f64": [_p, _l, _i, _i, _p, _l, _i, _p],
     "mbpls_nan_census_f64": [_p, _l, _i, _i, _p, _i, _p, _p, _l, _p, _p],
     "mbpls_standardize_fit_f64": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p],

@@ -105,9 +105,14 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
       if (last_is_pad) x[k].y = 0.0;  // element n of an odd-length feature is not a sample (an adopted view may hold anything there)
       bad |= !isfinite(x[k].x) | !isfinite(x[k].y);
       if (mean) {  // StandardScaler.transform fused into the product (mbpls.py:1097,:1369): z = (x - mean) / scale
-        const double m = __ldg(mean + j + k), sc = __ldg(scale + j + k);
-        x[k].x = (x[k].x - m) / sc;
-        x[k].y = (x[k].y - m) / sc;
+        const double m = __ldg(mean + j + k);
+        x[k].x -= m;
+        x[k].y -= m;
+        if (scale) {  // (scale == NULL: the caller folded 1 / scale into Bm, no fp64 division in the streaming loop)
+          const double sc = __ldg(scale + j + k);
+          x[k].x /= sc;
+          x[k].y /= sc;
+        }
       }
       if (isnan(x[k].x)) x[k].x = 0.0;
       if (isnan(x[k].y)) x[k].y = 0.0;
@@ -129,9 +134,14 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
     if (last_is_pad) x.y = 0.0;
     bad |= !isfinite(x.x) | !isfinite(x.y);
     if (mean) {
-      const double m = __ldg(mean + j), sc = __ldg(scale + j);
-      x.x = (x.x - m) / sc;
-      x.y = (x.y - m) / sc;
+      const double m = __ldg(mean + j);
+      x.x -= m;
+      x.y -= m;
+      if (scale) {
+        const double sc = __ldg(scale + j);
+        x.x /= sc;
+        x.y /= sc;
+      }
     }
     if (isnan(x.x)) x.x = 0.0;
     if (isnan(x.y)) x.y = 0.0;
@@ -220,7 +230,7 @@ int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const do
 int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
                           const int* split_f1, int nsplit, double* out_part, long ldo, const double* mean,
                           const double* scale, int* nonfinite_flag, void* stream) {
-  if ((mean == nullptr) != (scale == nullptr)) return MBPLS_ERR_ARG;
+  if (scale != nullptr && mean == nullptr) return MBPLS_ERR_ARG;  // mean alone: centring only (1 / scale folded into Bm)
   if (!Xt || !Bm || !split_f0 || !split_f1 || !out_part || C < 1 || (ld % 2) != 0 || (ldo % 2) != 0) return MBPLS_ERR_ARG;
   if (nsplit == 0 || n == 0) return MBPLS_OK;
   if (nsplit > 65535) return MBPLS_ERR_SIZE;

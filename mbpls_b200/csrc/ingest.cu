@@ -12,7 +12,8 @@ using namespace mbpls;
 // the feature-major matrix at features [0, cols) (dst already offset to the block) and samples
 // [row0, row0 + rows).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) transpose_in_kernel(const double* __restrict__ src, long lds, int rows, int cols,
+template <class T>  // T = double, or float: single-precision sources are widened here, on the device, after a half-size upload
+__global__ void __launch_bounds__(256) transpose_in_kernel(const T* __restrict__ src, long lds, int rows, int cols,
                                                            double* __restrict__ dst, long ld, int row0) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -20,7 +21,7 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const double* __restr
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = r0 + ty + 8 * k, c = c0 + tx;
-    if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[static_cast<size_t>(r) * lds + c];
+    if (r < rows && c < cols) tile[ty + 8 * k][tx] = static_cast<double>(src[static_cast<size_t>(r) * lds + c]);
   }
   __syncthreads();
 #pragma unroll
@@ -419,7 +420,15 @@ int mbpls_transpose_in_f64(const double* src, long lds, int rows, int cols, doub
   if (!src || !dst || rows < 0 || cols < 0) return MBPLS_ERR_ARG;
   if (rows == 0 || cols == 0) return MBPLS_OK;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  transpose_in_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, dst, ld, row0);
+  transpose_in_kernel<double><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, dst, ld, row0);
+  MBPLS_RETURN_LAST();
+}
+
+int mbpls_transpose_in_f32(const float* src, long lds, int rows, int cols, double* dst, long ld, int row0, void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0) return MBPLS_ERR_ARG;
+  if (rows == 0 || cols == 0) return MBPLS_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_in_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, rows, cols, dst, ld, row0);
   MBPLS_RETURN_LAST();
 }
 

@@ -39,12 +39,12 @@ __device__ __forceinline__ double sf_ingest_feature(const double* __restrict__ s
   double mean = 0.0, var = 0.0, scale = 1.0;
   if (standardize) {
     double s = 0.0;
-    for (int t = lane; t < ntr; t += 32) s += src[tr[t]];
+    for (int t = lane; t < ntr; t += 32) s += src[tr ? tr[t] : t];
     s = warp_sum(s);
     mean = s / ntr;
     double c = 0.0, ss = 0.0;
     for (int t = lane; t < ntr; t += 32) {
-      const double d = src[tr[t]] - mean;
+      const double d = src[tr ? tr[t] : t] - mean;
       c += d;
       ss += d * d;
     }
@@ -54,7 +54,7 @@ __device__ __forceinline__ double sf_ingest_feature(const double* __restrict__ s
   }
   double z2 = 0.0;
   for (int t = lane; t < ntr; t += 32) {
-    double z = src[tr[t]];
+    double z = src[tr ? tr[t] : t];
     if (standardize) {
       z = z - mean;
       z = z / scale;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) smallfit_kernel(const mbpls_sma
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = a.p, B = a.B, q = a.q, K = a.K;
   const long ldw = a.ldw;
-  const int ntr = a.train_cnt[f];
-  const int* __restrict__ tr = a.train_idx + static_cast<size_t>(f) * a.ld_idx;
+  const int ntr = a.train_cnt ? a.train_cnt[f] : a.n_src;  // train_idx == NULL: every sample of the source, in order
+  const int* __restrict__ tr = a.train_idx ? a.train_idx + static_cast<size_t>(f) * a.ld_idx : nullptr;
 
   double* Xw = a.Xw + static_cast<size_t>(f) * p * ldw;
   double* Yw = a.Yw + static_cast<size_t>(f) * q * ldw;
@@ -415,12 +415,13 @@ int mbpls_smallfit_scratch_doubles(int p, int B, long ldw) {
 }
 
 int mbpls_smallfit_nipals_f64(const mbpls_smallfit_args* a, void* stream) {
-  if (!a || !a->Xsrc || !a->Ysrc || !a->block_off || !a->train_idx || !a->train_cnt || !a->Xw || !a->Yw || !a->stats || !a->Wt ||
+  if (!a || !a->Xsrc || !a->Ysrc || !a->block_off || (a->train_idx && !a->train_cnt) || !a->Xw || !a->Yw || !a->stats || !a->Wt ||
       !a->W || !a->P || !a->Ts || !a->U || !a->Tb || !a->small || !a->R || !a->beta || !a->scratch)
     return MBPLS_ERR_ARG;
   if (a->B < 1 || a->B > SF_MAXB || a->q < 1 || a->q > SF_MAXQ || a->K < 1 || a->K > SF_THREADS || a->p < 1 || a->nfits < 1)
     return MBPLS_ERR_SIZE;
   if (a->preds && (!a->test_idx || !a->test_cnt)) return MBPLS_ERR_ARG;
+  if (!a->train_idx && (a->nfits != 1 || a->ldw < a->n_src)) return MBPLS_ERR_ARG;
   const int need = mbpls_smallfit_scratch_doubles(a->p, a->B, a->ldw);
   if (need < 0 || a->scratch_stride < need) return MBPLS_ERR_ARG;
   smallfit_kernel<<<a->nfits, SF_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*a);

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import math
+import warnings
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -124,31 +125,35 @@ def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, dev
     cols = c1 - c0
     if cols <= 0:
         return
+    # float32 sources stay float32 until they are on the device (half the PCIe bytes; the reference widens them on the host,
+    # check_array(dtype=float64) at mbpls.py:310); anything else that is not float64 is widened here
     if isinstance(block, torch.Tensor):
-        t = block if block.dtype == F64 else block.to(F64)
+        t = block if block.dtype in (F64, torch.float32) else block.to(F64)
     else:
         arr = np.asarray(block)
-        if arr.dtype != np.float64:
+        if arr.dtype not in (np.float64, np.float32):
             arr = arr.astype(np.float64)
-        if not arr.flags.writeable:
-            arr = arr.copy()
-        t = torch.from_numpy(arr)
+        with warnings.catch_warnings():  # read-only sources (memory maps, pandas views) are only ever read
+            warnings.simplefilter("ignore")
+            t = torch.from_numpy(arr)
     view = t[:, c0:c1]
+    f32 = view.dtype == torch.float32
+    tr_in = "mbpls_transpose_in_f32" if f32 else "mbpls_transpose_in_f64"
     if view.stride(0) == 1 and n > 1:  # column-major == feature-major
-        dst[:, :n].copy_(view.t(), non_blocking=True)
+        dst[:, :n].copy_(view.t(), non_blocking=True)  # (widens float32 on the device side of the copy)
         torch.cuda.current_stream(device).synchronize()
         return
     if view.stride(1) != 1:
         view = view.contiguous()
     if view.is_cuda:
-        call("mbpls_transpose_in_f64", ptr(view), view.stride(0), n, cols, ptr(dst), ld, 0, stream_ptr(device))
+        call(tr_in, ptr(view), view.stride(0), n, cols, ptr(dst), ld, 0, stream_ptr(device))
         torch.cuda.current_stream(device).synchronize()  # `view` may be a temporary
         return
-    rows_per = max(1, min(n, _STAGE_BYTES // max(8 * cols, 1)))
+    rows_per = max(1, min(n, _STAGE_BYTES // max(view.element_size() * cols, 1)))
     # two staging buffers: the copy engine fills one (side stream) while the transpose kernel drains the other
     main = torch.cuda.current_stream(device)
     side = _copy_stream(device)
-    stages = [torch.empty((rows_per, cols), dtype=F64, device=device) for _ in range(2 if n > rows_per else 1)]
+    stages = [torch.empty((rows_per, cols), dtype=view.dtype, device=device) for _ in range(2 if n > rows_per else 1)]
     drained = [None] * len(stages)
     side.wait_stream(main)  # dst / staging allocations and earlier writes are ordered on the main stream
     for idx, r0 in enumerate(range(0, n, rows_per)):
@@ -161,7 +166,7 @@ def ingest_feature_major(block, n: int, c0: int, c1: int, dst: torch.Tensor, dev
             filled = torch.cuda.Event()
             filled.record(side)
         main.wait_event(filled)
-        call("mbpls_transpose_in_f64", ptr(stages[i]), cols, r1 - r0, cols, ptr(dst), ld, r0, stream_ptr(device))
+        call(tr_in, ptr(stages[i]), cols, r1 - r0, cols, ptr(dst), ld, r0, stream_ptr(device))
         drained[i] = torch.cuda.Event()
         drained[i].record(main)
     main.synchronize()
@@ -733,6 +738,11 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
     p, ld = Xt.shape
     Cc = Bm.shape[0]
     out = torch.zeros((Cc, ld), dtype=F64, device=dev)
+    if scale is not None and p > 0:
+        # (x - mean) / scale . b  ==  (x - mean) . (b / scale): the division moves from every element of X to the C x p
+        # coefficients (an fp64 divide per element halves the rate of this memory-bound pass)
+        Bm = (Bm[:, :p] / scale[:p].view(1, -1)).contiguous()
+        scale = None
     if p > 0 and n > 0:
         f0, f1, _ = make_splits(block_off, n, sm_count(dev))
         ns = len(f0)

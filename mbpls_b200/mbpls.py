@@ -96,8 +96,8 @@ def _as_2d_source(a, what: str, allow_empty: bool = False):
     if isinstance(a, torch.Tensor):
         t = a
     else:
-        t = np.asarray(a)
-        if t.dtype != np.float64:
+        t = np.asarray(a)  # pandas DataFrames included (a view when the frame is one float block)
+        if t.dtype not in (np.float64, np.float32):  # float32 is widened on the device, after the upload (engine.ingest_feature_major)
             try:
                 t = t.astype(np.float64)
             except (TypeError, ValueError) as exc:
@@ -502,8 +502,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         D, n, sizes, p, q, ldx = SF.pack_source(blocks, Ysrc, device)
         shard = ShardMap.build(sizes, 0, 1)
         lay, out, _, keep = SF.launch(D, n, p, q, ldx, shard.block_off, K, bool(self.standardize),
-                                      E.norm_kind_of(self.nipals_convergence_norm), self.max_tol, rt["max_iter"],
-                                      [np.arange(n, dtype=np.int32)])
+                                      E.norm_kind_of(self.nipals_convergence_norm), self.max_tol, rt["max_iter"], None)
         host = E.to_host(out)  # one copy: every result of the fit
         ldw = lay.ldw
         sm = SF.unpack_small(lay.view(host, "small"), K, q, B)
@@ -528,14 +527,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.__dict__["_dev"] = dict(shard=shard, R=R_d, beta=beta_d, W=W_d, P=P_d, V=V_d, _keep=(out, keep))
         self.__dict__["_cv_weights"] = Wt_d
         st_d, st_h = lay.view(out, "stats"), lay.view(host, "stats")
+        lazy = {}
         if self.standardize:
             self.__dict__["_dev_scalers"] = (st_d[0:p], st_d[2 * p:3 * p], st_d[4 * p:4 * p + q], st_d[4 * p + 2 * q:4 * p + 3 * q])
+            off_ = shard.block_off
             seen = np.full(p, n, dtype=np.int64)
-            off = shard.block_off
-            self.x_scalers_ = [_make_scaler(st_h[off[b]:off[b + 1]], st_h[p + off[b]:p + off[b + 1]],
-                                            st_h[2 * p + off[b]:2 * p + off[b + 1]], seen[off[b]:off[b + 1]]) for b in range(B)]
-            self.y_scaler_ = _make_scaler(st_h[4 * p:4 * p + q], st_h[4 * p + q:4 * p + 2 * q], st_h[4 * p + 2 * q:4 * p + 3 * q],
-                                          np.full(q, n, dtype=np.int64))
+            # scikit-learn scaler objects on first access (constructing B + 1 estimators is a tenth of this path's time)
+            lazy["x_scalers_"] = lambda: [_make_scaler(st_h[off_[b]:off_[b + 1]], st_h[p + off_[b]:p + off_[b + 1]],
+                                                       st_h[2 * p + off_[b]:2 * p + off_[b + 1]], seen[off_[b]:off_[b + 1]])
+                                          for b in range(B)]
+            lazy["y_scaler_"] = lambda: _make_scaler(st_h[4 * p:4 * p + q], st_h[4 * p + q:4 * p + 2 * q],
+                                                     st_h[4 * p + 2 * q:4 * p + 3 * q], np.full(q, n, dtype=np.int64))
         A = np.ascontiguousarray(sm["A"].T)
         self.A_ = A
         if self.calc_all:  # mbpls.py:932-964 from the reduced scalars
@@ -558,7 +560,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         self.T_ = [np.ascontiguousarray(Tb[b][:, :n].T) for b in range(B)]
         self.W_, self.W_non_normal_, self.P_ = split(hv("W", K, p)), split(hv("Wt", K, p)), split(hv("P", K, p))
         self.R_, self.beta_ = R_h, beta_h
-        self.__dict__["_lazy"] = None
+        self.__dict__["_lazy"] = lazy or None
         return True
 
     # ---- helpers of fit

@@ -40,29 +40,35 @@ def eligible(method: str, sparse: bool, group, n: int, p: int, force) -> bool:
 
 
 def pack_source(blocks: Sequence, Y, device):
-    """Feature-major source matrix [X_1' ; ... ; X_B' ; Y'] ((p + q) x ldx, raw values) on the device in one copy.
-    Host arrays are transposed into one pinned staging buffer; device tensors are concatenated on the device."""
+    """Feature-major source matrix [X_1' ; ... ; X_B' ; Y'] ((p + q) x ldx, raw values) on the device in ONE copy, with the
+    block offset table (B + 1 int32) behind it in the same buffer.  Host arrays are transposed into one pinned staging
+    buffer; device tensors are concatenated on the device.  Returns (flat device buffer, n, sizes, p, q, ldx)."""
     n = int(blocks[0].shape[0])
     sizes = [int(b.shape[1]) for b in blocks]
     p, q = sum(sizes), int(Y.shape[1])
     ldx = (n + 1) // 2 * 2
+    off = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    tail = (len(off) + 1) // 2  # doubles that hold the int32 table
     if all(isinstance(b, torch.Tensor) and b.is_cuda for b in blocks):
         Yd = Y if isinstance(Y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64))
         parts = [b.to(F64).t() for b in blocks] + [Yd.to(device=device, dtype=F64).t()]
-        D = torch.zeros((p + q, ldx), dtype=F64, device=device)
-        D[:, :n] = torch.cat(parts, dim=0)
+        D = torch.zeros((p + q) * ldx + tail, dtype=F64, device=device)
+        D[:(p + q) * ldx].view(p + q, ldx)[:, :n] = torch.cat(parts, dim=0)
+        D[(p + q) * ldx:].view(torch.int32)[:len(off)] = torch.from_numpy(off).to(device)
         return D, n, sizes, p, q, ldx
-    H = torch.empty((p + q, ldx), dtype=F64, pin_memory=True)
+    H = torch.empty((p + q) * ldx + tail, dtype=F64, pin_memory=True)
     Hn = H.numpy()
+    M = Hn[:(p + q) * ldx].reshape(p + q, ldx)
     o = 0
     for b in blocks:
         a = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
-        Hn[o:o + a.shape[1], :n] = a.T
+        M[o:o + a.shape[1], :n] = a.T
         o += a.shape[1]
     Ya = Y.detach().cpu().numpy() if isinstance(Y, torch.Tensor) else np.asarray(Y)
-    Hn[p:p + q, :n] = Ya.T
+    M[p:p + q, :n] = Ya.T
     if ldx > n:
-        Hn[:, n:] = 0.0
+        M[:, n:] = 0.0
+    Hn[(p + q) * ldx:].view(np.int32)[:len(off)] = off
     return H.to(device, non_blocking=True), n, sizes, p, q, ldx
 
 
@@ -93,32 +99,39 @@ class Layout:
 
 
 def launch(D: torch.Tensor, n_src: int, p: int, q: int, ldx: int, block_off: Sequence[int], K: int, standardize: bool,
-           norm_kind: int, max_tol: float, max_iter: int, train_sets: List[np.ndarray],
+           norm_kind: int, max_tol: float, max_iter: int, train_sets: Optional[List[np.ndarray]],
            test_sets: Optional[List[np.ndarray]] = None):
-    """Run ``len(train_sets)`` fits concurrently.  Returns (layout, packed device buffer, preds device tensor or None)."""
+    """Run ``len(train_sets)`` fits concurrently (train_sets None: one fit on all samples).  ``D`` is pack_source's buffer.
+    Returns (layout, packed device result buffer, preds device tensor or None, buffers to keep alive)."""
     dev = D.device
-    F = len(train_sets)
     B = len(block_off) - 1
-    ld_idx = max(len(t) for t in train_sets)
-    ldw = (ld_idx + 1) // 2 * 2
-    tr = np.zeros((F, ld_idx), dtype=np.int32)
-    cnt = np.zeros(F, dtype=np.int32)
-    for f, t in enumerate(train_sets):
-        tr[f, :len(t)] = t
-        cnt[f] = len(t)
-    ints = [tr.ravel(), cnt, np.asarray(block_off, dtype=np.int32)]
-    ld_t = 0
-    if test_sets is not None:
-        ld_t = max(1, max(len(t) for t in test_sets))
-        te = np.zeros((F, ld_t), dtype=np.int32)
-        tcnt = np.zeros(F, dtype=np.int32)
-        for f, t in enumerate(test_sets):
-            te[f, :len(t)] = t
-            tcnt[f] = len(t)
-        ints += [te.ravel(), tcnt]
-    packed = torch.from_numpy(np.concatenate(ints)).to(dev, non_blocking=True)  # every index table in one copy
-    offs = np.cumsum([0] + [len(a) for a in ints])
-    iptr = lambda i: C.c_void_p(packed.data_ptr() + 4 * int(offs[i]))
+    boff_ptr = C.c_void_p(D.data_ptr() + 8 * (p + q) * ldx)  # the table pack_source put behind the matrix
+    packed = None
+    if train_sets is None:  # one fit on every sample of the source: no index tables at all
+        F, ld_idx, ldw, ld_t = 1, n_src, (n_src + 1) // 2 * 2, 0
+        iptr = lambda i: None
+    else:
+        F = len(train_sets)
+        ld_idx = max(len(t) for t in train_sets)
+        ldw = (ld_idx + 1) // 2 * 2
+        tr = np.zeros((F, ld_idx), dtype=np.int32)
+        cnt = np.zeros(F, dtype=np.int32)
+        for f, t in enumerate(train_sets):
+            tr[f, :len(t)] = t
+            cnt[f] = len(t)
+        ints = [tr.ravel(), cnt]
+        ld_t = 0
+        if test_sets is not None:
+            ld_t = max(1, max(len(t) for t in test_sets))
+            te = np.zeros((F, ld_t), dtype=np.int32)
+            tcnt = np.zeros(F, dtype=np.int32)
+            for f, t in enumerate(test_sets):
+                te[f, :len(t)] = t
+                tcnt[f] = len(t)
+            ints += [te.ravel(), tcnt]
+        packed = torch.from_numpy(np.concatenate(ints)).to(dev, non_blocking=True)  # every index table in one copy
+        offs = np.cumsum([0] + [len(a) for a in ints])
+        iptr = lambda i: C.c_void_p(packed.data_ptr() + 4 * int(offs[i]))
     lay = Layout(F, p, q, B, K, ldw)
     out = torch.empty(lay.total, dtype=F64, device=dev)
     work = torch.empty(F * (p + q) * ldw, dtype=F64, device=dev)
@@ -128,10 +141,10 @@ def launch(D: torch.Tensor, n_src: int, p: int, q: int, ldx: int, block_off: Seq
     base = out.data_ptr()
     sec = lambda name: C.c_void_p(base + 8 * lay.off[name])
     args = _cabi.SmallFitArgs(
-        n_src=n_src, p=p, B=B, q=q, K=K, nfits=F, ldx=ldx, Xsrc=D.data_ptr(), Ysrc=D.data_ptr() + 8 * p * ldx, block_off=iptr(2),
+        n_src=n_src, p=p, B=B, q=q, K=K, nfits=F, ldx=ldx, Xsrc=D.data_ptr(), Ysrc=D.data_ptr() + 8 * p * ldx, block_off=boff_ptr,
         standardize=1 if standardize else 0, norm_kind=norm_kind, max_iter=int(min(max_iter, 2**31 - 1)), max_tol=float(max_tol),
         train_idx=iptr(0), train_cnt=iptr(1), ld_idx=ld_idx,
-        test_idx=iptr(3) if test_sets is not None else None, test_cnt=iptr(4) if test_sets is not None else None, ld_tidx=ld_t,
+        test_idx=iptr(2) if test_sets is not None else None, test_cnt=iptr(3) if test_sets is not None else None, ld_tidx=ld_t,
         ldw=ldw, Xw=work.data_ptr(), Yw=work.data_ptr() + 8 * F * p * ldw, stats=sec("stats"), Wt=sec("Wt"), W=sec("W"), P=sec("P"),
         Ts=sec("Ts"), U=sec("U"), Tb=sec("Tb"), small=sec("small"), R=sec("R"), beta=sec("beta"),
         preds=preds.data_ptr() if preds is not None else None, scratch=scratch.data_ptr(), scratch_stride=sstride)

@@ -35,7 +35,13 @@ def test_one_kernel_fit_matches_reference_fixture(name):
     assert used == 1, f"the whole fit must be one kernel launch, counted {used}"
     ours = snapshot_model(m, Xt, Yt)
     compare(ours, ref, TOL, name + " [one kernel]")
-    assert_fixture_trips(ours["n_iter_"], name, ref)
+    # trip counts: exact wherever the numpy oracle's diff_t leaves the loop with margin (a deep PLS1 component whose second-trip
+    # diff_t -- pure rounding noise -- sits at 1e-14 may take a third and fourth trip here or there, SURVEY.md finding 4)
+    from oracle import OracleMBPLS
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(**kwargs).fit(cp(X), cp(Y))
+    assert_trips(list(m.n_iter_), list(o.n_iter_), o.diff_trace_, kwargs.get("max_tol", 1e-14), name)
 
 
 def test_readme_quickstart_takes_the_one_kernel_path_by_default(monkeypatch):
