@@ -117,4 +117,8 @@ def assert_trips(ours, oracle_trips, oracle_traces, tol, what=""):
         if margin or tr is None:
             assert a == b, f"{what}: component {k}: {a} trips vs oracle {b}"
         else:
-            assert abs(a - b) <= 2, f"{what}: component {k}: {a} trips vs oracle {b} (grazing exit)"
+            # Grazing exit.  Once diff_t has come within 3x of the threshold every further trip is a coin flip on rounding
+            # noise (a PLS1 component, whose second trip repeats the first, took 2 trips with the numpy oracle on one host and
+            # 5 on another): any exit between the first trip of that hovering phase and two trips past the oracle's is accepted.
+            hover = next((i for i, d in enumerate(tr) if d < 3 * tol), len(tr) - 1) + 2  # tr[0] is the diff_t of trip 2
+            assert abs(a - b) <= 2 or hover <= a <= b + 2, f"{what}: component {k}: {a} trips vs oracle {b} (grazing exit)"
