@@ -80,8 +80,11 @@ right_multiply_kernel(const double* __restrict__ in, long ldin, int K, int p, co
 }
 
 // out_part[(s*C + c0 + c)*ldo + i] = sum_{j in split s} nan0(Xt[j][i]) * Bm[(c0+c)*ldb + j],  c < NC
-template <int NC>
-__global__ void __launch_bounds__(256)
+// FB features per step = independent 16-byte loads in flight per thread: 8 for narrow outputs (ncu at the C5 predict shape,
+// 1 M samples x 2,000 features, showed 79 % of the stall samples on the loads with 4 in flight), 4 when NC = 8 / 16
+// accumulator pairs already fill the registers.
+template <int NC, int FB>
+__global__ void __launch_bounds__(256, (NC <= 4 ? 3 : 1))
 skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* __restrict__ Bm, long ldb, int C, int c0,
                    const int* __restrict__ split_f0, const int* __restrict__ split_f1, double* __restrict__ out_part,
                    long ldo, const double* __restrict__ mean, const double* __restrict__ scale, int* __restrict__ flag) {
@@ -97,10 +100,10 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
   for (int c = 0; c < NC; ++c) ax[c] = ay[c] = 0.0;
   const double* __restrict__ xp = Xt + r;
   int j = f0;
-  for (; j + 4 <= f1; j += 4) {
-    double2 x[4];
+  for (; j + FB <= f1; j += FB) {
+    double2 x[FB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < FB; ++k) {
       x[k] = ld_stream(reinterpret_cast<const double2*>(xp + static_cast<size_t>(j + k) * ld));
       if (last_is_pad) x[k].y = 0.0;  // element n of an odd-length feature is not a sample (an adopted view may hold anything there)
       bad |= !isfinite(x[k].x) | !isfinite(x[k].y);
@@ -121,7 +124,7 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
     for (int c = 0; c < NC; ++c) {
       if (c < nc) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < FB; ++k) {
           const double bv = __ldg(Bm + static_cast<size_t>(c0 + c) * ldb + j + k);
           ax[c] = fma(x[k].x, bv, ax[c]);
           ay[c] = fma(x[k].y, bv, ay[c]);
@@ -238,11 +241,11 @@ int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, lo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int c0 = 0; c0 < C; c0 += 16) {
     const int nc = C - c0;
-    if (nc >= 16 || nc > 8) skinny_gemm_kernel<16><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
-    else if (nc > 4) skinny_gemm_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
-    else if (nc > 2) skinny_gemm_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
-    else if (nc > 1) skinny_gemm_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
-    else skinny_gemm_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    if (nc >= 16 || nc > 8) skinny_gemm_kernel<16, 4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 4) skinny_gemm_kernel<8, 4><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 2) skinny_gemm_kernel<4, 6><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else if (nc > 1) skinny_gemm_kernel<2, 8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
+    else skinny_gemm_kernel<1, 8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
   }
   MBPLS_RETURN_LAST();
 }

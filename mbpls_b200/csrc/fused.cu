@@ -585,7 +585,6 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 using CfgA = Cfg<512, 5, 2, 3>;   // <= 5120 units: one worker per CTA, 40 KB chunks (u + ring = 200 KB)
 using CfgA4 = Cfg<512, 2, 5, 4>;  // same length with two resident vectors (deflate: ts and u0): only 64 KB of ring left
 using CfgB = Cfg<256, 5, 2, 3>;   // <= 2560 units: two workers, 20 KB chunks
-using CfgB4 = Cfg<256, 5, 2, 4>;  // same with a deeper ring: the trip kernel on CTA pairs (half of u per CTA leaves room for 160 KB)
 using CfgC = Cfg<128, 5, 2, 4>;   // <= 1280 units: four workers, 10 KB chunks
 using CfgD = Cfg<64, 10, 1, 2>;   // <= 640 units: eight workers, one chunk per feature
 
@@ -679,16 +678,6 @@ Plan plan_of(long ld) {
     pl.trip = 1;
     pl.deflate = 5;
     pl.workers = sms * CfgA::G;
-    static int trip_pairs = -2;  // MBPLS_FUSED_TRIP_CLUSTER=1: the trip kernel on CTA pairs too (experiment switch)
-    if (trip_pairs == -2) {
-      trip_pairs = -1;
-      if (cluster_enabled() && env_int("MBPLS_FUSED_TRIP_CLUSTER", 0))
-        trip_pairs = max_active_pairs(fused_trip_kernel<false, CfgB4, true>, fused_smem_bytes<CfgB4>(ld >> 1, 1));
-    }
-    if (trip_pairs * CfgB4::G >= pl.workers) {
-      pl.trip = 6;
-      pl.trip_cl = true;
-    }
     if (cluster_enabled()) {
       if (pairs_b < 0) pairs_b = max_active_pairs(fused_deflate_kernel<false, CfgB, true>, fused_smem_bytes<CfgB>(ld >> 1, 2));
       if (pairs_b * CfgB::G >= pl.workers * 9 / 10) {  // (almost) every SM gets a CTA: worth it
@@ -719,7 +708,6 @@ int dispatch_trip(int cfg, const FusedArgs& a, cudaStream_t st) {
   switch (cfg) {
     case 1: return launch_fused(fused_trip_kernel<NANMODE, CfgA, CL>, a, CfgA::G, fused_smem_bytes<CfgA>(vlen, 1), CL, st);
     case 2: return launch_fused(fused_trip_kernel<NANMODE, CfgB, CL>, a, CfgB::G, fused_smem_bytes<CfgB>(vlen, 1), CL, st);
-    case 6: return launch_fused(fused_trip_kernel<NANMODE, CfgB4, CL>, a, CfgB4::G, fused_smem_bytes<CfgB4>(vlen, 1), CL, st);
     case 3: return launch_fused(fused_trip_kernel<NANMODE, CfgC, false>, a, CfgC::G, fused_smem_bytes<CfgC>(a.ld, 1), false, st);
     case 4: return launch_fused(fused_trip_kernel<NANMODE, CfgD, false>, a, CfgD::G, fused_smem_bytes<CfgD>(a.ld, 1), false, st);
     default: return MBPLS_ERR_SIZE;

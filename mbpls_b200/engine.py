@@ -615,8 +615,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     for k in range(K):
         call("mbpls_nipals_begin_component_f64", ptr(u0), n, ptr(u), ptr(scal), ptr(ctrl), st)
         launched = 0
+        batch, prev_diff = trips_per_sync, None
         while True:
-            for _ in range(trips_per_sync):
+            for _ in range(max(1, min(batch, max_iter - launched))):
                 first = launched == 0
                 have_scores = first and w_ready == "scores"  # the deflation pass has already left the first trip's scores
                 if have_scores or (use_op and not (first and w_ready == "w")):
@@ -648,6 +649,16 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 raise _cabi.MbplsCudaError("a peer GPU did not arrive at the in-kernel exchange of a NIPALS trip (timeout)")
             if int(ctrl_h[_cabi.CTRL_DONE]) or int(ctrl_h[_cabi.CTRL_TRIPS]) >= max_iter:
                 break
+            # PLS2 loops converge geometrically: from the last two readings of diff_t estimate how many trips remain and enqueue
+            # most of them before the next readback (trips past convergence are no-ops, so an over-estimate costs microseconds;
+            # diff_t is bit-identical on every rank, so every rank enqueues the same number of exchanges)
+            d = float(scal_h[_cabi.SCAL_DIFF])
+            batch = trips_per_sync
+            if prev_diff is not None and 0.0 < d < prev_diff and d > max_tol > 0.0:
+                rate = (d / prev_diff) ** (1.0 / max(1, last_batch))
+                if 0.0 < rate < 0.999:
+                    batch = int(min(64, max(trips_per_sync, math.log(max_tol / d) / math.log(rate) - 1)))
+            prev_diff, last_batch = d, batch
         res.n_iter.append(int(ctrl_h[_cabi.CTRL_TRIPS]))
         res.diff.append(float(scal_h[_cabi.SCAL_DIFF]))
         res.tt.append(float(scal_h[_cabi.SCAL_TT]))
