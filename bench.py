@@ -658,7 +658,8 @@ def run_ours(args):
 
     x_bytes_local = 8.0 * n * shard.p_local
     kern = {}
-    for key, mult in (("trip", 1.0), ("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0), ("loadings", 1.0), ("standardize", 2.0)):
+    for key, mult in (("trip", 1.0), ("xtu", 1.0), ("xw", 1.0), ("deflate", 2.0), ("loadings", 1.0), ("standardize", 2.0),
+                      ("xchg", 0.0)):  # xchg: split sums + exchange between the GPUs + superlevel step (no X traffic; time incl. peer wait)
         t = mean_ms(key)
         if t:
             kern[key] = {"ms": t, "launches": len(profile[key]), "algorithmic_bytes": mult * x_bytes_local,
@@ -667,7 +668,7 @@ def run_ours(args):
     rank_skew = None
     if world > 1:
         try:
-            keys = ("trip", "deflate", "standardize", "loadings")
+            keys = ("trip", "deflate", "standardize", "loadings", "xchg")
             mine = torch.tensor([kern[k]["ms"] if k in kern else 0.0 for k in keys], dtype=torch.float64, device=dev)
             allv = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allv, mine, group=group)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 11
+#define MBPLS_ABI_VERSION 12
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -290,6 +290,11 @@ int mbpls_right_multiply_f64(const double* in, long ldin, int K, int p, const do
 int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, long ldb, int C, const int* split_f0,
                           const int* split_f1, int nsplit, double* out_part, long ldo, const double* mean,
                           const double* scale, int* nonfinite_flag, void* stream);
+/* The same product for tall batches (m >> p, at most 4 outputs, all p features): out[c*ldo + i] written directly.
+ * Persistent CTAs stream 16 KB chunks of every feature through a 192 KB ring of bulk (TMA) copies instead of issuing
+ * per-thread loads 8 MB apart.  mean (optional) centres; 1 / scale must already be folded into Bm. */
+int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* Bm, long ldb, int C, double* out, long ldo,
+                               const double* mean, int* nonfinite_flag, void* stream);
 /* X_b <- X_b - ts p_b' for new data (transform, mbpls.py:1145,1204); NaNs stay NaN */
 int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, const double* pvec, void* stream);
 /* column norms / scaling of a C x ld feature-major array over n samples */

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -110,6 +110,7 @@ SIGNATURES = {
     "mbpls_reduce_chunks_f64": [_p, _i, _i, _p, _p],
     "mbpls_right_multiply_f64": [_p, _l, _i, _i, _p, _p, _i, _p, _l, _p],
     "mbpls_skinny_gemm_f64": [_p, _l, _i, _p, _l, _i, _p, _p, _i, _p, _l, _p, _p, _p, _p],
+    "mbpls_skinny_gemm_tall_f64": [_p, _l, _i, _i, _p, _l, _i, _p, _l, _p, _p, _p],
     "mbpls_rank1_update_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_rows_sumsq_f64": [_p, _l, _i, _i, _p, _p],
     "mbpls_rows_scale_f64": [_p, _l, _i, _i, _p, _i, _p],

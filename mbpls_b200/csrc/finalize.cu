@@ -167,6 +167,117 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
   if (flag && bad) *flag = 1;  // idempotent: lets the caller reject NaN/inf input without an extra pass
 }
 
+// ------------------------------------------------------------------------------------------
+// Tall batches (predict / superscores on m >> p new samples, BASELINE config 5): the same product as skinny_gemm_kernel
+// fed by a shared-memory ring instead of per-thread loads.  With one feature 8 MB long every thread-level load of the
+// kernel above touches a different row; ncu (1 M x 2,000 -> 4) showed 79 % of its stall samples on those loads with
+// <= 74 KB in flight per SM (3.3 TB/s).  Here a persistent CTA owns tiles of TS samples: a producer warp streams the
+// tile's chunk of every feature (TS * 8 bytes, 1-D bulk / TMA copy) through a ring of TR stages tracked by full / empty
+// mbarriers (192 KB in flight per SM), 8 consumer warps hold the tile's NC x TS outputs in registers.  One CTA covers
+// all features of its tile, so results are written directly (no split partials, fixed summation order).
+// ------------------------------------------------------------------------------------------
+#define TALL_TS 2048  // samples per tile = 16 KB per feature chunk
+#define TALL_TR 12    // ring stages (192 KB)
+#define TALL_U 4      // 16-byte units per consumer thread (256 consumer threads x 4 x 2 samples = TS)
+
+template <int NC>
+__global__ void __launch_bounds__(288, 1)
+skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ Bm, long ldb, int C,
+                   double* __restrict__ out, long ldo, const double* __restrict__ mean, int* __restrict__ flag) {
+  extern __shared__ __align__(128) unsigned char tall_smem[];
+  double* ring = reinterpret_cast<double*>(tall_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tall_smem + static_cast<size_t>(TALL_TR) * TALL_TS * sizeof(double));
+  uint64_t* empty = full + TALL_TR;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntiles = (n + TALL_TS - 1) / TALL_TS;
+  const int nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long total = static_cast<long>(nmine) * p;  // chunks this CTA streams, in (tile, feature) order
+  if (tid == 0) {
+    for (int s = 0; s < TALL_TR; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 8) {  // producer: one elected lane issues every bulk copy
+    if (lane == 0) {
+      for (long c = 0; c < total; ++c) {
+        const int s = static_cast<int>(c % TALL_TR);
+        if (c >= TALL_TR) mbar_wait(&empty[s], static_cast<uint32_t>(((c / TALL_TR) - 1) & 1));
+        const int tile = blockIdx.x + static_cast<int>(c / p) * gridDim.x, j = static_cast<int>(c % p);
+        const long i0 = static_cast<long>(tile) * TALL_TS;
+        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long>(TALL_TS), ld - i0)) * 8u;  // ld % 16 == 0: whole 128-byte lines
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(ring + static_cast<size_t>(s) * TALL_TS, Xt + static_cast<size_t>(j) * ld + i0, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  const int nc = min(NC, C);
+  int bad = 0;
+  long c = 0;
+  for (int t = 0; t < nmine; ++t) {
+    const int tile = blockIdx.x + t * gridDim.x;
+    const long i0 = static_cast<long>(tile) * TALL_TS;
+    const int valid_units = static_cast<int>(min(static_cast<long>(TALL_TS), ld - i0) >> 1);
+    double2 acc[TALL_U][NC];
+#pragma unroll
+    for (int k = 0; k < TALL_U; ++k)
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) acc[k][cc] = make_double2(0.0, 0.0);
+    for (int j = 0; j < p; ++j, ++c) {
+      const int s = static_cast<int>(c % TALL_TR);
+      mbar_wait(&full[s], static_cast<uint32_t>((c / TALL_TR) & 1));
+      const double2* __restrict__ xs = reinterpret_cast<const double2*>(ring + static_cast<size_t>(s) * TALL_TS);
+      double2 x[TALL_U];
+#pragma unroll
+      for (int k = 0; k < TALL_U; ++k) {
+        const int uidx = tid + k * 256;
+        x[k] = uidx < valid_units ? xs[uidx] : make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);  // the chunk sits in registers: hand the stage back
+      const double m = mean ? __ldg(mean + j) : 0.0;
+      double bv[NC];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) bv[cc] = cc < nc ? __ldg(Bm + static_cast<size_t>(cc) * ldb + j) : 0.0;
+#pragma unroll
+      for (int k = 0; k < TALL_U; ++k) {
+        const long i = i0 + 2 * (tid + k * 256);
+        if (i + 1 >= n) {  // samples beyond n (padding, or whatever an adopted view holds there) are not data
+          if (i >= n) x[k].x = m;
+          x[k].y = m;
+        }
+        bad |= ((__double2hiint(x[k].x) & 0x7ff00000) == 0x7ff00000) | ((__double2hiint(x[k].y) & 0x7ff00000) == 0x7ff00000);
+        double zx = x[k].x - m, zy = x[k].y - m;  // StandardScaler.transform: 1 / scale is folded into Bm by the caller
+        if (isnan(zx)) zx = 0.0;                    // NaN entries count as zero after scaling (:1379-1383)
+        if (isnan(zy)) zy = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+          acc[k][cc].x = fma(zx, bv[cc], acc[k][cc].x);
+          acc[k][cc].y = fma(zy, bv[cc], acc[k][cc].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TALL_U; ++k) {
+      const long i = i0 + 2 * (tid + k * 256);
+      if (i < n) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          if (cc < nc) {
+            double* o = out + static_cast<size_t>(cc) * ldo + i;
+            *reinterpret_cast<double2*>(o) = make_double2(acc[k][cc].x, i + 1 < n ? acc[k][cc].y : 0.0);
+          }
+      }
+    }
+  }
+  if (flag && bad) *flag = 1;
+}
+
 __global__ void __launch_bounds__(256)
 rank1_update_kernel(double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ ts,
                     const double* __restrict__ pvec) {
@@ -247,6 +358,30 @@ int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, lo
     else if (nc > 1) skinny_gemm_kernel<2, 8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
     else skinny_gemm_kernel<1, 8><<<grid, 256, 0, st>>>(Xt, ld, n, Bm, ldb, C, c0, split_f0, split_f1, out_part, ldo, mean, scale, nonfinite_flag);
   }
+  MBPLS_RETURN_LAST();
+}
+
+/* tall batches: same product for C <= 4 outputs and ALL p features, written directly to out[c*ldo + i] (no partials).
+ * Persistent CTAs stream 16 KB chunks of every feature through a 192 KB TMA ring (csrc/finalize.cu skinny_tall_kernel).
+ * mean (optional): centring; 1 / scale must already be folded into Bm. */
+int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* Bm, long ldb, int C, double* out, long ldo,
+                               const double* mean, int* nonfinite_flag, void* stream) {
+  if (!Xt || !Bm || !out || C < 1 || C > 4 || (ld % 16) != 0 || (ldo % 2) != 0 || ld < n) return MBPLS_ERR_ARG;
+  if (n == 0 || p == 0) return MBPLS_OK;
+  const size_t smem = static_cast<size_t>(TALL_TR) * TALL_TS * sizeof(double) + 2 * TALL_TR * sizeof(uint64_t) + 64;
+  if (smem > static_cast<size_t>(smem_optin())) return MBPLS_ERR_SIZE;
+  const int ntiles = (n + TALL_TS - 1) / TALL_TS;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TALL_LAUNCH(NCV)                                                                                                   \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(skinny_tall_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
+    skinny_tall_kernel<NCV><<<grid, 288, smem, st>>>(Xt, ld, n, p, Bm, ldb, C, out, ldo, mean, nonfinite_flag);           \
+  } while (0)
+  if (C > 2) TALL_LAUNCH(4);
+  else if (C > 1) TALL_LAUNCH(2);
+  else TALL_LAUNCH(1);
+#undef TALL_LAUNCH
   MBPLS_RETURN_LAST();
 }
 

@@ -208,6 +208,7 @@ def try_adopt_feature_major(blocks, n: int, writable: bool):
 
 
 _PIN_MIN_BYTES = 1 << 20
+TALL_MIN_SAMPLES = 1 << 18   # predict / transform batches at least this long take the TMA-ring product kernel
 
 
 def to_host(t: torch.Tensor, transpose: bool = False) -> np.ndarray:
@@ -574,7 +575,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if px is not None:
                 px.seq += 1
                 xa.seq = px.seq
-            call("mbpls_nipals_xchg_epilogue_f64", C.byref(xa), 0, st)
+            timed("xchg", lambda: call("mbpls_nipals_xchg_epilogue_f64", C.byref(xa), 0, st))
             return
         call("mbpls_nipals_reduce_partials_f64", ptr(Tn), ptr(Td), ld, n, B, ptr(bso_dev), ptr(npart_t), nparts_,
              ptr(red_local), nan, done_p, st)
@@ -754,6 +755,13 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         # coefficients (an fp64 divide per element halves the rate of this memory-bound pass)
         Bm = (Bm[:, :p] / scale[:p].view(1, -1)).contiguous()
         scale = None
+    if p > 0 and n >= TALL_MIN_SAMPLES and Cc <= 4 and scale is None and ld % 16 == 0 and os.environ.get("MBPLS_TALL", "1") != "0":
+        # tall batch: persistent CTAs fed by a TMA ring, results written directly (csrc/finalize.cu skinny_tall_kernel)
+        Bc = Bm if Bm.stride(1) == 1 else Bm.contiguous()
+        call("mbpls_skinny_gemm_tall_f64", ptr(Xt), ld, n, p, ptr(Bc), Bc.stride(0), Cc, ptr(out), ld, ptr(mean), ptr(flag),
+             stream_ptr(dev))
+        allreduce_(out, group)
+        return out
     if p > 0 and n > 0:
         f0, f1, _ = make_splits(block_off, n, sm_count(dev))
         ns = len(f0)

@@ -1,6 +1,7 @@
 """GPU: edge cases of the fit path against the live oracle -- ragged / tiny shapes, single-feature blocks, one
 component, constant columns (scale 1 rule), K equal to the rank budget, many blocks, float32 / list inputs,
 NaN mode with a fully observed block, copy=False semantics."""
+import os
 import warnings
 
 import numpy as np
@@ -221,3 +222,45 @@ def test_row_slice_views_of_a_taller_device_matrix_are_never_written(n_train, N)
         m2 = MBPLS(n_components=3, copy=False).fit(views(0, n_train), Y[:n_train].copy())
         assert torch.equal(buf[:, n_train:], parent[:, n_train:]), "fit(copy=False) wrote beyond the n samples it was given"
         assert rel_err(m2.beta_, o.beta_) < TOL
+
+
+def test_tall_batches_take_the_tma_ring_product_kernel():
+    """predict / transform on m >= 2^18 new samples with at most 4 outputs run through skinny_tall_kernel (persistent CTAs fed
+    by a ring of bulk copies, csrc/finalize.cu); same numbers as the reference's X.dot(beta_) / X.dot(R_) (:1386, :1117),
+    ragged tail tile, odd m, NaN rows counted as zero (:1379-1383), +-inf rejected."""
+    from mbpls_b200 import MBPLS, engine
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(150, (25, 14), 2, 3, seed=71)
+    m = engine.TALL_MIN_SAMPLES + 4097  # not a multiple of the 2,048-sample tile, odd
+    rng = np.random.default_rng(72)
+    Xn = [rng.standard_normal((m, 25)), rng.standard_normal((m, 14))]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = MBPLS(n_components=3).fit([x.copy() for x in X], Y.copy())
+        yh = model.predict(Xn)
+        Ts = model.transform(Xn)
+    Z = np.hstack([sc.transform(x) for sc, x in zip(model.x_scalers_, Xn)])
+    want = model.y_scaler_.inverse_transform(Z @ model.beta_)
+    assert yh.shape == want.shape and rel_err(yh, want) < 1e-12
+    assert rel_err(Ts, Z @ model.R_) < 1e-12
+    os.environ["MBPLS_TALL"] = "0"  # the per-thread-load kernel on the same batch
+    try:
+        assert rel_err(model.predict(Xn), want) < 1e-12
+    finally:
+        del os.environ["MBPLS_TALL"]
+    # NaN mode: missing entries of new data count as zero after scaling
+    Xm = [x.copy() for x in Xn]
+    Xm[0][::7, 3] = np.nan
+    Xm[1][m - 1, 0] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp = MBPLS(n_components=3, sparse_data=True).fit([x.copy() for x in X], Y.copy())
+        got = sp.predict(Xm)
+    Zm = np.nan_to_num(np.hstack([sc.transform(x) for sc, x in zip(sp.x_scalers_, Xm)]), nan=0.0)
+    assert rel_err(got, sp.y_scaler_.inverse_transform(Zm @ sp.beta_)) < 1e-12
+    with pytest.raises(ValueError):
+        model.predict(Xm)  # dense model: NaN in new data is an error (check_array, :1368)
+    Xi = [x.copy() for x in Xn]
+    Xi[1][m - 2, 7] = np.inf
+    with pytest.raises(ValueError):
+        model.predict(Xi)
