@@ -292,9 +292,10 @@ int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, lo
                           const double* scale, int* nonfinite_flag, void* stream);
 /* The same product for tall batches (m >> p, at most 4 outputs, all p features): out[c*ldo + i] written directly.
  * Persistent CTAs stream 16 KB chunks of every feature through a 192 KB ring of bulk (TMA) copies instead of issuing
- * per-thread loads 8 MB apart.  mean (optional) centres; 1 / scale must already be folded into Bm. */
-int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* Bm, long ldb, int C, double* out, long ldo,
-                               const double* mean, int* nonfinite_flag, void* stream);
+ * per-thread loads 8 MB apart; the coefficients of a feature travel with its chunk.  coef: p x 8 doubles, row j =
+ * {mean_j (0: no centring), b_0j, b_1j, b_2j, b_3j, 0, 0, 0} with 1 / scale_j already folded into the b's. */
+int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* coef, int C, double* out, long ldo,
+                               int* nonfinite_flag, void* stream);
 /* X_b <- X_b - ts p_b' for new data (transform, mbpls.py:1145,1204); NaNs stay NaN */
 int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, const double* pvec, void* stream);
 /* column norms / scaling of a C x ld feature-major array over n samples */

@@ -110,7 +110,7 @@ SIGNATURES = {
     "mbpls_reduce_chunks_f64": [_p, _i, _i, _p, _p],
     "mbpls_right_multiply_f64": [_p, _l, _i, _i, _p, _p, _i, _p, _l, _p],
     "mbpls_skinny_gemm_f64": [_p, _l, _i, _p, _l, _i, _p, _p, _i, _p, _l, _p, _p, _p, _p],
-    "mbpls_skinny_gemm_tall_f64": [_p, _l, _i, _i, _p, _l, _i, _p, _l, _p, _p, _p],
+    "mbpls_skinny_gemm_tall_f64": [_p, _l, _i, _i, _p, _i, _p, _l, _p, _p],
     "mbpls_rank1_update_f64": [_p, _l, _i, _i, _p, _p, _p],
     "mbpls_rows_sumsq_f64": [_p, _l, _i, _i, _p, _p],
     "mbpls_rows_scale_f64": [_p, _l, _i, _i, _p, _i, _p],

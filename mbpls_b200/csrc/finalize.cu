@@ -182,11 +182,14 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 
 template <int NC>
 __global__ void __launch_bounds__(288, 1)
-skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ Bm, long ldb, int C,
-                   double* __restrict__ out, long ldo, const double* __restrict__ mean, int* __restrict__ flag) {
+skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ coef, int C,
+                   double* __restrict__ out, long ldo, int* __restrict__ flag) {
+  // coef: p x 8 doubles, row j = {mean_j (0 without centring), b_0j, b_1j, b_2j, b_3j, -, -, -}: travels through the ring with
+  // the chunk of feature j, so the consumers read their coefficients as shared-memory broadcasts
   extern __shared__ __align__(128) unsigned char tall_smem[];
   double* ring = reinterpret_cast<double*>(tall_smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tall_smem + static_cast<size_t>(TALL_TR) * TALL_TS * sizeof(double));
+  double* cring = ring + static_cast<size_t>(TALL_TR) * TALL_TS;  // [TALL_TR][8]
+  uint64_t* full = reinterpret_cast<uint64_t*>(cring + TALL_TR * 8);
   uint64_t* empty = full + TALL_TR;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = (n + TALL_TS - 1) / TALL_TS;
@@ -209,8 +212,9 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
         const int tile = blockIdx.x + static_cast<int>(c / p) * gridDim.x, j = static_cast<int>(c % p);
         const long i0 = static_cast<long>(tile) * TALL_TS;
         const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long>(TALL_TS), ld - i0)) * 8u;  // ld % 16 == 0: whole 128-byte lines
-        mbar_arrive_expect_tx(&full[s], bytes);
+        mbar_arrive_expect_tx(&full[s], bytes + 64u);
         bulk_g2s(ring + static_cast<size_t>(s) * TALL_TS, Xt + static_cast<size_t>(j) * ld + i0, bytes, &full[s]);
+        bulk_g2s(cring + s * 8, coef + static_cast<size_t>(j) * 8, 64u, &full[s]);
       }
     }
     return;
@@ -223,6 +227,14 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
     const int tile = blockIdx.x + t * gridDim.x;
     const long i0 = static_cast<long>(tile) * TALL_TS;
     const int valid_units = static_cast<int>(min(static_cast<long>(TALL_TS), ld - i0) >> 1);
+    // samples of this thread that lie beyond n (padding, or whatever an adopted view holds there) are not data
+    bool live_x[TALL_U], live_y[TALL_U];
+#pragma unroll
+    for (int k = 0; k < TALL_U; ++k) {
+      const long i = i0 + 2 * (tid + k * 256);
+      live_x[k] = i < n && (tid + k * 256) < valid_units;
+      live_y[k] = i + 1 < n && (tid + k * 256) < valid_units;
+    }
     double2 acc[TALL_U][NC];
 #pragma unroll
     for (int k = 0; k < TALL_U; ++k)
@@ -232,29 +244,27 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
       const int s = static_cast<int>(c % TALL_TR);
       mbar_wait(&full[s], static_cast<uint32_t>((c / TALL_TR) & 1));
       const double2* __restrict__ xs = reinterpret_cast<const double2*>(ring + static_cast<size_t>(s) * TALL_TS);
+      const double2* __restrict__ cf = reinterpret_cast<const double2*>(cring + s * 8);
       double2 x[TALL_U];
 #pragma unroll
-      for (int k = 0; k < TALL_U; ++k) {
-        const int uidx = tid + k * 256;
-        x[k] = uidx < valid_units ? xs[uidx] : make_double2(0.0, 0.0);
-      }
+      for (int k = 0; k < TALL_U; ++k) x[k] = live_x[k] ? xs[tid + k * 256] : make_double2(0.0, 0.0);
+      const double2 c01 = cf[0], c23 = cf[1], c4 = cf[2];  // {mean, b0}, {b1, b2}, {b3, -}
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);  // the chunk sits in registers: hand the stage back
-      const double m = mean ? __ldg(mean + j) : 0.0;
-      double bv[NC];
-#pragma unroll
-      for (int cc = 0; cc < NC; ++cc) bv[cc] = cc < nc ? __ldg(Bm + static_cast<size_t>(cc) * ldb + j) : 0.0;
+      const double m = c01.x;
+      const double bv[4] = {c01.y, c23.x, c23.y, c4.x};
 #pragma unroll
       for (int k = 0; k < TALL_U; ++k) {
-        const long i = i0 + 2 * (tid + k * 256);
-        if (i + 1 >= n) {  // samples beyond n (padding, or whatever an adopted view holds there) are not data
-          if (i >= n) x[k].x = m;
-          x[k].y = m;
+        const int hx = __double2hiint(x[k].x), hy = __double2hiint(x[k].y);
+        double zx = x[k].x - m, zy = x[k].y - m;  // StandardScaler.transform: 1 / scale is folded into the coefficients
+        if (((hx & 0x7ff00000) == 0x7ff00000) | ((hy & 0x7ff00000) == 0x7ff00000)) {  // rare: NaN or +-inf in this unit
+          if (live_x[k] && ((hx & 0x7ff00000) == 0x7ff00000)) bad = 1;
+          if (live_y[k] && ((hy & 0x7ff00000) == 0x7ff00000)) bad = 1;
+          if (isnan(zx)) zx = 0.0;  // NaN entries count as zero after scaling (:1379-1383)
+          if (isnan(zy)) zy = 0.0;
         }
-        bad |= ((__double2hiint(x[k].x) & 0x7ff00000) == 0x7ff00000) | ((__double2hiint(x[k].y) & 0x7ff00000) == 0x7ff00000);
-        double zx = x[k].x - m, zy = x[k].y - m;  // StandardScaler.transform: 1 / scale is folded into Bm by the caller
-        if (isnan(zx)) zx = 0.0;                    // NaN entries count as zero after scaling (:1379-1383)
-        if (isnan(zy)) zy = 0.0;
+        if (!live_x[k]) zx = 0.0;
+        if (!live_y[k]) zy = 0.0;
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) {
           acc[k][cc].x = fma(zx, bv[cc], acc[k][cc].x);
@@ -265,12 +275,12 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
 #pragma unroll
     for (int k = 0; k < TALL_U; ++k) {
       const long i = i0 + 2 * (tid + k * 256);
-      if (i < n) {
+      if (live_x[k]) {
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
           if (cc < nc) {
             double* o = out + static_cast<size_t>(cc) * ldo + i;
-            *reinterpret_cast<double2*>(o) = make_double2(acc[k][cc].x, i + 1 < n ? acc[k][cc].y : 0.0);
+            *reinterpret_cast<double2*>(o) = make_double2(acc[k][cc].x, live_y[k] ? acc[k][cc].y : 0.0);
           }
       }
     }
@@ -363,12 +373,12 @@ int mbpls_skinny_gemm_f64(const double* Xt, long ld, int n, const double* Bm, lo
 
 /* tall batches: same product for C <= 4 outputs and ALL p features, written directly to out[c*ldo + i] (no partials).
  * Persistent CTAs stream 16 KB chunks of every feature through a 192 KB TMA ring (csrc/finalize.cu skinny_tall_kernel).
- * mean (optional): centring; 1 / scale must already be folded into Bm. */
-int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* Bm, long ldb, int C, double* out, long ldo,
-                               const double* mean, int* nonfinite_flag, void* stream) {
-  if (!Xt || !Bm || !out || C < 1 || C > 4 || (ld % 16) != 0 || (ldo % 2) != 0 || ld < n) return MBPLS_ERR_ARG;
+ * coef: p x 8 doubles, row j = {mean_j or 0, b_0j .. b_3j, 0, 0, 0} with 1 / scale_j already folded into the b's. */
+int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const double* coef, int C, double* out, long ldo,
+                               int* nonfinite_flag, void* stream) {
+  if (!Xt || !coef || !out || C < 1 || C > 4 || (ld % 16) != 0 || (ldo % 2) != 0 || ld < n) return MBPLS_ERR_ARG;
   if (n == 0 || p == 0) return MBPLS_OK;
-  const size_t smem = static_cast<size_t>(TALL_TR) * TALL_TS * sizeof(double) + 2 * TALL_TR * sizeof(uint64_t) + 64;
+  const size_t smem = static_cast<size_t>(TALL_TR) * TALL_TS * sizeof(double) + TALL_TR * 64 + 2 * TALL_TR * sizeof(uint64_t) + 64;
   if (smem > static_cast<size_t>(smem_optin())) return MBPLS_ERR_SIZE;
   const int ntiles = (n + TALL_TS - 1) / TALL_TS;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
@@ -376,7 +386,7 @@ int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const do
 #define TALL_LAUNCH(NCV)                                                                                                   \
   do {                                                                                                                     \
     cudaFuncSetAttribute(skinny_tall_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
-    skinny_tall_kernel<NCV><<<grid, 288, smem, st>>>(Xt, ld, n, p, Bm, ldb, C, out, ldo, mean, nonfinite_flag);           \
+    skinny_tall_kernel<NCV><<<grid, 288, smem, st>>>(Xt, ld, n, p, coef, C, out, ldo, nonfinite_flag);                     \
   } while (0)
   if (C > 2) TALL_LAUNCH(4);
   else if (C > 1) TALL_LAUNCH(2);

@@ -757,9 +757,11 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         scale = None
     if p > 0 and n >= TALL_MIN_SAMPLES and Cc <= 4 and scale is None and ld % 16 == 0 and os.environ.get("MBPLS_TALL", "1") != "0":
         # tall batch: persistent CTAs fed by a TMA ring, results written directly (csrc/finalize.cu skinny_tall_kernel)
-        Bc = Bm if Bm.stride(1) == 1 else Bm.contiguous()
-        call("mbpls_skinny_gemm_tall_f64", ptr(Xt), ld, n, p, ptr(Bc), Bc.stride(0), Cc, ptr(out), ld, ptr(mean), ptr(flag),
-             stream_ptr(dev))
+        coef = torch.zeros((p, 8), dtype=F64, device=dev)  # row j: {mean_j, b_0j .. b_3j, -, -, -}: rides through the ring with feature j
+        if mean is not None:
+            coef[:, 0] = mean[:p]
+        coef[:, 1:1 + Cc] = Bm[:, :p].t()
+        call("mbpls_skinny_gemm_tall_f64", ptr(Xt), ld, n, p, ptr(coef), Cc, ptr(out), ld, ptr(flag), stream_ptr(dev))
         allreduce_(out, group)
         return out
     if p > 0 and n > 0:
