@@ -573,3 +573,4 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
         extra["T_"] = lambda: [np.empty((ng, 0)) for _ in shard.sizes]
         extra["U_"] = (lambda: np.empty((ng, 0))) if ng >= pg else (lambda: model._gather_samples(U, n))
     _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb if calc_all else None, Tb, extra)
+    model.__dict__["_cv_weights"] = Wc  # prefix models: R_k = W_k pinv(P_k'W_k) (the column scaling of P_ / V_ cancels in beta)

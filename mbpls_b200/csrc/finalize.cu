@@ -299,12 +299,22 @@ rank1_update_kernel(double* __restrict__ Xt, long ld, int n, int p, const double
     x[i] = __dsub_rn(x[i], __dmul_rn(ts[i], pj));
 }
 
-__global__ void __launch_bounds__(256) rows_sumsq_kernel(const double* __restrict__ M, long ld, int n, double* __restrict__ out) {
+// one CTA per row; four independent loads in flight per thread (a row can be 8 MB: K x p weights at the headline size)
+__global__ void __launch_bounds__(1024) rows_sumsq_kernel(const double* __restrict__ M, long ld, int n, double* __restrict__ out) {
   __shared__ double scratch[32];
   const double* m = M + static_cast<size_t>(blockIdx.x) * ld;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(m[i], m[i], s);
-  s = block_sum1(s, scratch);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int nt = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * nt < n; i += 4 * nt) {
+    const double a0 = m[i], a1 = m[i + nt], a2 = m[i + 2 * nt], a3 = m[i + 3 * nt];
+    s0 = fma(a0, a0, s0);
+    s1 = fma(a1, a1, s1);
+    s2 = fma(a2, a2, s2);
+    s3 = fma(a3, a3, s3);
+  }
+  for (; i < n; i += nt) s0 = fma(m[i], m[i], s0);
+  const double s = block_sum1((s0 + s1) + (s2 + s3), scratch);
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
@@ -412,7 +422,7 @@ int mbpls_rank1_update_f64(double* Xt, long ld, int n, int p, const double* ts, 
 int mbpls_rows_sumsq_f64(const double* M, long ld, int rows, int n, double* out, void* stream) {
   if (!M || !out || rows < 0) return MBPLS_ERR_ARG;
   if (rows == 0) return MBPLS_OK;
-  rows_sumsq_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(M, ld, n, out);
+  rows_sumsq_kernel<<<rows, 1024, 0, static_cast<cudaStream_t>(stream)>>>(M, ld, n, out);
   MBPLS_RETURN_LAST();
 }
 

@@ -101,11 +101,12 @@ def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[
 
     Returns an (n, q) array like ``sklearn.model_selection.cross_val_predict``; with ``n_components_list`` a dict
     ``{k: (n, q) array}`` obtained from one fit per fold with ``max(k)`` components.
-    KERNEL is supported through its prefix-independent quantities only when ``n_components_list`` is None.
+    With a process group in the estimator's runtime options the FOLDS are spread over the ranks (rank r fits folds r, r + world,
+    ...; the data is replicated, every fit runs on one GPU) and the out-of-fold predictions are summed across the ranks, so every
+    rank returns the complete result.
     """
     rt = estimator._runtime()
-    if rt["group"] is not None:
-        raise NotImplementedError("cross_val_predict runs on one GPU")
+    group = rt["group"]
     device = E.require_cuda(rt["device"])
     blocks = X if _is_block_list(X) else [X]
     blocks = [_as_2d_source(b, "X") for b in blocks]
@@ -117,18 +118,34 @@ def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[
     n, q = int(Ysrc.shape[0]), int(Ysrc.shape[1])
     sizes = [int(b.shape[1]) for b in blocks]
     ks = None if n_components_list is None else sorted(set(int(k) for k in n_components_list))
-    if ks is not None and estimator.method == 'KERNEL':
-        raise NotImplementedError("n_components_list needs prefix-stable weights; use NIPALS, UNIPALS or SIMPLS")
     K = estimator.n_components if ks is None else max(ks)
     folds = _folds(n, cv)
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        folds = folds[rank::world]
+
+    def finish(preds):
+        """dict k -> (n, q) with NaN outside this rank's folds -> the complete arrays on every rank"""
+        if group is not None:
+            keys = sorted(preds)
+            stack = torch.from_numpy(np.stack([preds[k] for k in keys])).to(device)
+            seen = (~torch.isnan(stack)).to(F64)
+            stack = torch.nan_to_num(stack, nan=0.0)
+            dist.all_reduce(stack, group=group)
+            dist.all_reduce(seen, group=group)
+            stack = torch.where(seen > 0, stack / seen.clamp(min=1.0), torch.full_like(stack, float("nan")))
+            host = stack.cpu().numpy()
+            preds = {k: host[i] for i, k in enumerate(keys)}
+        if ks is None:
+            return preds[K].ravel() if y1d else preds[K]
+        return {k: (v.ravel() if y1d else v) for k, v in preds.items()}
 
     with torch.cuda.device(device):
         shard = E.ShardMap.build(sizes, 0, 1)
-        batched = _batched_small_cv(estimator, blocks, Ysrc, n, q, sizes, shard, K, ks, folds, device)
+        batched = _batched_small_cv(estimator, blocks, Ysrc, n, q, sizes, shard, K, ks, folds, device) if folds else None
         if batched is not None:
-            if ks is None:
-                return batched[K].ravel() if y1d else batched[K]
-            return {k: (v.ravel() if y1d else v) for k, v in batched.items()}
+            return finish(batched)
         Xraw = E.ingest_blocks(blocks, n, shard, device)          # p x ld, uploaded once
         Yraw = E.alloc_feature_major(q, n, device)
         E.ingest_feature_major(Ysrc, n, 0, q, Yraw, device)
@@ -161,7 +178,4 @@ def cross_val_predict(estimator: MBPLS, X, y, cv=5, n_components_list: Optional[
                             E.call("mbpls_scaler_inverse_f64", E.ptr(Yh), Yh.shape[1], mm, q, E.ptr(ymean), E.ptr(yscale),
                                    E.stream_ptr(device))
                         preds[k][te] = Yh[:, :mm].cpu().numpy().T
-    if ks is None:
-        out = preds[K]
-        return out.ravel() if y1d else out
-    return {k: (v.ravel() if y1d else v) for k, v in preds.items()}
+    return finish(preds)

@@ -72,6 +72,23 @@ def gpu_checks(group, rank, world, dev):
         print(f"rank {rank}: world={world} {method} n={n} worst={worst}", flush=True)
 
 
+def cv_checks(group, rank, world, dev):
+    """Folds spread over the ranks: every rank returns the complete out-of-fold predictions of the single-GPU run."""
+    from mbpls_b200 import MBPLS
+    from mbpls_b200.model_selection import cross_val_predict
+    from oracle.cases import latent_blocks
+    X, Y = latent_blocks(42, (18, 11), 2, 3, seed=91)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for small in (True, False):
+            one = cross_val_predict(MBPLS(n_components=3).set_runtime(device=dev, small_path=small), X, Y, cv=7, n_components_list=[1, 2, 3])
+            many = cross_val_predict(MBPLS(n_components=3).set_runtime(device=dev, group=group, small_path=small), X, Y, cv=7,
+                                     n_components_list=[1, 2, 3])
+            for k in (1, 2, 3):
+                assert many[k].shape == one[k].shape and np.allclose(many[k], one[k], rtol=1e-12, atol=1e-14), (small, k)
+    print(f"rank {rank}: fold-parallel CV ok", flush=True)
+
+
 def host_checks(group, rank, world):
     from mbpls_b200.engine import ShardMap
     from mbpls_b200.mbpls import MBPLS
@@ -99,6 +116,7 @@ def main():
         dev = torch.device("cuda", local)
         dist.init_process_group("nccl", device_id=dev)
         gpu_checks(dist.group.WORLD, rank, world, dev)
+        cv_checks(dist.group.WORLD, rank, world, dev)
     else:
         dist.init_process_group("gloo")
         host_checks(dist.group.WORLD, rank, world)

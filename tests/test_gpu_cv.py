@@ -37,7 +37,7 @@ def test_leave_one_out_matches_refit_loop(method):
     assert got.shape == want.shape and rel_err(got, want) < 1e-9
 
 
-@pytest.mark.parametrize("method", ["NIPALS", "UNIPALS", "SIMPLS"])
+@pytest.mark.parametrize("method", ["NIPALS", "UNIPALS", "SIMPLS", "KERNEL"])
 def test_component_path_from_one_fit_per_fold(method):
     """Predictions for k = 1..K read off one K-component fit per fold equal K separate cross-validations."""
     from mbpls_b200 import MBPLS

@@ -13,3 +13,4 @@ def test_feature_sharded_fit_two_gpus():
     r = run_workers("nccl", 2, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     assert r.stdout.count("worst=") == 18  # (3 NIPALS + 6 other-method cases) x 2 ranks
+    assert r.stdout.count("fold-parallel CV ok") == 2
