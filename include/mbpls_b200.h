@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 12
+#define MBPLS_ABI_VERSION 13
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -203,6 +203,15 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
                             const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
                             double* Tnum, long ldt, void* stream);
+
+/* StandardScaler.fit_transform of X in place (mbpls.py:307,314) fused with the complete first trip of the first component
+ * (u = u0 = the first standardised Y column, :838): per-feature statistics as mbpls_standardize_fit_f64, first weights w,
+ * norm_part and Tnum as mbpls_nipals_fused_trip_f64 -- 1 read + 1 write of X instead of 2 reads + 1 write.  Dense data,
+ * features of up to 10,240 samples (MBPLS_ERR_SIZE otherwise: standardise and trip separately). */
+int mbpls_fused_standardize_f64(double* Xt, long ld, int n, const double* u0, const double* u0u0, const int* split_f0,
+                                const int* split_f1, const int* split_block, int nsplit, int B, double* mean, double* var,
+                                double* scale, long long* seen, double* zss, double* w, double* norm_part, double* Tnum, long ldt,
+                                void* stream);
 
 /* ---- whole dense NIPALS fits in one kernel (csrc/smallfit.cu): one persistent CTA per fit, device-side while loop -----
  * For problems that are launch-latency bound through the streaming kernels (README quickstart, the leave-one-out loops of

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -99,6 +99,7 @@ SIGNATURES = {
     "mbpls_fused_total_workers": [_l],
     "mbpls_fused_uses_clusters": [_l],
     "mbpls_nipals_fused_trip_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _l, _p, _p],
+    "mbpls_fused_standardize_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p],
     "mbpls_fused_deflate_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p],
     "mbpls_vec_dot_f64": [_p, _p, _i, _p, _p],
     "mbpls_nan_bitmask_ldw": [_i],

@@ -579,6 +579,163 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
   if (CL) cluster_sync_all();
 }
 
+// ------------------------------------------------------------------------------------------
+// StandardScaler.fit_transform (mbpls.py:307,314) AND the first trip of the first component in one read + one write.
+// The first trip's u is the first (standardised) Y column -- known before X is touched -- so while a feature sits in
+// registers for its statistics it can also deliver its first weight w~_j = z_j . u0 / u0'u0 and add to the first block-score
+// partials, exactly as the deflation pass does for later components.  Three worker reductions per feature: sum (mean), the
+// corrected two-pass variance (sklearn's _incremental_mean_and_var: sum of deviations and of their squares), and
+// {sum z^2, z . u0}.  Dense data only (a NaN shows up as a non-finite mean and is reported by the caller, like check_array).
+// Samples beyond n (the zero padding of a feature) take no part and stay zero.
+// ------------------------------------------------------------------------------------------
+struct StdArgs {
+  double* mean;
+  double* var;
+  double* scale;
+  long long* seen;
+  double* zss;
+};
+
+template <class C, bool PAD>  // PAD: n < ld, the last elements of a feature are padding
+__global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedArgs a, const StdArgs so) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Geo ge = make_geo<C, false>(a.ld, a.n);
+  const Smem<C> sm(smem_raw, 2 * ge.units, 1);  // u0
+  init_sync<C>(sm, a.sync_mode);
+  for (int i = threadIdx.x; i < 2 * ge.units; i += blockDim.x) sm.vec0[i] = i < a.n ? a.u[i] : 0.0;
+  __syncthreads();
+  const long ld = a.ld;
+  const int units = ge.units;
+  const int ncf = (units + C::UC - 1) / C::UC;
+  const int g = threadIdx.x / C::kTG, tg = threadIdx.x % C::kTG;
+  const int lane = threadIdx.x & 31, wig = tg >> 5;
+  const int wk = ge.wbase + g;
+  if (wk >= a.nsplit) return;
+  double* __restrict__ X = a.Xw;
+  const int f0 = a.split_f0[wk], f1 = a.split_f1[wk];
+  if (tg == 0) prime_ring<C>(X, ld, units, ncf, g, f0, f1, sm);
+  const double inv_uu = 1.0 / *a.uu;
+  const double cnt = static_cast<double>(a.n);
+  const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
+  double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
+  const int sync_mode = a.sync_mode;
+  // which of this thread's elements are padding (index >= n): they are excluded from the statistics and stay zero
+  uint32_t padx = 0, pady = 0;
+  if (PAD) {
+#pragma unroll
+    for (int k = 0; k < C::EPT; ++k) {
+      const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+      if (2 * gi >= a.n) padx |= 1u << k;
+      if (2 * gi + 1 >= a.n) pady |= 1u << k;
+    }
+  }
+
+  double2 acc[C::EPT], x[C::EPT];
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
+  double normsq = 0.0, wj = 0.0;
+  int s = 0;
+  uint32_t ph = 0;
+  int flip = 0;
+
+  for (int j = f0; j <= f1; ++j) {
+    const bool load = j < f1;
+    double sa = 0.0, sb = 0.0, sc = 0.0, sd = 0.0;
+    int s_use = s;
+    uint32_t ph_use = ph;
+#pragma unroll
+    for (int c = 0; c < C::CPF; ++c) {
+      const bool have = load && c < ncf;
+      const double2* __restrict__ xs_ = reinterpret_cast<const double2*>(sm.stage(g, s));
+      if (have) {
+        mbar_wait(&sm.full[g * C::S + s], ph);
+        if (++s == C::S) { s = 0; ph ^= 1u; }
+      }
+      const bool whole = c + 1 < ncf;
+#pragma unroll
+      for (int e = 0; e < C::EPTC; ++e) {
+        const int l = tg + e * C::kTG, gi = c * C::UC + l, k = c * C::EPTC + e;
+        acc[k].x = fma(wj, x[k].x, acc[k].x);  // first block-score partials with the previous feature's weight
+        acc[k].y = fma(wj, x[k].y, acc[k].y);
+        double2 xv = make_double2(0.0, 0.0);
+        if (have && (whole || gi < units)) xv = xs_[l];
+        if (e & 1) {
+          sc += xv.x;
+          sd += xv.y;
+        } else {
+          sa += xv.x;
+          sb += xv.y;
+        }
+        x[k] = xv;
+      }
+      if (have) {
+        refill_if_last<C>(arrive_stage<C>(g, s_use, lane, sm, sync_mode, ph_use), X, ld, units, ncf, g, s_use, j, c, f1, sm);
+        if (++s_use == C::S) { s_use = 0; ph_use ^= 1u; }
+      }
+    }
+    if (!load) break;
+    double one[1] = {(sa + sb) + (sc + sd)};
+    worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
+    flip ^= 1;
+    const double mean = one[0] / cnt;
+    double two[2] = {0.0, 0.0};  // sum of deviations (correction term), sum of squared deviations
+#pragma unroll
+    for (int k = 0; k < C::EPT; ++k) {
+      double2 d;
+      d.x = (PAD && ((padx >> k) & 1u)) ? 0.0 : x[k].x - mean;
+      d.y = (PAD && ((pady >> k) & 1u)) ? 0.0 : x[k].y - mean;
+      two[0] += d.x + d.y;
+      two[1] = fma(d.x, d.x, two[1]);
+      two[1] = fma(d.y, d.y, two[1]);
+      x[k] = d;
+    }
+    worker_sum<2, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
+    flip ^= 1;
+    double ssq = two[1] - two[0] * two[0] / cnt;
+    const double var = ssq / cnt;
+    const double eps = 2.220446049250313e-16;
+    const double bound = cnt * eps * var + (cnt * mean * eps) * (cnt * mean * eps);
+    const double scale = (var <= bound) ? 1.0 : sqrt(var);  // _is_constant_feature -> scale 1
+    double2* __restrict__ xg = reinterpret_cast<double2*>(X + static_cast<size_t>(j) * ld);
+    double thr[2] = {0.0, 0.0};  // sum z^2, z . u0
+#pragma unroll
+    for (int k = 0; k < C::EPT; ++k) {
+      const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+      if (((k / C::EPTC) + 1 < ncf) || gi < units) {
+        double2 z;
+        z.x = x[k].x / scale;  // (x - mean) / scale with a true division, like StandardScaler
+        z.y = x[k].y / scale;
+        st_stream(xg + gi, z);
+        const double2 uv = u2[gi];
+        thr[0] = fma(z.x, z.x, thr[0]);
+        thr[0] = fma(z.y, z.y, thr[0]);
+        thr[1] = fma(z.x, uv.x, thr[1]);
+        thr[1] = fma(z.y, uv.y, thr[1]);
+        x[k] = z;
+      }
+    }
+    worker_sum<2, C::kTG>(thr, scratch + flip * 3 * C::NW, g, wig, lane);
+    flip ^= 1;
+    wj = thr[1] * inv_uu;
+    normsq = fma(wj, wj, normsq);
+    if (tg == 0) {
+      so.mean[j] = mean;
+      so.var[j] = var;
+      so.scale[j] = scale;
+      so.seen[j] = static_cast<long long>(a.n);
+      so.zss[j] = thr[0];
+      a.w[j] = wj;
+    }
+  }
+  double2* tn = reinterpret_cast<double2*>(a.Tnum + static_cast<size_t>(wk) * a.ldt);
+#pragma unroll
+  for (int k = 0; k < C::EPT; ++k) {
+    const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+    if (gi < units) tn[gi] = acc[k];
+  }
+  if (tg == 0) a.norm_part[static_cast<size_t>(wk) * a.B + a.split_block[wk]] = normsq;
+}
+
 // Configurations by feature length (units = 16-byte units per feature handled by ONE CTA <= TG*EPTC*CPF).  Measured
 // (profiles/r1_notes.md): every chunk costs a worker ~0.2 us of handshakes (wait, counter, refill), so chunks are as large as
 // the ring allows: the 16 KB x 8 ring ran the n = 10,000 trip at 4.9 TB/s, the 40 KB x 3 ring runs it at 6.6 TB/s.
@@ -777,6 +934,46 @@ int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.deflate_cl) return rden_ts ? dispatch_deflate<true, true>(pl.deflate, a, st) : dispatch_deflate<false, true>(pl.deflate, a, st);
   return rden_ts ? dispatch_deflate<true, false>(pl.deflate, a, st) : dispatch_deflate<false, false>(pl.deflate, a, st);
+}
+
+/* StandardScaler.fit_transform of X in place (mbpls.py:307,314) fused with the complete first trip of the first component
+ * (u = u0, the first standardised Y column): statistics out as for mbpls_standardize_fit_f64, plus w, norm_part, Tnum as for
+ * mbpls_nipals_fused_trip_f64.  Dense data, features of up to 10,240 samples (returns MBPLS_ERR_SIZE otherwise). */
+int mbpls_fused_standardize_f64(double* Xt, long ld, int n, const double* u0, const double* u0u0, const int* split_f0,
+                                const int* split_f1, const int* split_block, int nsplit, int B, double* mean, double* var,
+                                double* scale, long long* seen, double* zss, double* w, double* norm_part, double* Tnum, long ldt,
+                                void* stream) {
+  if (!Xt || !u0 || !u0u0 || !split_f0 || !split_f1 || !split_block || !mean || !var || !scale || !seen || !zss || !w ||
+      !norm_part || !Tnum || ld < n || ldt < ld || B < 1)
+    return MBPLS_ERR_ARG;
+  if (nsplit == 0) return MBPLS_OK;
+  const Plan pl = plan_of(ld);
+  if (!pl.trip || pl.trip_cl || nsplit > pl.workers) return MBPLS_ERR_SIZE;
+  FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, nullptr, nullptr, nullptr, split_f0, split_f1, split_block, nsplit, B,
+              w, norm_part, Tnum, ldt, nullptr, nullptr, nullptr, default_sync_mode()};
+  const StdArgs so{mean, var, scale, seen, zss};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define STD_LAUNCH(CFG)                                                                                                      \
+  do {                                                                                                                       \
+    const size_t smem = fused_smem_bytes<CFG>(ld, 1);                                                                        \
+    if (smem > static_cast<size_t>(smem_optin())) return MBPLS_ERR_SIZE;                                                     \
+    if (n < ld) {                                                                                                            \
+      cudaFuncSetAttribute(fused_standardize_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+      fused_standardize_kernel<CFG, true><<<(nsplit + CFG::G - 1) / CFG::G, 512, smem, st>>>(a, so);                         \
+    } else {                                                                                                                 \
+      cudaFuncSetAttribute(fused_standardize_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+      fused_standardize_kernel<CFG, false><<<(nsplit + CFG::G - 1) / CFG::G, 512, smem, st>>>(a, so);                        \
+    }                                                                                                                        \
+  } while (0)
+  switch (pl.trip) {
+    case 1: STD_LAUNCH(CfgA); break;
+    case 2: STD_LAUNCH(CfgB); break;
+    case 3: STD_LAUNCH(CfgC); break;
+    case 4: STD_LAUNCH(CfgD); break;
+    default: return MBPLS_ERR_SIZE;
+  }
+#undef STD_LAUNCH
+  MBPLS_RETURN_LAST();
 }
 
 }  // extern "C"

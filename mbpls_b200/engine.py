@@ -294,6 +294,60 @@ def standardize_apply(Xt: torch.Tensor, n: int, mean: torch.Tensor, scale: torch
     call("mbpls_standardize_apply_f64", ptr(Xt), ld, n, p, ptr(mean), ptr(scale), stream_ptr(Xt.device))
 
 
+@dataclass
+class OnePassTables:
+    """Split table of the one-pass kernels (csrc/fused.cu): one split per persistent worker, never straddling a block."""
+    nsplit: int
+    f0: torch.Tensor
+    f1: torch.Tensor
+    bso: torch.Tensor     # B+1: first split of every block
+    blk: torch.Tensor     # block of every split
+
+
+def onepass_tables(block_off: Sequence[int], ld: int, p: int, device) -> Optional[OnePassTables]:
+    nworkers = call("mbpls_fused_total_workers", ld) if p > 0 else 0
+    if nworkers <= 0:
+        return None
+    B = len(block_off) - 1
+    of0, of1, obso = make_splits(block_off, 1, nworkers, ctas_per_sm=1, min_feats=16)
+    oblk = [b for b in range(B) for _ in range(obso[b + 1] - obso[b])]
+    return OnePassTables(len(of0), _i32(of0, device), _i32(of1, device), _i32(obso, device), _i32(oblk, device))
+
+
+@dataclass
+class FirstTrip:
+    """What mbpls_fused_standardize_f64 leaves behind for the first trip of the first component."""
+    tables: OnePassTables
+    w: torch.Tensor
+    norm_part: torch.Tensor
+    Tnum: torch.Tensor
+
+
+def standardize_fit_first_trip(Xt: torch.Tensor, n: int, block_off: Sequence[int], u0: torch.Tensor):
+    """StandardScaler.fit_transform of X in place AND the complete first trip of the first component (u = u0, the first
+    standardised Y column) in one read + one write of X (csrc/fused.cu fused_standardize_kernel).  Returns
+    (ScalerStats, FirstTrip), or None when the shape is not covered (features longer than 10,240 samples)."""
+    p, ld = Xt.shape
+    dev = Xt.device
+    if p == 0 or (call("mbpls_fused_uses_clusters", ld) & 1):
+        return None
+    tb = onepass_tables(block_off, ld, p, dev)
+    if tb is None:
+        return None
+    B = len(block_off) - 1
+    st = ScalerStats(*(torch.empty(p, dtype=F64, device=dev) for _ in range(3)), torch.empty(p, dtype=torch.int64, device=dev),
+                     torch.empty(p, dtype=F64, device=dev))
+    w = torch.empty(p, dtype=F64, device=dev)
+    norm_part = torch.zeros(tb.nsplit * B, dtype=F64, device=dev)
+    Tnum = torch.zeros((tb.nsplit, ld), dtype=F64, device=dev)
+    u0u0 = torch.empty(1, dtype=F64, device=dev)
+    call("mbpls_rows_sumsq_f64", ptr(u0), ld, 1, n, ptr(u0u0), stream_ptr(dev))
+    call("mbpls_fused_standardize_f64", ptr(Xt), ld, n, ptr(u0), ptr(u0u0), ptr(tb.f0), ptr(tb.f1), ptr(tb.blk), tb.nsplit, B,
+         ptr(st.mean), ptr(st.var), ptr(st.scale), ptr(st.seen), ptr(st.zss), ptr(w), ptr(norm_part), ptr(Tnum), ld,
+         stream_ptr(dev))
+    return st, FirstTrip(tb, w, norm_part, Tnum)
+
+
 def feature_sumsq(Xt: torch.Tensor, n: int) -> torch.Tensor:
     p, ld = Xt.shape
     out = torch.empty(max(p, 1), dtype=F64, device=Xt.device)
@@ -465,7 +519,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                max_iter: int = 1_000_000, group=None, fuse_next_xtu: bool = True, deflate_mode: int = 0,
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
                deflate_last: bool = False, one_pass: Optional[bool] = None,
-               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None) -> NipalsResult:
+               one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None,
+               first_trip: Optional["FirstTrip"] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -493,21 +548,21 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     # NaN-masked data runs through the same kernels with NaN read as zero; every masked denominator is derived from the
     # NaN bit matrix (csrc/nanmask.cu), which needs the per-feature NaN counts of the census (col_nan).
     want_op = one_pass is not False and (not nan or col_nan is not None)
-    nworkers = call("mbpls_fused_total_workers", ld) if (want_op and p > 0) else 0
-    use_op = nworkers > 0
+    tables = first_trip.tables if first_trip is not None else (onepass_tables(block_off, ld, p, dev) if want_op else None)
+    use_op = tables is not None
     if one_pass is True and not use_op and p > 0:
         raise ValueError("one_pass=True needs a leading dimension of at most 20480 samples (and, for NaN data, the census)")
     use_opd = use_op and one_pass_deflate is not False and deflate_mode == 0
     if use_op:
-        of0, of1, obso = make_splits(block_off, 1, nworkers, ctas_per_sm=1, min_feats=16)
-        nsplit_o = len(of0)
-        oblk = [b for b in range(B) for _ in range(obso[b + 1] - obso[b])]
-        osf0, osf1, osbso, osblk = _i32(of0, dev), _i32(of1, dev), _i32(obso, dev), _i32(oblk, dev)
-        Tnum_o = buf(nsplit_o, ld, zero=True)
+        nsplit_o, osf0, osf1, osbso, osblk = tables.nsplit, tables.f0, tables.f1, tables.bso, tables.blk
+        if first_trip is not None:  # the fused standardisation pass has already run the first trip's pass over X
+            Tnum_o, norm_part_o = first_trip.Tnum, first_trip.norm_part
+        else:
+            Tnum_o = buf(nsplit_o, ld, zero=True)
+            norm_part_o = buf(nsplit_o * B, zero=True)
         Tden_o = buf(nsplit_o, ld, zero=True) if nan else None
-        norm_part_o = buf(nsplit_o * B, zero=True)
 
-    w = buf(p)
+    w = first_trip.w if first_trip is not None else buf(p)
     norm_part = buf(max(nparts, 1) * B, zero=True)
     Tnum = buf(nsplit, ld, zero=True)
     Tden = buf(nsplit, ld, zero=True) if nan else None
@@ -599,7 +654,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         trips_per_sync = 2 if est_ms > 1.0 else 4
     # what the closing pass of the previous component left behind for the first trip of the coming one:
     # None, "w" (its weights) or "scores" (weights, squared norms and partial block scores: no pass over X needed)
-    w_ready = None
+    w_ready = "scores" if first_trip is not None else None
     cur = torch.cuda.current_stream(dev)
 
     def timed(key, fn):

@@ -40,6 +40,7 @@ _RUNTIME_DEFAULTS = dict(
     group=None,           # torch.distributed process group: shard the feature axis over its ranks
     materialize=True,     # copy fitted attributes to numpy at the end of fit (False: on first access)
     fuse_next_xtu=True,   # loadings+deflation pass also emits the next component's first weights
+    fuse_first_trip=True,  # dense NIPALS: the standardisation pass also runs the first component's first trip (csrc/fused.cu)
     deflate_mode=0,       # 0 auto (smem-resident pipeline), 1 force global-memory fallback
     standardize_mode=0,   # idem for the standardisation pass
     trips_per_sync=None,  # NIPALS trips enqueued per convergence-flag readback (None: auto)
@@ -308,7 +309,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
 
         # (explicit choices among the streaming kernels keep the fit on them)
         tuned = any(rt[k] != _RUNTIME_DEFAULTS[k] for k in ("one_pass", "one_pass_deflate", "deflate_mode", "standardize_mode",
-                                                            "fuse_next_xtu", "trips_per_sync", "deflate_last"))
+                                                            "fuse_next_xtu", "fuse_first_trip", "trips_per_sync", "deflate_last"))
         if self.method == 'NIPALS' and not sparse and group is None and rt["global_sizes"] is None and rt["small_path"] is not False \
                 and rt["profile"] is None and (rt["small_path"] is True or not tuned):
             with torch.cuda.device(device):
@@ -364,16 +365,25 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             # ---- standardisation (mbpls.py:299-326)
             zss = None
             pre_lazy = None
+            first_trip = None
             if self.standardize:
                 prof = rt["profile"]
+                ys = E.standardize_fit(Yt, n, rt["standardize_mode"])
                 if prof is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record(torch.cuda.current_stream(device))
-                xs = E.standardize_fit(Xt, n, rt["standardize_mode"])
+                xs = None
+                if self.method == 'NIPALS' and not sparse and rt["one_pass"] is not False and rt["standardize_mode"] == 0 \
+                        and rt["fuse_first_trip"] and rt["one_pass_deflate"] is not False and rt["deflate_mode"] == 0:
+                    # dense NIPALS: the standardisation pass also runs the first trip of the first component (u = Y[:, 0])
+                    fused = E.standardize_fit_first_trip(Xt, n, shard.block_off, Yt[0])
+                    if fused is not None:
+                        xs, first_trip = fused
+                if xs is None:
+                    xs = E.standardize_fit(Xt, n, rt["standardize_mode"])
                 if prof is not None:
                     ev[1].record(torch.cuda.current_stream(device))
                     prof.setdefault("standardize", []).append(ev)
-                ys = E.standardize_fit(Yt, n, rt["standardize_mode"])
                 if not sparse:
                     # NaN shows up as seen < n, +-inf as a non-finite column mean / variance: no extra pass over X
                     pl = shard.p_local
@@ -388,7 +398,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             mark("standardize")
 
             if self.method == 'NIPALS':
-                self._fit_nipals(Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device)
+                self._fit_nipals(Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device, first_trip)
             else:
                 from . import crossmethods
                 crossmethods.fit(self, Xt, Yt, n, q, shard, boff_dev, zss, group, device)
@@ -628,7 +638,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         return s.cpu().numpy()
 
     # ---- NIPALS (mbpls.py:809-993)
-    def _fit_nipals(self, Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device):
+    def _fit_nipals(self, Xt, Yt, n, q, shard, boff_dev, zss, row_flag, ycol_flag, group, device, first_trip=None):
         rt = self._runtime()
         B, K = len(shard.sizes), int(self.n_components)
         sparse = bool(self.sparse_data)
@@ -657,7 +667,7 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
-                           one_pass_deflate=rt["one_pass_deflate"], col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
+                           one_pass_deflate=rt["one_pass_deflate"], first_trip=first_trip, col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
         self.n_iter_ = list(res.n_iter)
         self.__dict__["_exchange"] = res.exchange
         if any(it >= rt["max_iter"] for it in res.n_iter):

@@ -147,3 +147,29 @@ def test_deep_pls1_fit_keeps_two_trips_per_component():
     m, o = _pair(kw, X, Y.ravel(), one_pass=True)
     _check(m, o, X, Y.ravel(), kw, "exact deflation, long fit")
     assert list(m.n_iter_) == [2] * K == list(o.n_iter_)
+
+
+@pytest.mark.parametrize("n,sizes", [(37, (21, 40)), (640, (90, 33)), (1300, (64, 48, 9)), (2570, (75, 30)), (5200, (50, 45)),
+                                     (9999, (30, 25)), (10000, (40, 56)), (10240, (33, 31))])
+def test_standardisation_fused_with_the_first_trip(n, sizes):
+    """fused_standardize_kernel: StandardScaler.fit_transform and the first component's first trip in one read + write of X,
+    for every worker configuration, with and without padding (n % 16), constant columns included -- against the oracle and
+    against the separate standardise / trip kernels."""
+    from oracle.cases import latent_blocks
+    from mbpls_b200 import MBPLS
+    X, Y = latent_blocks(n, sizes, 2, 3, seed=n % 89 + 1)
+    X[0][:, 2] = 3.25        # constant feature: scale 1, z = 0
+    X[1][:, 0] += 1e6        # large offset: the corrected two-pass variance must survive it
+    kw = dict(n_components=3, method="NIPALS")
+    m, o = _pair(kw, X, Y, one_pass=True, fuse_first_trip=True)
+    _check(m, o, X, Y, kw, f"fused standardise n={n}")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s = MBPLS(**kw).set_runtime(one_pass=True, fuse_first_trip=False).fit([x.copy() for x in X], Y.copy())
+    assert list(m.n_iter_) == list(s.n_iter_)
+    assert rel_err(m.beta_, s.beta_) < 1e-10
+    for a, b in zip(m.x_scalers_, s.x_scalers_):
+        assert np.allclose(a.mean_, b.mean_, rtol=1e-14, atol=0) and np.allclose(a.scale_, b.scale_, rtol=1e-13, atol=0)
+        assert np.allclose(a.var_, b.var_, rtol=1e-12, atol=1e-300)
+    assert m.x_scalers_[0].scale_[2] == 1.0
+    assert np.allclose(np.asarray(m.explained_var_xblocks_), np.asarray(s.explained_var_xblocks_), rtol=1e-10)
