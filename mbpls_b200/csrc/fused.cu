@@ -583,9 +583,9 @@ __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a
 // StandardScaler.fit_transform (mbpls.py:307,314) AND the first trip of the first component in one read + one write.
 // The first trip's u is the first (standardised) Y column -- known before X is touched -- so while a feature sits in
 // registers for its statistics it can also deliver its first weight w~_j = z_j . u0 / u0'u0 and add to the first block-score
-// partials, exactly as the deflation pass does for later components.  Three worker reductions per feature: sum (mean), the
-// corrected two-pass variance (sklearn's _incremental_mean_and_var: sum of deviations and of their squares), and
-// {sum z^2, z . u0}.  Dense data only (a NaN shows up as a non-finite mean and is reported by the caller, like check_array).
+// partials, exactly as the deflation pass does for later components.  Two worker reductions per feature: the sum (mean), then
+// {sum of deviations, sum of squared deviations, deviations . u0} -- the corrected two-pass variance of sklearn's
+// _incremental_mean_and_var, and, because z = d / scale, also sum z^2 and z . u0 without a third one.  Dense data only (a NaN shows up as a non-finite mean and is reported by the caller, like check_array).
 // Samples beyond n (the zero padding of a feature) take no part and stay zero.
 // ------------------------------------------------------------------------------------------
 struct StdArgs {
@@ -596,7 +596,7 @@ struct StdArgs {
   double* zss;
 };
 
-template <class C, bool PAD>  // PAD: n < ld, the last elements of a feature are padding
+template <class C>
 __global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedArgs a, const StdArgs so) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Geo ge = make_geo<C, false>(a.ld, a.n);
@@ -619,17 +619,7 @@ __global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedAr
   const double2* __restrict__ u2 = reinterpret_cast<const double2*>(sm.vec0);
   double* scratch = sm.scratch + static_cast<size_t>(g) * 2 * 3 * C::NW;
   const int sync_mode = a.sync_mode;
-  // which of this thread's elements are padding (index >= n): they are excluded from the statistics and stay zero
-  uint32_t padx = 0, pady = 0;
-  if (PAD) {
-#pragma unroll
-    for (int k = 0; k < C::EPT; ++k) {
-      const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
-      if (2 * gi >= a.n) padx |= 1u << k;
-      if (2 * gi + 1 >= a.n) pady |= 1u << k;
-    }
-  }
-
+  const int nn = a.n;  // register slots at or beyond sample n (padding of the feature, or beyond it) hold no data
   double2 acc[C::EPT], x[C::EPT];
 #pragma unroll
   for (int k = 0; k < C::EPT; ++k) acc[k] = x[k] = make_double2(0.0, 0.0);
@@ -678,26 +668,34 @@ __global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedAr
     worker_sum<1, C::kTG>(one, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
     const double mean = one[0] / cnt;
-    double two[2] = {0.0, 0.0};  // sum of deviations (correction term), sum of squared deviations
+    double thr[3] = {0.0, 0.0, 0.0};  // sum of deviations (correction term), sum of squared deviations, deviations . u0
 #pragma unroll
     for (int k = 0; k < C::EPT; ++k) {
+      const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
+      const int e0 = 2 * gi;
       double2 d;
-      d.x = (PAD && ((padx >> k) & 1u)) ? 0.0 : x[k].x - mean;
-      d.y = (PAD && ((pady >> k) & 1u)) ? 0.0 : x[k].y - mean;
-      two[0] += d.x + d.y;
-      two[1] = fma(d.x, d.x, two[1]);
-      two[1] = fma(d.y, d.y, two[1]);
+      d.x = e0 < nn ? x[k].x - mean : 0.0;
+      d.y = e0 + 1 < nn ? x[k].y - mean : 0.0;
+      if (e0 < nn) {
+        const double2 uv = u2[gi];
+        thr[2] = fma(d.x, uv.x, thr[2]);
+        thr[2] = fma(d.y, uv.y, thr[2]);
+      }
+      thr[0] += d.x + d.y;
+      thr[1] = fma(d.x, d.x, thr[1]);
+      thr[1] = fma(d.y, d.y, thr[1]);
       x[k] = d;
     }
-    worker_sum<2, C::kTG>(two, scratch + flip * 3 * C::NW, g, wig, lane);
+    worker_sum<3, C::kTG>(thr, scratch + flip * 3 * C::NW, g, wig, lane);
     flip ^= 1;
-    double ssq = two[1] - two[0] * two[0] / cnt;
-    const double var = ssq / cnt;
+    const double var = (thr[1] - thr[0] * thr[0] / cnt) / cnt;
     const double eps = 2.220446049250313e-16;
     const double bound = cnt * eps * var + (cnt * mean * eps) * (cnt * mean * eps);
     const double scale = (var <= bound) ? 1.0 : sqrt(var);  // _is_constant_feature -> scale 1
+    // z = d / scale: sum z^2 = sum d^2 / scale^2 and z . u0 = (d . u0) / scale need no third reduction
+    wj = thr[2] / scale * inv_uu;
+    normsq = fma(wj, wj, normsq);
     double2* __restrict__ xg = reinterpret_cast<double2*>(X + static_cast<size_t>(j) * ld);
-    double thr[2] = {0.0, 0.0};  // sum z^2, z . u0
 #pragma unroll
     for (int k = 0; k < C::EPT; ++k) {
       const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
@@ -706,24 +704,15 @@ __global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedAr
         z.x = x[k].x / scale;  // (x - mean) / scale with a true division, like StandardScaler
         z.y = x[k].y / scale;
         st_stream(xg + gi, z);
-        const double2 uv = u2[gi];
-        thr[0] = fma(z.x, z.x, thr[0]);
-        thr[0] = fma(z.y, z.y, thr[0]);
-        thr[1] = fma(z.x, uv.x, thr[1]);
-        thr[1] = fma(z.y, uv.y, thr[1]);
         x[k] = z;
       }
     }
-    worker_sum<2, C::kTG>(thr, scratch + flip * 3 * C::NW, g, wig, lane);
-    flip ^= 1;
-    wj = thr[1] * inv_uu;
-    normsq = fma(wj, wj, normsq);
     if (tg == 0) {
       so.mean[j] = mean;
       so.var[j] = var;
       so.scale[j] = scale;
       so.seen[j] = static_cast<long long>(a.n);
-      so.zss[j] = thr[0];
+      so.zss[j] = thr[1] / (scale * scale);
       a.w[j] = wj;
     }
   }
@@ -957,13 +946,8 @@ int mbpls_fused_standardize_f64(double* Xt, long ld, int n, const double* u0, co
   do {                                                                                                                       \
     const size_t smem = fused_smem_bytes<CFG>(ld, 1);                                                                        \
     if (smem > static_cast<size_t>(smem_optin())) return MBPLS_ERR_SIZE;                                                     \
-    if (n < ld) {                                                                                                            \
-      cudaFuncSetAttribute(fused_standardize_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-      fused_standardize_kernel<CFG, true><<<(nsplit + CFG::G - 1) / CFG::G, 512, smem, st>>>(a, so);                         \
-    } else {                                                                                                                 \
-      cudaFuncSetAttribute(fused_standardize_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-      fused_standardize_kernel<CFG, false><<<(nsplit + CFG::G - 1) / CFG::G, 512, smem, st>>>(a, so);                        \
-    }                                                                                                                        \
+    cudaFuncSetAttribute(fused_standardize_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    fused_standardize_kernel<CFG><<<(nsplit + CFG::G - 1) / CFG::G, 512, smem, st>>>(a, so);                                  \
   } while (0)
   switch (pl.trip) {
     case 1: STD_LAUNCH(CfgA); break;
