@@ -40,7 +40,9 @@ _RUNTIME_DEFAULTS = dict(
     group=None,           # torch.distributed process group: shard the feature axis over its ranks
     materialize=True,     # copy fitted attributes to numpy at the end of fit (False: on first access)
     fuse_next_xtu=True,   # loadings+deflation pass also emits the next component's first weights
-    fuse_first_trip=True,  # dense NIPALS: the standardisation pass also runs the first component's first trip (csrc/fused.cu)
+    fuse_first_trip=False,  # dense NIPALS: the standardisation pass also runs the first component's first trip (csrc/fused.cu).
+                          # Opt-in: saves 6 ms of the 835 ms headline fit, but its statistics are summed in another order than
+                          # the standalone pass, which moves noise-floor exits of deep PLS1 components by a trip
     deflate_mode=0,       # 0 auto (smem-resident pipeline), 1 force global-memory fallback
     standardize_mode=0,   # idem for the standardisation pass
     trips_per_sync=None,  # NIPALS trips enqueued per convergence-flag readback (None: auto)
