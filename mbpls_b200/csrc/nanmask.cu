@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) nan_bitmask_kernel(const double* __restri
 // SMEM: the products v_i v2_i are staged once per CTA in shared memory (8 n bytes), so the gather under every set bit is a
 // shared-memory read instead of a global one (ncu on the global form: 64 % of the stall samples on those gathers).
 template <bool SMEM>
-__global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __restrict__ bits, long ldw, int n, int p,
+__global__ void __launch_bounds__(SMEM ? 1024 : 256, SMEM ? 2 : 1) masked_colden_kernel(const unsigned* __restrict__ bits, long ldw, int n, int p,
                                                             const int* __restrict__ col_nan, const double* __restrict__ v,
                                                             const double* __restrict__ v2, const double* __restrict__ vv_ptr, int mode,
                                                             double* __restrict__ out, const int* __restrict__ done) {
@@ -67,16 +67,27 @@ __global__ void __launch_bounds__(256) masked_colden_kernel(const unsigned* __re
       continue;
     }
     const unsigned* row = bits + static_cast<size_t>(j) * ldw;
-    double miss = 0.0;
-    for (int w = lane; w < nwords; w += 32) {
-      unsigned m = row[w];
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        miss += SMEM ? cd_prod[w * 32 + b] : v[w * 32 + b] * v2[w * 32 + b];
+    // two mask words per lane at a time, each with its own accumulator: two independent gather + add chains per iteration, and
+    // the iteration count of the warp (its longest lane) follows max(popc) over word pairs instead of the sum over single words
+    double miss = 0.0, miss2 = 0.0;
+    for (int w = lane; w < nwords; w += 64) {
+      unsigned ma = row[w];
+      unsigned mb = w + 32 < nwords ? row[w + 32] : 0u;
+      const int ia = w * 32, ib = ia + 1024;
+      while (ma | mb) {
+        if (ma) {
+          const int b = __ffs(ma) - 1;
+          ma &= ma - 1;
+          miss += SMEM ? cd_prod[ia + b] : v[ia + b] * v2[ia + b];
+        }
+        if (mb) {
+          const int b = __ffs(mb) - 1;
+          mb &= mb - 1;
+          miss2 += SMEM ? cd_prod[ib + b] : v[ib + b] * v2[ib + b];
+        }
       }
     }
-    miss = warp_sum(miss);
+    miss = warp_sum(miss + miss2);
     double obs = vv - miss;
     if (fabs(miss) > 0.5 * fabs(vv)) {
       // most of the mass sits under the holes: "total minus missing" would cancel (and could reach 0 or change sign where
@@ -104,6 +115,13 @@ __global__ void __launch_bounds__(1024) vec_dot_kernel(const double* __restrict_
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(a[i], b[i], acc);
   acc = block_sum1(acc, scratch);
   if (threadIdx.x == 0) out[0] = acc;
+}
+
+// 1.0 where bit b of the mask word is clear (sample observed), 0.0 where it is set: only the high word depends on the bit (one
+// 32-bit select), and q * {0.0, 1.0} + acc is exact, so the predicated addition `acc += bit ? 0 : q` (LOP3 + 2 FSEL + DADD) becomes
+// LOP3 + SEL + DFMA -- the kernel is bound by its instruction count.
+__device__ __forceinline__ double obs_factor(unsigned m, int b) {
+  return __hiloint2double(((m >> b) & 1u) ? 0 : 0x3ff00000, 0);
 }
 
 // Tden[s][i] = sum over the features j of split s that are observed in sample i of w_j^2.
@@ -135,10 +153,10 @@ __global__ void __launch_bounds__(256) masked_rowden_kernel(const unsigned* __re
     const double q0 = a0 * a0, q1 = a1 * a1, q2 = a2 * a2, q3 = a3 * a3;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-      acc[b] += ((m0 >> b) & 1u) ? 0.0 : q0;
-      acc[b] += ((m1 >> b) & 1u) ? 0.0 : q1;
-      acc[b] += ((m2 >> b) & 1u) ? 0.0 : q2;
-      acc[b] += ((m3 >> b) & 1u) ? 0.0 : q3;
+      acc[b] = fma(q0, obs_factor(m0, b), acc[b]);
+      acc[b] = fma(q1, obs_factor(m1, b), acc[b]);
+      acc[b] = fma(q2, obs_factor(m2, b), acc[b]);
+      acc[b] = fma(q3, obs_factor(m3, b), acc[b]);
     }
   }
   for (; j + 8 < f1; j += 16) {  // two features per step
@@ -148,8 +166,8 @@ __global__ void __launch_bounds__(256) masked_rowden_kernel(const unsigned* __re
     const double q0 = a0 * a0, q1 = a1 * a1;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-      acc[b] += ((m0 >> b) & 1u) ? 0.0 : q0;
-      acc[b] += ((m1 >> b) & 1u) ? 0.0 : q1;
+      acc[b] = fma(q0, obs_factor(m0, b), acc[b]);
+      acc[b] = fma(q1, obs_factor(m1, b), acc[b]);
     }
   }
   for (; j < f1; j += 8) {
@@ -157,7 +175,7 @@ __global__ void __launch_bounds__(256) masked_rowden_kernel(const unsigned* __re
     const double a0 = __ldg(w + j);
     const double q0 = a0 * a0;
 #pragma unroll
-    for (int b = 0; b < 32; ++b) acc[b] += ((m0 >> b) & 1u) ? 0.0 : q0;
+    for (int b = 0; b < 32; ++b) acc[b] = fma(q0, obs_factor(m0, b), acc[b]);
   }
   double* out = Tden + static_cast<size_t>(s) * ldt;
 #pragma unroll
@@ -201,10 +219,11 @@ int mbpls_masked_colden_f64(const unsigned* bits, long ldw, int n, int p, const 
   int grid = (p + 7) / 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(n) * sizeof(double);
-  if (smem <= 100 * 1024) {  // two CTAs per SM keep their copy of the products resident
+  if (smem <= 100 * 1024) {  // two 1024-thread CTAs per SM (all 64 warps: the gathers are latency-bound), each with its copy of the products
+    grid = (p + 31) / 32;
     if (grid > num_sms() * 2) grid = num_sms() * 2;
     cudaFuncSetAttribute(masked_colden_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    masked_colden_kernel<true><<<grid, 256, smem, st>>>(bits, ldw, n, p, col_nan, v, v2 ? v2 : v, vv, mode, out, done);
+    masked_colden_kernel<true><<<grid, 1024, smem, st>>>(bits, ldw, n, p, col_nan, v, v2 ? v2 : v, vv, mode, out, done);
   } else {
     if (grid > num_sms() * 16) grid = num_sms() * 16;
     masked_colden_kernel<false><<<grid, 256, 0, st>>>(bits, ldw, n, p, col_nan, v, v2 ? v2 : v, vv, mode, out, done);

@@ -18,6 +18,21 @@
 
 using namespace mbpls;
 
+// Phase timestamps of xchg_epilogue_kernel for scripts/probes/xchg_probe.cu (compiled in with -DMBPLS_XCHG_STAMPS only)
+#ifdef MBPLS_XCHG_STAMPS
+__device__ unsigned long long g_xchg_stamps[16];
+#define XSTAMP(k)                                                                   \
+  do {                                                                              \
+    if (threadIdx.x == 0) {                                                         \
+      unsigned long long t_;                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                        \
+      atomicMax(&g_xchg_stamps[k], t_);                                             \
+    }                                                                               \
+  } while (0)
+#else
+#define XSTAMP(k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // xtu: one warp handles two features at a time, lanes stride along the sample axis with 16-byte
 // loads, four loads per feature in flight.  NaN mode accumulates the masked denominator in the same
@@ -476,6 +491,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
     }
   }
   block_sum<8>(ab, scratch);
+  XSTAMP(5);
   if (tid == 0) {  // superweights to unit length (:880)
     double s = 0.0;
     for (int b = 0; b < B; ++b) {
@@ -549,6 +565,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
     s_sc[0] = diff;
   }
   const double tt = v4[3];
+  XSTAMP(6);
 
   // phase 4: Y weights v = Y'ts / ts'ts (:899), eight columns per pass
   for (int c0 = 0; c0 < q; c0 += 8) {
@@ -583,6 +600,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   const double vv = s_sc[1];
 
   // phase 5: Y scores u = Y v / v'v, normalised (:911-913)
+  XSTAMP(7);
   double un = 0.0;
 #pragma unroll
   for (int k = 0; k < EPS_ITEMS; ++k) {
@@ -675,6 +693,7 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
   const int tid = threadIdx.x, G = gridDim.x;
   const bool multi = x.world > 1;
   double* mine = multi ? reinterpret_cast<double*>(x.peer_bufs[x.rank]) + (x.seq & 1ull) * x.slot_elems : const_cast<double*>(a.red);
+  XSTAMP(0);
 
   // ---- A: split partials -> this rank's sums
   for (long it = static_cast<long>(blockIdx.x) * blockDim.x + tid; it < nitems; it += static_cast<long>(G) * blockDim.x) {
@@ -693,6 +712,7 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
       mine[norm_off + b] = acc;
     }
   }
+  XSTAMP(1);
   if (multi) {
     __threadfence_system();
     __syncthreads();
@@ -726,6 +746,7 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
       if (tid == 0) a.ctrl[MBPLS_CTRL_ERROR] = 1;
       return;
     }
+    XSTAMP(2);
     double* red = const_cast<double*>(a.red);
     const size_t slot = (x.seq & 1ull) * x.slot_elems;
     for (long it = static_cast<long>(blockIdx.x) * blockDim.x + tid; it < nitems + B; it += static_cast<long>(G) * blockDim.x) {
@@ -742,6 +763,7 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
     }
   }
   // ---- C: the last CTA runs the superlevel step on the sums
+  XSTAMP(3);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -752,8 +774,10 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
+  XSTAMP(4);
   if (epilogue_small_ok(a)) epilogue_body_small(a);
   else epilogue_body(a);
+  XSTAMP(9);
 }
 
 // ------------------------------------------------------------------------------------------
