@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 13
+#define MBPLS_ABI_VERSION 14
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -161,6 +161,7 @@ typedef struct mbpls_record_args {
   const int* block_off;
   const double *w, *red, *T, *ts, *u, *v, *a;
   double *Wt_k, *W_k, *Ts_k, *U_k, *T_k, *V_k, *A_k;
+  const int* only_if_done; /* may be NULL; else the launch is a no-op unless *only_if_done is set (see mbpls_fused_deflate_f64) */
 } mbpls_record_args;
 /* append the converged component (mbpls.py:975-983): W_non_normal_, W_, Ts_, U_, T_, V_, A_ */
 int mbpls_nipals_record_component_f64(const mbpls_record_args* args_host, void* stream);
@@ -198,11 +199,14 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
 /* Loadings p_j = x_j . ts and X <- X - ts p' (mbpls.py:917-930, :968-969) in place, and -- if u0 != NULL -- the complete
  * first trip of the next component (u restarts from u0, :838): w_next[j] = x_j(deflated) . u0 / u0'u0, its squared norms
  * and its partial block scores Tnum.  1 read + 1 write of X.  NaN mode (rden_ts != NULL): masked loadings / weights through
- * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0); NaN entries stay NaN. */
+ * the reciprocal denominators rden_ts (for ts, dense features: 1) and rden_u0 (for u0); NaN entries stay NaN.
+ * only_if_done != NULL: the launch is a no-op unless *only_if_done (ctrl[MBPLS_CTRL_DONE]) is set -- the host enqueues the
+ * closing pass of a component behind its trips before it knows whether they converged, so the GPU never idles while the
+ * host reads the flag back; if they did not, it enqueues more trips and the closing pass again. */
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
                             const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
-                            double* Tnum, long ldt, void* stream);
+                            double* Tnum, long ldt, const int* only_if_done, void* stream);
 
 /* StandardScaler.fit_transform of X in place (mbpls.py:307,314) fused with the complete first trip of the first component
  * (u = u0 = the first standardised Y column, :838): per-feature statistics as mbpls_standardize_fit_f64, first weights w,

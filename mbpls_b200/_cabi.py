@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -64,6 +64,7 @@ class RecordArgs(C.Structure):
         ("block_off", _p),
         ("w", _p), ("red", _p), ("T", _p), ("ts", _p), ("u", _p), ("v", _p), ("a", _p),
         ("Wt_k", _p), ("W_k", _p), ("Ts_k", _p), ("U_k", _p), ("T_k", _p), ("V_k", _p), ("A_k", _p),
+        ("only_if_done", _p),
     ]
 
 
@@ -100,7 +101,7 @@ SIGNATURES = {
     "mbpls_fused_uses_clusters": [_l],
     "mbpls_nipals_fused_trip_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _l, _p, _p],
     "mbpls_fused_standardize_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p],
-    "mbpls_fused_deflate_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p],
+    "mbpls_fused_deflate_f64": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p],
     "mbpls_vec_dot_f64": [_p, _p, _i, _p, _p],
     "mbpls_nan_bitmask_ldw": [_i],
     "mbpls_nan_bitmask_f64": [_p, _l, _i, _i, _p, _l, _p],

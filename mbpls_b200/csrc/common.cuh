@@ -100,6 +100,33 @@ __device__ __forceinline__ double block_sum1(double x, double* scratch) {
   return v[0];
 }
 
+// ---- exact division by a divisor shared by many elements ---------------------------------------------------
+// Standardisation divides a whole feature by its scale, the superlevel step divides n-vectors by their norms: one divisor,
+// thousands of dividends.  An IEEE fp64 division is ~30 instructions on the FP64 pipe (MUFU.RCP64H seed, Newton steps,
+// correction, range checks) and is what those passes stall on.  With r = RN(1/b) computed ONCE (a true division), Markstein's
+// theorem gives the correctly rounded quotient in three instructions:
+//     q0 = RN(a r);   e = a - b q0  (exact, one FMA);   q = RN(q0 + e r)  ==  RN(a / b)
+// (q0 is within an ulp of a/b because r is correctly rounded; the FMA residual is exact; the final FMA rounds once.)  The
+// result is bit-identical to `a / b`, so nothing downstream -- trip counts included -- can tell the difference.  Quotients that
+// are zero, denormal-range, huge or not finite, and divisors far from 1 in magnitude, take the ordinary division.
+struct UniformDivisor {
+  double b, r;
+  bool fast;
+  __device__ __forceinline__ explicit UniformDivisor(double divisor) : b(divisor), r(1.0 / divisor) {
+    const double ab = fabs(divisor);
+    fast = ab >= 0x1p-200 && ab <= 0x1p200;
+  }
+  __device__ __forceinline__ double operator()(double a) const {
+    if (fast) {
+      const double q0 = a * r;
+      const double q = fma(fma(-q0, b, a), r, q0);
+      const double aq = fabs(q);
+      if (aq >= 0x1p-700 && aq <= 0x1p700) return q;
+    }
+    return a / b;
+  }
+};
+
 // ---- mbarrier + 1-D bulk async copies (TMA engine; SASS: UBLKCP / SYNCS) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

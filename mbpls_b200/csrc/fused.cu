@@ -76,7 +76,7 @@ struct FusedArgs {
   long ldt;
   double* P_k;  // deflate: loadings out
   double* pss;  // deflate: p_j^2 out
-  const int* done;
+  const int* done;  // trip: skip the launch once *done is set; deflate: (may be null) run only if *done is set
   int sync_mode;  // stage hand-off protocol, see arrive_stage(): 2 = "empty" mbarrier (default), 0 / 1 = shared-memory counters
 };
 
@@ -564,6 +564,7 @@ __device__ __forceinline__ void fused_deflate_body(const FusedArgs& a, const Sme
 
 template <bool NANMODE, class C, bool CL>
 __global__ void __launch_bounds__(512, 1) fused_deflate_kernel(const FusedArgs a) {
+  if (a.done && !*a.done) return;  // enqueued behind trips that have not converged yet: nothing to close (see engine.nipals_fit)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Geo ge = make_geo<C, CL>(a.ld, a.n);
   const Smem<C> sm(smem_raw, 2 * ge.units, 2);  // ts | u0 (this CTA's share)
@@ -696,13 +697,14 @@ __global__ void __launch_bounds__(512, 1) fused_standardize_kernel(const FusedAr
     wj = thr[2] / scale * inv_uu;
     normsq = fma(wj, wj, normsq);
     double2* __restrict__ xg = reinterpret_cast<double2*>(X + static_cast<size_t>(j) * ld);
+    const UniformDivisor by_scale(scale);  // (x - mean) / scale, bit-identical to StandardScaler's true division (common.cuh)
 #pragma unroll
     for (int k = 0; k < C::EPT; ++k) {
       const int gi = (k / C::EPTC) * C::UC + tg + (k % C::EPTC) * C::kTG;
       if (((k / C::EPTC) + 1 < ncf) || gi < units) {
         double2 z;
-        z.x = x[k].x / scale;  // (x - mean) / scale with a true division, like StandardScaler
-        z.y = x[k].y / scale;
+        z.x = by_scale(x[k].x);
+        z.y = by_scale(x[k].y);
         st_stream(xg + gi, z);
         x[k] = z;
       }
@@ -912,14 +914,14 @@ int mbpls_nipals_fused_trip_f64(const double* Xt, long ld, int n, const double* 
 int mbpls_fused_deflate_f64(double* Xt, long ld, int n, const double* ts, const double* rden_ts, const double* u0,
                             const double* u0u0, const double* rden_u0, const int* split_f0, const int* split_f1,
                             const int* split_block, int nsplit, int B, double* P_k, double* pss, double* w_next, double* norm_part,
-                            double* Tnum, long ldt, void* stream) {
+                            double* Tnum, long ldt, const int* only_if_done, void* stream) {
   if (!Xt || !ts || !split_f0 || !split_f1 || !split_block || !P_k || !pss || ld < n || B < 1) return MBPLS_ERR_ARG;
   if (u0 && (!u0u0 || !w_next || !norm_part || !Tnum || ldt < ld || (rden_ts && !rden_u0))) return MBPLS_ERR_ARG;
   if (nsplit == 0) return MBPLS_OK;
   const Plan pl = plan_of(ld);
   if (!pl.deflate || nsplit > pl.workers) return MBPLS_ERR_SIZE;
   FusedArgs a{nullptr, Xt, ld, n, u0, u0u0, ts, rden_ts, rden_u0, split_f0, split_f1, split_block, nsplit, B,
-              w_next, norm_part, Tnum, ldt, P_k, pss, nullptr, default_sync_mode()};
+              w_next, norm_part, Tnum, ldt, P_k, pss, only_if_done, default_sync_mode()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.deflate_cl) return rden_ts ? dispatch_deflate<true, true>(pl.deflate, a, st) : dispatch_deflate<false, true>(pl.deflate, a, st);
   return rden_ts ? dispatch_deflate<true, false>(pl.deflate, a, st) : dispatch_deflate<false, false>(pl.deflate, a, st);

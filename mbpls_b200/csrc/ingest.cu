@@ -131,9 +131,10 @@ __device__ __forceinline__ void standardize_resident(double* x, int n, int j, co
   double var;
   const double scale = scale_from(cnt, mean, c[0], c[1], var);
   double z[1] = {0.0};
+  const UniformDivisor by_scale(scale);  // bit-identical to `/ scale` (StandardScaler's true division), a tenth of the instructions
   for (int i = tid; i < n; i += nt) {
     double zi = x[i] - mean;
-    zi = zi / scale;
+    zi = by_scale(zi);
     x[i] = zi;
     if (!isnan(zi)) z[0] += zi * zi;
   }
@@ -203,10 +204,11 @@ struct StandardizeWideOp {
       double var;
       const double scale = scale_from(cnt, mean, c[0], c[1], var);
       double z[1] = {0.0};
+      const UniformDivisor by_scale(scale);
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = threadIdx.x + k * nt;
-        const double zi = xr[k] / scale;
+        const double zi = by_scale(xr[k]);
         if (i < n) x[i] = zi;
         if (!isnan(zi)) z[0] = fma(zi, zi, z[0]);
       }
@@ -279,11 +281,12 @@ __global__ void __launch_bounds__(256, 2) standardize_regs_kernel(double* __rest
     double2* x2 = reinterpret_cast<double2*>(Xt + static_cast<size_t>(j) * ld);
     const double2* xn = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(jn < p ? jn : j) * ld);
     double z[1] = {0.0};
+    const UniformDivisor by_scale(scale);
 #pragma unroll
     for (int k = 0; k < EPT2; ++k) {
       const int i = threadIdx.x + k * 256;
       if (i < n2) {
-        double2 zi = make_double2(xr[k].x / scale, xr[k].y / scale);
+        double2 zi = make_double2(by_scale(xr[k].x), by_scale(xr[k].y));
         if (!isnan(zi.x)) z[0] = fma(zi.x, zi.x, z[0]);
         if (!isnan(zi.y)) z[0] = fma(zi.y, zi.y, z[0]);
         if (odd && i == n2 - 1) zi.y = 0.0;  // keep the padding element zero
@@ -332,11 +335,12 @@ __global__ void __launch_bounds__(256) standardize_apply_kernel(double* __restri
                                                                 const double* __restrict__ scale) {
   const int j = blockIdx.y;
   if (j >= p) return;
-  const double m = mean[j], s = scale[j];
+  const double m = mean[j];
+  const UniformDivisor by_scale(scale[j]);
   double* x = Xt + static_cast<size_t>(j) * ld;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double z = x[i] - m;
-    x[i] = z / s;
+    x[i] = by_scale(z);
   }
 }
 

@@ -286,13 +286,14 @@ __device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
   // phase 1: block scores t_b (:862-875) and T'u (:879)
   for (int b = 0; b < B; ++b) {
     const double nb = s_norm[b];
+    const UniformDivisor by_nb(nb);  // (bit-identical to `/ nb`, a tenth of the instructions: common.cuh)
     double acc = 0.0;
     double* tb = a.T + static_cast<size_t>(b) * ldt;
     for (int i = tid; i < n; i += nt) {
       const double num = red_num[static_cast<size_t>(b) * ldt + i];
       double t;
       if (nan && a.row_flag[static_cast<size_t>(b) * a.ldf + i]) t = nb * num / red_den[static_cast<size_t>(b) * ldt + i];
-      else t = num / nb;
+      else t = by_nb(num);
       tb[i] = t;
       acc = fma(t, a.u[i], acc);
     }
@@ -321,12 +322,13 @@ __device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
   }
   ss = block_sum1(ss, scratch);
   const double tsn = sqrt(ss);
+  const UniformDivisor by_tsn(tsn);
 
   // phase 3: normalise, convergence metric against ts_old (:884-888), ts'ts
   double v4[4] = {0.0, 0.0, 0.0, 0.0};  // sum d^2, sum |d|, (unused), ts'ts
   double dmax = 0.0, dmin = INFINITY;
   for (int i = tid; i < n; i += nt) {
-    const double t = a.ts[i] / tsn;
+    const double t = by_tsn(a.ts[i]);
     const double d = a.ts_old[i] - t;
     a.ts[i] = t;
     a.ts_old[i] = t;
@@ -397,6 +399,7 @@ __device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
   // phase 5: Y scores u = Y v / v'v, normalised (:901-913).  NaN mode: rows flagged in the *last X
   // block* use observed Y columns only (the reference indexes sparse_X_info_[block] at :903).
   double un = 0.0;
+  const UniformDivisor by_vv(vv);
   for (int i = tid; i < n; i += nt) {
     double val;
     if (nan && a.row_flag[static_cast<size_t>(B - 1) * a.ldf + i]) {
@@ -412,16 +415,17 @@ __device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
     } else {
       double num = 0.0;
       for (int c = 0; c < q; ++c) num = fma(a.Yt[static_cast<size_t>(c) * ldt + i], s_v[c], num);
-      val = num / vv;
+      val = by_vv(num);
     }
     a.u[i] = val;
     un = fma(val, val, un);
   }
   un = block_sum1(un, scratch);
   const double unorm = sqrt(un);
+  const UniformDivisor by_un(unorm);
   double uu_new = 0.0;
   for (int i = tid; i < n; i += nt) {
-    const double val = a.u[i] / unorm;
+    const double val = by_un(a.u[i]);
     a.u[i] = val;
     uu_new = fma(val, val, uu_new);
   }
@@ -478,12 +482,12 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     if (b < B) {
-      const double nb = s_norm[b];
+      const UniformDivisor by_nb(s_norm[b]);  // (bit-identical to `/ nb`, a tenth of the instructions: common.cuh)
 #pragma unroll
       for (int k = 0; k < EPS_ITEMS; ++k) {
         const int i = tid + k * NT;
         if (i < n) {
-          const double t = red_num[static_cast<size_t>(b) * ldt + i] / nb;
+          const double t = by_nb(red_num[static_cast<size_t>(b) * ldt + i]);
           a.T[static_cast<size_t>(b) * ldt + i] = t;
           ab[b] = fma(t, ur[k], ab[b]);
         }
@@ -520,6 +524,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   }
   ss = block_sum1(ss, scratch);
   const double tsn = sqrt(ss);
+  const UniformDivisor by_tsn(tsn);
 
   // phase 3: normalise, convergence metric against ts_old (:884-888), ts'ts
   double v4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -528,7 +533,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   for (int k = 0; k < EPS_ITEMS; ++k) {
     const int i = tid + k * NT;
     if (i < n) {
-      const double t = tsr[k] / tsn;
+      const double t = by_tsn(tsr[k]);
       const double d = a.ts_old[i] - t;
       tsr[k] = t;
       a.ts[i] = t;
@@ -602,6 +607,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   // phase 5: Y scores u = Y v / v'v, normalised (:911-913)
   XSTAMP(7);
   double un = 0.0;
+  const UniformDivisor by_vv(vv);
 #pragma unroll
   for (int k = 0; k < EPS_ITEMS; ++k) {
     const int i = tid + k * NT;
@@ -609,19 +615,20 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
     if (i < n) {
       double num = 0.0;
       for (int c = 0; c < q; ++c) num = fma(a.Yt[static_cast<size_t>(c) * ldt + i], s_v[c], num);
-      val = num / vv;
+      val = by_vv(num);
     }
     ur[k] = val;
     un = fma(val, val, un);
   }
   un = block_sum1(un, scratch);
   const double unorm = sqrt(un);
+  const UniformDivisor by_un(unorm);
   double uu_new = 0.0;
 #pragma unroll
   for (int k = 0; k < EPS_ITEMS; ++k) {
     const int i = tid + k * NT;
     if (i < n) {
-      const double val = ur[k] / unorm;
+      const double val = by_un(ur[k]);
       a.u[i] = val;
       uu_new = fma(val, val, uu_new);
     }
@@ -786,6 +793,7 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 record_component_kernel(mbpls_record_args a) {
+  if (a.only_if_done && !*a.only_if_done) return;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gsz = gridDim.x * blockDim.x;
   const double* red_nrm = a.red + static_cast<size_t>(a.nanmode ? 2 * a.B : a.B) * a.ldt;

@@ -657,8 +657,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     w_ready = "scores" if first_trip is not None else None
     cur = torch.cuda.current_stream(dev)
 
-    def timed(key, fn):
-        """Optionally bracket one launch with CUDA events on the launching stream (bench.py roofline)."""
+    def timed(key, fn, sink=None):
+        """Optionally bracket one launch with CUDA events on the launching stream (bench.py roofline).  `sink`: collect the
+        event pair there instead (speculative launches count only if they turn out to have run)."""
         if profile is None:
             fn()
             return
@@ -666,12 +667,51 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         e0.record(cur)
         fn()
         e1.record(cur)
-        profile.setdefault(key, []).append((e0, e1))
+        (profile.setdefault(key, []) if sink is None else sink).append((e0, e1))
+
+    ready = torch.cuda.Event()
+    spec_events: list = []
+
+    def record(k, predicated):
+        rec = _cabi.RecordArgs(n=n, p=p, B=B, q=q, nanmode=nan, ldt=ld, T_block_stride=K * ld,
+                               block_off=boff.data_ptr(), w=w.data_ptr(), red=red.data_ptr(), T=T.data_ptr(),
+                               ts=ts.data_ptr(), u=u.data_ptr(), v=v.data_ptr(), a=a.data_ptr(),
+                               Wt_k=res.Wt[k].data_ptr(), W_k=res.W[k].data_ptr(), Ts_k=res.Ts[k].data_ptr(),
+                               U_k=res.U[k].data_ptr(), T_k=res.Tb[0, k].data_ptr(), V_k=res.V[k].data_ptr(),
+                               A_k=res.A[k].data_ptr(), only_if_done=ctrl.data_ptr() if predicated else None)
+        call("mbpls_nipals_record_component_f64", C.byref(rec), st)
+
+    def close_fused(k, fuse, predicated):
+        """Bookkeeping + loadings + deflation + the next component's first trip; `predicated`: every launch is a no-op unless the
+        component has converged (ctrl[DONE]) -- enqueued behind the trips BEFORE the host knows, so the GPU runs the 3-26 ms
+        deflation pass while the host reads the flag back and enqueues the next component instead of idling ~70 us per component
+        (gpurun_out/p_timeline_s0125.log: 20 x 69.5 us 'Memcpy DtoH -> record_component')."""
+        only = done_p if predicated else None
+        record(k, predicated)
+        if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
+            call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
+                 ptr(rden_ts), None, st)
+        timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
+                                      ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
+                                      ptr(rden_u0) if fuse else None,
+                                      ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
+                                      ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
+                                      ptr(Tnum_o) if fuse else None, ld, only, st), sink=spec_events if predicated else None)
+        if nan and fuse:
+            call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1), nsplit_o, ptr(Tden_o), ld,
+                 None, st)
+        # (sums whatever `pss` holds: after a no-op deflation the result is overwritten when the component really closes)
+        call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
 
     for k in range(K):
         call("mbpls_nipals_begin_component_f64", ptr(u0), n, ptr(u), ptr(scal), ptr(ctrl), st)
+        last = (k == K - 1)
+        fuse = fuse_next_xtu and not last
+        # dense fits on the one-pass kernels close every component but the last speculatively (see close_fused)
+        speculate = use_opd and not nan and not (last and not deflate_last)
         launched = 0
         batch, prev_diff = trips_per_sync, None
+        closed = False
         while True:
             for _ in range(max(1, min(batch, max_iter - launched))):
                 first = launched == 0
@@ -700,10 +740,18 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                 launched += 1
             ctrl_h.copy_(ctrl, non_blocking=True)
             scal_h.copy_(scal, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
+            if speculate:
+                ready.record(cur)
+                close_fused(k, fuse, True)
+                ready.synchronize()
+            else:
+                cur.synchronize()
             if int(ctrl_h[_cabi.CTRL_ERROR]):
                 raise _cabi.MbplsCudaError("a peer GPU did not arrive at the in-kernel exchange of a NIPALS trip (timeout)")
-            if int(ctrl_h[_cabi.CTRL_DONE]) or int(ctrl_h[_cabi.CTRL_TRIPS]) >= max_iter:
+            if int(ctrl_h[_cabi.CTRL_DONE]):
+                closed = speculate
+                break
+            if int(ctrl_h[_cabi.CTRL_TRIPS]) >= max_iter:
                 break
             # PLS2 loops converge geometrically: from the last two readings of diff_t estimate how many trips remain and enqueue
             # most of them before the next readback (trips past convergence are no-ops, so an over-estimate costs microseconds;
@@ -719,38 +767,26 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         res.diff.append(float(scal_h[_cabi.SCAL_DIFF]))
         res.tt.append(float(scal_h[_cabi.SCAL_TT]))
         res.vv.append(float(scal_h[_cabi.SCAL_VV]))
-        rec = _cabi.RecordArgs(n=n, p=p, B=B, q=q, nanmode=nan, ldt=ld, T_block_stride=K * ld,
-                               block_off=boff.data_ptr(), w=w.data_ptr(), red=red.data_ptr(), T=T.data_ptr(),
-                               ts=ts.data_ptr(), u=u.data_ptr(), v=v.data_ptr(), a=a.data_ptr(),
-                               Wt_k=res.Wt[k].data_ptr(), W_k=res.W[k].data_ptr(), Ts_k=res.Ts[k].data_ptr(),
-                               U_k=res.U[k].data_ptr(), T_k=res.Tb[0, k].data_ptr(), V_k=res.V[k].data_ptr(),
-                               A_k=res.A[k].data_ptr())
-        call("mbpls_nipals_record_component_f64", C.byref(rec), st)
-        last = (k == K - 1)
-        fuse = fuse_next_xtu and not last
+        if closed:
+            if profile is not None and spec_events:
+                profile.setdefault("deflate", []).append(spec_events[-1])  # the launch that found the flag set
+            spec_events.clear()
+            w_ready = "scores" if fuse else None
+            continue
+        spec_events.clear()
         if last and not deflate_last:
             # the deflated X of the last component is never read (mbpls.py:968-969 is followed by the end of the
             # loop), so only the loadings are computed: one read instead of read + write
+            record(k, False)
             timed("loadings", lambda: call("mbpls_nipals_xtu_f64", ptr(Xt), ld, n, p, ptr(ts), None, ptr(boff), B,
                                            ptr(res.P[k]), None, nan, None, st))
             if p > 0:
                 call("mbpls_block_sumsq_f64", ptr(res.P[k]), ptr(boff), B, ptr(res.pssb[k]), st)
         elif use_opd:
-            if nan:  # 1 / sum over the observed samples of ts^2 per feature (:923-925); scal[TT] = ts'ts
-                call("mbpls_masked_colden_f64", ptr(bits), ldw, n, p, ptr(col_nan), ptr(ts), None, ptr(scal[_cabi.SCAL_TT:]), 0,
-                     ptr(rden_ts), None, st)
-            timed("deflate", lambda: call("mbpls_fused_deflate_f64", ptr(Xt), ld, n, ptr(ts), ptr(rden_ts),
-                                          ptr(u0) if fuse else None, ptr(u0u0) if fuse else None,
-                                          ptr(rden_u0) if fuse else None,
-                                          ptr(osf0), ptr(osf1), ptr(osblk), nsplit_o, B, ptr(res.P[k]), ptr(pss),
-                                          ptr(w) if fuse else None, ptr(norm_part_o) if fuse else None,
-                                          ptr(Tnum_o) if fuse else None, ld, st))
-            if nan and fuse:
-                call("mbpls_masked_rowden_f64", ptr(bits), ldw, n, ptr(w), ptr(osf0), ptr(osf1), nsplit_o, ptr(Tden_o), ld,
-                     None, st)
-            call("mbpls_segsum_f64", ptr(pss), ptr(boff), B, ptr(res.pssb[k]), st)
+            close_fused(k, fuse, False)  # NaN data, or the max_iter cap was hit before convergence
             w_ready = "scores" if fuse else None
         else:
+            record(k, False)
             timed("deflate", lambda: call("mbpls_loadings_deflate_f64", ptr(Xt), ld, n, p, ptr(ts),
                                           ptr(u0) if fuse else None, ptr(u0u0) if fuse else None, ptr(res.P[k]),
                                           ptr(w) if fuse else None, ptr(pss), nan, deflate_mode, st))
