@@ -152,6 +152,11 @@ typedef struct mbpls_xchg_args {
   long slot_elems, flags_off;
   unsigned long long seq;
   unsigned int* counters;
+  double* work;                  /* optional: 32768 doubles of scratch, zero before the first call.  With it (and epoch > 0),
+                                    dense fits with B <= 8, q <= 16 and n <= 1024 * CTAs spread the superlevel step over all
+                                    CTAs of the launch (grid-wide sums through this buffer) */
+  unsigned long long epoch;      /* with `work`: 1, 2, 3, ... growing by one per call on this buffer */
+  int tpi, ch;                   /* set by the library (warps sharing one split sum, samples per CTA); callers leave them 0 */
 } mbpls_xchg_args;
 int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* args_host, int ctas, void* stream);
 

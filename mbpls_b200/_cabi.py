@@ -40,7 +40,8 @@ class XchgArgs(C.Structure):
         ("epi", EpilogueArgs),
         ("Tnum", _p), ("Tden", _p), ("ldp", _l), ("block_split_off", _p), ("norm_part", _p), ("n_norm_parts", _i),
         ("world", _i), ("rank", _i),
-        ("peer_bufs", _p), ("slot_elems", _l), ("flags_off", _l), ("seq", C.c_ulonglong), ("counters", _p),
+        ("peer_bufs", _p), ("slot_elems", _l), ("flags_off", _l), ("seq", C.c_ulonglong), ("counters", _p), ("work", _p),
+        ("epoch", C.c_ulonglong), ("tpi", _i), ("ch", _i),
     ]
 
 

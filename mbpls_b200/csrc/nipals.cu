@@ -449,6 +449,9 @@ __device__ __forceinline__ void epilogue_body(const mbpls_epilogue_args& a) {
 // one 8-wide block reduction, the q Y columns likewise, and no vector is re-read from global memory between the phases.
 // (The general body above makes 9 latency-bound passes and 9 reductions for B = 4, q = 1: 59 us at n = 10,000, which is a
 // third of a PLS2 trip on an 8-GPU shard.)  Same arithmetic per element; only the order of the block-wide sums differs.
+// Every phase first issues ALL of its global loads into registers and only then computes and stores: the stores (T, ts_old)
+// may alias the loads as far as the compiler can tell, and interleaved they ran as ~40 dependent L2 round trips (20 us for the
+// block scores alone, scripts/probes/xchg_probe.cu).
 #define EPS_ITEMS 10
 __device__ __forceinline__ bool epilogue_small_ok(const mbpls_epilogue_args& a) {
   return !a.nanmode && a.n <= EPS_ITEMS * 1024 && a.B <= 8 && a.q <= 16 && blockDim.x == 1024;
@@ -483,11 +486,17 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   for (int b = 0; b < 8; ++b) {
     if (b < B) {
       const UniformDivisor by_nb(s_norm[b]);  // (bit-identical to `/ nb`, a tenth of the instructions: common.cuh)
+      double num[EPS_ITEMS];
+#pragma unroll
+      for (int k = 0; k < EPS_ITEMS; ++k) {
+        const int i = tid + k * NT;
+        num[k] = i < n ? __ldcg(red_num + static_cast<size_t>(b) * ldt + i) : 0.0;
+      }
 #pragma unroll
       for (int k = 0; k < EPS_ITEMS; ++k) {
         const int i = tid + k * NT;
         if (i < n) {
-          const double t = by_nb(red_num[static_cast<size_t>(b) * ldt + i]);
+          const double t = by_nb(num[k]);
           a.T[static_cast<size_t>(b) * ldt + i] = t;
           ab[b] = fma(t, ur[k], ab[b]);
         }
@@ -511,17 +520,24 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   __syncthreads();
 
   // phase 2: superscore ts = T a, normalised (:882-883)
-  double tsr[EPS_ITEMS];
+  double tsr[EPS_ITEMS], old[EPS_ITEMS];
   double ss = 0.0;
 #pragma unroll
   for (int k = 0; k < EPS_ITEMS; ++k) {
     const int i = tid + k * NT;
-    double t = 0.0;
-    if (i < n)
-      for (int b = 0; b < B; ++b) t = fma(a.T[static_cast<size_t>(b) * ldt + i], s_a[b], t);
-    tsr[k] = t;
-    ss = fma(t, t, ss);
+    tsr[k] = 0.0;
+    old[k] = i < n ? a.ts_old[i] : 0.0;  // for phase 3: in flight during the reduction below
   }
+  for (int b = 0; b < B; ++b) {  // same order of the sum over blocks per element as before: b ascending
+    const double ab_ = s_a[b];
+#pragma unroll
+    for (int k = 0; k < EPS_ITEMS; ++k) {
+      const int i = tid + k * NT;
+      if (i < n) tsr[k] = fma(a.T[static_cast<size_t>(b) * ldt + i], ab_, tsr[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < EPS_ITEMS; ++k) ss = fma(tsr[k], tsr[k], ss);
   ss = block_sum1(ss, scratch);
   const double tsn = sqrt(ss);
   const UniformDivisor by_tsn(tsn);
@@ -534,7 +550,7 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
     const int i = tid + k * NT;
     if (i < n) {
       const double t = by_tsn(tsr[k]);
-      const double d = a.ts_old[i] - t;
+      const double d = old[k] - t;
       tsr[k] = t;
       a.ts[i] = t;
       a.ts_old[i] = t;
@@ -609,14 +625,20 @@ __device__ __forceinline__ void epilogue_body_small(const mbpls_epilogue_args& a
   double un = 0.0;
   const UniformDivisor by_vv(vv);
 #pragma unroll
+  for (int k = 0; k < EPS_ITEMS; ++k) ur[k] = 0.0;
+  for (int c = 0; c < q; ++c) {  // (column loop outside: the loads of one column are independent of each other)
+    const double vc = s_v[c];
+    const double* y = a.Yt + static_cast<size_t>(c) * ldt;
+#pragma unroll
+    for (int k = 0; k < EPS_ITEMS; ++k) {
+      const int i = tid + k * NT;
+      if (i < n) ur[k] = fma(y[i], vc, ur[k]);
+    }
+  }
+#pragma unroll
   for (int k = 0; k < EPS_ITEMS; ++k) {
     const int i = tid + k * NT;
-    double val = 0.0;
-    if (i < n) {
-      double num = 0.0;
-      for (int c = 0; c < q; ++c) num = fma(a.Yt[static_cast<size_t>(c) * ldt + i], s_v[c], num);
-      val = by_vv(num);
-    }
+    const double val = i < n ? by_vv(ur[k]) : 0.0;
     ur[k] = val;
     un = fma(val, val, un);
   }
@@ -702,15 +724,43 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
   double* mine = multi ? reinterpret_cast<double*>(x.peer_bufs[x.rank]) + (x.seq & 1ull) * x.slot_elems : const_cast<double*>(a.red);
   XSTAMP(0);
 
-  // ---- A: split partials -> this rank's sums
-  for (long it = static_cast<long>(blockIdx.x) * blockDim.x + tid; it < nitems; it += static_cast<long>(G) * blockDim.x) {
-    const int r = static_cast<int>(it / n), i = static_cast<int>(it - static_cast<long>(r) * n);
-    const int b = r < B ? r : r - B;
-    const double* src = r < B ? x.Tnum : x.Tden;
-    const int s0 = x.block_split_off[b], s1 = x.block_split_off[b + 1];
-    double acc = 0.0;
-    for (int sp = s0; sp < s1; ++sp) acc += src[static_cast<size_t>(sp) * x.ldp + i];
-    mine[static_cast<size_t>(r) * ldt + i] = acc;
+  // ---- A: split partials -> this rank's sums.  An item (row r, sample i) is the sum of its block's split partials; `tpi`
+  // warps share an item (warp w of a group takes the splits s0 + w, s0 + w + tpi, ...; lanes = 32 consecutive samples, so every
+  // load is a full 256-byte row segment) and their partial sums are added in a fixed order -- short problems with many splits
+  // (n = 2,000 in 592 splits: 222 dependent additions per item) would otherwise leave most of the CTAs idle.
+  {
+    __shared__ double s_part[1024];
+    const int tpi = x.tpi > 1 ? x.tpi : 1;  // power of two <= 32, the same for every launch of a fit
+    const int ipc = 1024 / tpi;             // items per CTA and round
+    const int warp = tid >> 5, lane = tid & 31;
+    const int sub = warp % tpi, item_local = (warp / tpi) * 32 + lane;
+    for (long base = static_cast<long>(blockIdx.x) * ipc; base < nitems; base += static_cast<long>(G) * ipc) {
+      const long it = base + item_local;
+      double acc = 0.0;
+      int r = 0, i = 0;
+      if (it < nitems) {
+        r = static_cast<int>(it / n);
+        i = static_cast<int>(it - static_cast<long>(r) * n);
+        const int b = r < B ? r : r - B;
+        const double* src = r < B ? x.Tnum : x.Tden;
+        const int s0 = x.block_split_off[b], s1 = x.block_split_off[b + 1];
+        for (int sp = s0 + sub; sp < s1; sp += tpi) acc += src[static_cast<size_t>(sp) * x.ldp + i];
+      }
+      if (tpi == 1) {
+        if (it < nitems) mine[static_cast<size_t>(r) * ldt + i] = acc;
+      } else {
+        s_part[sub * ipc + item_local] = acc;
+        __syncthreads();
+        if (tid < ipc && base + tid < nitems) {
+          const long it2 = base + tid;
+          const int r2 = static_cast<int>(it2 / n), i2 = static_cast<int>(it2 - static_cast<long>(r2) * n);
+          double t = 0.0;
+          for (int k = 0; k < tpi; ++k) t += s_part[k * ipc + tid];
+          mine[static_cast<size_t>(r2) * ldt + i2] = t;
+        }
+        __syncthreads();
+      }
+    }
   }
   if (blockIdx.x == 0 && tid < 32) {  // squared block-weight norms: one lane per block at a time, fixed order
     for (int b = tid; b < B; b += 32) {
@@ -784,6 +834,325 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
   XSTAMP(4);
   if (epilogue_small_ok(a)) epilogue_body_small(a);
   else epilogue_body(a);
+  XSTAMP(9);
+}
+
+// ------------------------------------------------------------------------------------------
+// xchg_epilogue_mc: the same step with the superlevel arithmetic spread over ALL CTAs of the launch.
+//
+// One CTA doing the superlevel step moves ~1.5 MB through a single SM and makes ~10 dependent trips to L2 / HBM (everything small
+// has been evicted by the pass over X that precedes it): 50-65 us inside a fit (scripts/xchg_stamps.py), i.e. 15 % of a PLS2
+// trip on an 8-GPU shard.  Here CTA c owns the samples [c * ch, (c + 1) * ch): it forms their split sums (and, between GPUs,
+// their sums over the ranks), keeps block scores, superscore and Y rows of its samples in registers (one sample per thread), and
+// the five sums over all samples -- T'u, |ts|, {diff_t, ts'ts, Y'ts}, |u|, u'u -- are grid-wide reductions: every CTA writes its
+// partial into `work` and releases a flag, every CTA acquires all G flags (all CTAs are resident) and adds the G partials in
+// the same fixed order, so all of them -- and all GPUs -- continue from bit-identical scalars.
+// Dense data, B <= 8, q <= 16, ch <= 1024 (n <= 1024 * CTAs); everything else takes xchg_epilogue_kernel.
+// ------------------------------------------------------------------------------------------
+#define XMC_W 32       // doubles per (phase, CTA) slot of the work buffer
+#define XMC_GMAX 160   // slots per phase
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Grid-wide sum of NV values per CTA (all CTAs of the launch are resident).  Thread 0 writes this CTA's partials into its slot
+// of `work` and then RELEASES the launch's epoch into its flag word; thread g < G ACQUIRES CTA g's flag (one poll per CTA, all
+// in flight at once: no atomics, no arrival counter, no generation word -- the first version, an atomic-counter barrier, cost
+// ~6 us per sum, four dependent L2 round trips); after the CTA barrier warp k adds value k over the CTAs -- lanes take CTAs
+// lane, lane + 32, ... in order, then the fixed shuffle tree -- so every CTA ends up with identical bits in s_out[0 .. NV).
+// Flags only ever grow (epoch = number of the launch within the fit), one flag array per phase.
+template <int NV>
+__device__ __forceinline__ void grid_sum(double (&v)[NV], double* scratch, double* s_out, double* work, int phase,
+                                         const mbpls_xchg_args& x, int G) {
+  block_sum<NV>(v, scratch);
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(work + static_cast<size_t>(6) * XMC_GMAX * XMC_W) + phase * XMC_GMAX;
+  if (threadIdx.x == 0) {
+    double* slot = work + (static_cast<size_t>(phase) * XMC_GMAX + blockIdx.x) * XMC_W;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) slot[k] = v[k];
+    st_release_gpu_u64(flags + blockIdx.x, x.epoch);
+  }
+  if (threadIdx.x < G) {
+    while (ld_acquire_gpu_u64(flags + threadIdx.x) < x.epoch) {
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < NV) {
+    const double* base = work + static_cast<size_t>(phase) * XMC_GMAX * XMC_W + warp;
+    double t = 0.0;
+    for (int g = lane; g < G; g += 32) t += __ldcg(base + static_cast<size_t>(g) * XMC_W);
+    t = warp_sum(t);
+    if (lane == 0) s_out[warp] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) xchg_epilogue_mc_kernel(mbpls_xchg_args x) {
+  const mbpls_epilogue_args& a = x.epi;
+  if (a.ctrl[MBPLS_CTRL_DONE]) return;
+  __shared__ double s_part[1024];
+  __shared__ double scratch[32 * 19];
+  __shared__ double s_tot[32];
+  __shared__ double s_norm[8], s_a[8], s_v[16];
+  __shared__ double s_ext[64];
+  __shared__ int s_flag;
+  const int n = a.n, B = a.B, q = a.q;
+  const long ldt = a.ldt;
+  const int tid = threadIdx.x, G = gridDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool multi = x.world > 1;
+  const int ch = x.ch;                              // samples per CTA, a multiple of 32
+  const int i0 = blockIdx.x * ch;
+  const long norm_off = static_cast<long>(B) * ldt;  // B squared norms behind the B x ldt sums
+  double* mine = multi ? reinterpret_cast<double*>(x.peer_bufs[x.rank]) + (x.seq & 1ull) * x.slot_elems : const_cast<double*>(a.red);
+  double* red = const_cast<double*>(a.red);
+  XSTAMP(0);
+
+  // ---- A: split partials of this CTA's samples -> sums (tpi warps per item, see xchg_epilogue_kernel)
+  {
+    const int tpi = x.tpi > 1 ? x.tpi : 1;
+    const int ipc = 1024 / tpi;
+    const int sub = warp % tpi, l0 = (warp / tpi) * 32 + lane;
+    const int nloc = B * ch;  // local items: block b, local sample il
+    for (int base = 0; base < nloc; base += ipc) {
+      const int l = base + l0;
+      const int b = l / ch, il = l - b * ch, i = i0 + il;
+      double acc = 0.0;
+      const bool live = l < nloc && i < n;
+      if (live) {
+        const int s0 = x.block_split_off[b], s1 = x.block_split_off[b + 1];
+        for (int sp = s0 + sub; sp < s1; sp += tpi) acc += x.Tnum[static_cast<size_t>(sp) * x.ldp + i];
+      }
+      if (tpi == 1) {
+        if (live) mine[static_cast<size_t>(b) * ldt + i] = acc;
+      } else {
+        s_part[sub * ipc + l0] = acc;
+        __syncthreads();
+        if (tid < ipc) {
+          const int l2 = base + tid;
+          const int b2 = l2 / ch, i2 = i0 + (l2 - b2 * ch);
+          if (l2 < nloc && i2 < n) {
+            double t = 0.0;
+            for (int k = 0; k < tpi; ++k) t += s_part[k * ipc + tid];
+            mine[static_cast<size_t>(b2) * ldt + i2] = t;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // squared block-weight norms of this rank: warp b adds the parts lane, lane + 32, ... in order, then the shuffle tree.
+  // Single GPU: every CTA forms them (identical bits); several GPUs: CTA 0 publishes this rank's, every CTA adds the ranks'.
+  if (warp < B && (!multi || blockIdx.x == 0)) {
+    double t = 0.0;
+    for (int c = lane; c < x.n_norm_parts; c += 32) t += x.norm_part[static_cast<size_t>(c) * B + warp];
+    t = warp_sum(t);
+    if (lane == 0) {
+      if (multi) mine[norm_off + warp] = t;
+      else s_ext[warp] = t;
+    }
+  }
+  XSTAMP(1);
+  if (multi) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned old = atomicAdd(&x.counters[0], 1u);
+      if (old == static_cast<unsigned>(G) - 1u) {  // all CTAs of this rank have written their sums: publish
+        x.counters[0] = 0u;
+        __threadfence_system();
+        for (int r = 0; r < x.world; ++r) {
+          unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[r]) + x.flags_off);
+          st_release_sys_u64(flags + x.rank, x.seq);
+        }
+      }
+      const unsigned long long* myflags =
+          reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[x.rank]) + x.flags_off);
+      const unsigned long long t0 = global_timer_ns();
+      int ok = 1;
+      for (int r = 0; r < x.world && ok; ++r) {
+        while (ld_acquire_sys_u64(myflags + r) < x.seq) {
+          if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) {
+            ok = 0;
+            break;
+          }
+        }
+      }
+      if (!ok) a.ctrl[MBPLS_CTRL_ERROR] = 1;  // a peer never arrived: the host raises; keep going so the grid barriers stay matched
+      s_flag = ok;
+    }
+    __syncthreads();
+    XSTAMP(2);
+    const size_t slot = (x.seq & 1ull) * x.slot_elems;
+    for (int l = tid; l < B * ch; l += 1024) {  // sums over the ranks, in rank order, of this CTA's items
+      const int b = l / ch, i = i0 + (l - b * ch);
+      if (i < n) {
+        const size_t off = static_cast<size_t>(b) * ldt + i;
+        double acc = 0.0;
+        for (int r = 0; r < x.world; ++r) acc += __ldcv(reinterpret_cast<const double*>(x.peer_bufs[r]) + slot + off);
+        red[off] = acc;
+      }
+    }
+    if (tid < B) {
+      double acc = 0.0;
+      for (int r = 0; r < x.world; ++r) acc += __ldcv(reinterpret_cast<const double*>(x.peer_bufs[r]) + slot + norm_off + tid);
+      s_ext[tid] = acc;
+      if (blockIdx.x == 0) red[norm_off + tid] = acc;
+    }
+  }
+  __syncthreads();
+  if (!multi && blockIdx.x == 0 && tid < B) red[norm_off + tid] = s_ext[tid];  // record_component reads the norms from red
+  if (tid < B) s_norm[tid] = sqrt(s_ext[tid]);
+  __syncthreads();
+  XSTAMP(3);
+  XSTAMP(4);
+
+  // ---- C: superlevel step; thread tid < ch owns sample i0 + tid
+  const int i = i0 + tid;
+  const bool own = tid < ch && i < n;
+  const double uu = a.scal[MBPLS_SCAL_UU];
+  double tb[8], yv[16];
+  double ui = 0.0, old = 0.0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) tb[b] = (own && b < B) ? __ldcg(red + static_cast<size_t>(b) * ldt + i) : 0.0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) yv[c] = (own && c < q) ? a.Yt[static_cast<size_t>(c) * ldt + i] : 0.0;
+  if (own) {
+    ui = a.u[i];
+    old = a.ts_old[i];
+  }
+  // phase 1: block scores t_b (:862-875) and T'u (:879)
+  double ab[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    ab[b] = 0.0;
+    if (b < B) {
+      const UniformDivisor by_nb(s_norm[b]);
+      const double t = own ? by_nb(tb[b]) : 0.0;
+      tb[b] = t;
+      if (own) a.T[static_cast<size_t>(b) * ldt + i] = t;
+      ab[b] = t * ui;
+    }
+  }
+  grid_sum<8>(ab, scratch, s_tot, x.work, 0, x, G);
+  XSTAMP(5);
+  if (tid == 0) {  // superweights to unit length (:880)
+    double sq = 0.0;
+    for (int b = 0; b < B; ++b) {
+      s_a[b] = s_tot[b] / uu;
+      sq = fma(s_a[b], s_a[b], sq);
+    }
+    sq = sqrt(sq);
+    for (int b = 0; b < B; ++b) {
+      s_a[b] /= sq;
+      if (blockIdx.x == 0) a.a[b] = s_a[b];
+    }
+  }
+  __syncthreads();
+  // phase 2: superscore ts = T a, normalised (:882-883)
+  double ts = 0.0;
+  for (int b = 0; b < B; ++b) ts = fma(tb[b], s_a[b], ts);
+  double one[1] = {ts * ts};
+  grid_sum<1>(one, scratch, s_tot, x.work, 1, x, G);
+  const double tsn = sqrt(s_tot[0]);
+  __syncthreads();
+  // phase 3 + 4: normalise, convergence metric against ts_old (:884-888), ts'ts, Y'ts (:899)
+  const UniformDivisor by_tsn(tsn);
+  const double t = own ? by_tsn(ts) : 0.0;
+  const double d = own ? old - t : 0.0;
+  if (own) {
+    a.ts[i] = t;
+    a.ts_old[i] = t;
+  }
+  {
+    double dmax = warp_max(fabs(d));
+    double dmin = warp_min(own ? fabs(d) : INFINITY);
+    __syncthreads();
+    if (lane == 0) {
+      s_part[warp] = dmax;
+      s_part[32 + warp] = dmin;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double mx = 0.0, mn = INFINITY;
+      for (int wv = 0; wv < 32; ++wv) {
+        mx = fmax(mx, s_part[wv]);
+        mn = fmin(mn, s_part[32 + wv]);
+      }
+      double* slot = x.work + (static_cast<size_t>(5) * XMC_GMAX + blockIdx.x) * XMC_W;
+      slot[0] = mx;
+      slot[1] = mn;
+    }
+  }
+  double v19[19];
+  v19[0] = d * d;
+  v19[1] = fabs(d);
+  v19[2] = t * t;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v19[3 + c] = yv[c] * t;
+  grid_sum<19>(v19, scratch, s_tot, x.work, 2, x, G);
+  XSTAMP(6);
+  const double tt = s_tot[2];
+  if (tid == 0) {
+    double mx = 0.0, mn = INFINITY;
+    for (int g = 0; g < G; ++g) {
+      const double* slot = x.work + (static_cast<size_t>(5) * XMC_GMAX + g) * XMC_W;
+      mx = fmax(mx, __ldcg(slot));
+      mn = fmin(mn, __ldcg(slot + 1));
+    }
+    double diff;
+    switch (a.norm_kind) {
+      case MBPLS_NORM_L1: diff = s_tot[1]; break;
+      case MBPLS_NORM_MAX: diff = mx; break;
+      case MBPLS_NORM_MIN: diff = mn; break;
+      default: diff = sqrt(s_tot[0]);
+    }
+    s_ext[32] = diff;
+    double sq = 0.0;
+    for (int c = 0; c < q; ++c) {
+      s_v[c] = s_tot[3 + c] / tt;
+      sq = fma(s_v[c], s_v[c], sq);
+      if (blockIdx.x == 0) a.v[c] = s_v[c];
+    }
+    s_ext[33] = sq;
+  }
+  __syncthreads();
+  const double vv = s_ext[33];
+  XSTAMP(7);
+  // phase 5: Y scores u = Y v / v'v, normalised (:911-913)
+  const UniformDivisor by_vv(vv);
+  double un = 0.0;
+  for (int c = 0; c < q; ++c) un = fma(yv[c], s_v[c], un);
+  const double uval = own ? by_vv(un) : 0.0;
+  double one2[1] = {uval * uval};
+  grid_sum<1>(one2, scratch, s_tot, x.work, 3, x, G);
+  const double unorm = sqrt(s_tot[0]);
+  __syncthreads();
+  const UniformDivisor by_un(unorm);
+  const double unew = own ? by_un(uval) : 0.0;
+  if (own) a.u[i] = unew;
+  double one3[1] = {unew * unew};
+  grid_sum<1>(one3, scratch, s_tot, x.work, 4, x, G);
+  if (blockIdx.x == 0 && tid == 0) {
+    int* ctrl = a.ctrl;
+    const int trips = ctrl[MBPLS_CTRL_TRIPS] + 1;
+    ctrl[MBPLS_CTRL_TRIPS] = trips;
+    a.scal[MBPLS_SCAL_UU] = s_tot[0];
+    a.scal[MBPLS_SCAL_TT] = tt;
+    a.scal[MBPLS_SCAL_VV] = vv;
+    if (trips > 1) {  // the first trip has nothing to compare with (:884-885)
+      a.scal[MBPLS_SCAL_DIFF] = s_ext[32];
+      if (!(s_ext[32] > a.max_tol)) ctrl[MBPLS_CTRL_DONE] = 1;
+    }
+    if (a.diff_trace && trips <= a.diff_trace_len) a.diff_trace[trips - 1] = trips > 1 ? s_ext[32] : 1.0;
+  }
   XSTAMP(9);
 }
 
@@ -1343,14 +1712,46 @@ int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* x, int ctas, void* str
                        x->flags_off < 2 * x->slot_elems))
     return MBPLS_ERR_ARG;
   // every CTA must be resident at once (B spins on flags): at most one CTA per SM
-  int g = ctas > 0 ? ctas : 32;
-  if (g > num_sms()) g = num_sms();
+  int gmax = ctas > 0 ? ctas : 96;
+  if (gmax > num_sms()) gmax = num_sms();
   const long items = static_cast<long>(args->nanmode ? 2 : 1) * args->B * args->n;
-  const int need = static_cast<int>((items + 1023) / 1024);
-  if (g > need) g = need < 1 ? 1 : need;
-  xchg_epilogue_kernel<<<g, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*x);
+  mbpls_xchg_args xa = *x;
+  int tpi = 1;  // warps per item: as many as keep the grid within gmax CTAs (a pure function of the shapes: reproducible sums)
+  while (tpi < 32 && items * (2 * tpi) <= static_cast<long>(gmax) * 1024) tpi *= 2;
+  xa.tpi = tpi;
+  const long need = (items * tpi + 1023) / 1024;
+  const int g = need < 1 ? 1 : (need > gmax ? gmax : static_cast<int>(need));
+  static const bool mc_off = getenv("MBPLS_XCHG_MC") && atoi(getenv("MBPLS_XCHG_MC")) == 0;
+  if (x->work && x->epoch > 0 && !mc_off && !args->nanmode && args->B <= 8 && args->q <= 16 && gmax <= XMC_GMAX && args->n >= 1) {
+    // superlevel step on all CTAs: ch samples per CTA (a multiple of 32), one sample per thread
+    int ch = (args->n + gmax - 1) / gmax;
+    ch = (ch + 31) / 32 * 32;
+    if (ch <= 1024) {
+      const int gm = (args->n + ch - 1) / ch;
+      int t2 = 1;
+      while (t2 < 32 && static_cast<long>(args->B) * ch * (2 * t2) <= 1024) t2 *= 2;
+      xa.tpi = t2;
+      xa.ch = ch;
+      xchg_epilogue_mc_kernel<<<gm, 1024, 0, static_cast<cudaStream_t>(stream)>>>(xa);
+      MBPLS_RETURN_LAST();
+    }
+  }
+  xchg_epilogue_kernel<<<g, 1024, 0, static_cast<cudaStream_t>(stream)>>>(xa);
   MBPLS_RETURN_LAST();
 }
+
+#ifdef MBPLS_XCHG_STAMPS
+/* probe builds only (scripts/xchg_stamps.py): the phase timestamps of the most recent xchg_epilogue_kernel launch */
+int mbpls_debug_xchg_stamps(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_xchg_stamps, 16 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long zero[16] = {};
+    cudaMemcpyToSymbol(g_xchg_stamps, zero, sizeof(zero));
+  }
+  return 0;
+}
+#endif
 
 int mbpls_nipals_record_component_f64(const mbpls_record_args* args, void* stream) {
   if (!args) return MBPLS_ERR_ARG;

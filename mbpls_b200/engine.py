@@ -613,13 +613,15 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
     res.exchange = None if group is None else ("peer-memory kernel (NVLink loads, sums in rank order)" if px is not None
                                                else "ncclAllReduce")
     xcount = buf(2, dtype=torch.int32, zero=True)
+    xwork = buf(32768, zero=True)  # grid-wide sums of the superlevel step when it runs on all CTAs of the exchange kernel
+    xepoch = [0]
 
     def xchg_args(Tn, Td, ldp, bso_dev, npart_t, nparts_):
         return _cabi.XchgArgs(epi=epi, Tnum=Tn.data_ptr(), Tden=Td.data_ptr() if Td is not None else None, ldp=ldp,
                               block_split_off=bso_dev.data_ptr(), norm_part=npart_t.data_ptr(), n_norm_parts=nparts_,
                               world=px.world if px else 1, rank=px.rank if px else 0, peer_bufs=px.peer_bufs if px else None,
                               slot_elems=px.slot_elems if px else 0, flags_off=px.flags_off if px else 0, seq=0,
-                              counters=xcount.data_ptr())
+                              counters=xcount.data_ptr(), work=xwork.data_ptr())
 
     x_tp = xchg_args(Tnum, Tden, ld, sbso, norm_part, nparts) if fused_epi else None
     x_op = xchg_args(Tnum_o, Tden_o, ld, osbso, norm_part_o, nsplit_o) if (fused_epi and use_op) else None
@@ -630,6 +632,8 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
             if px is not None:
                 px.seq += 1
                 xa.seq = px.seq
+            xepoch[0] += 1
+            xa.epoch = xepoch[0]
             timed("xchg", lambda: call("mbpls_nipals_xchg_epilogue_f64", C.byref(xa), 0, st))
             return
         call("mbpls_nipals_reduce_partials_f64", ptr(Tn), ptr(Td), ld, n, B, ptr(bso_dev), ptr(npart_t), nparts_,
@@ -708,7 +712,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         last = (k == K - 1)
         fuse = fuse_next_xtu and not last
         # dense fits on the one-pass kernels close every component but the last speculatively (see close_fused)
-        speculate = use_opd and not nan and not (last and not deflate_last)
+        speculate = use_opd and not nan and not (last and not deflate_last) and os.environ.get("MBPLS_SPECULATE", "1") != "0"
         launched = 0
         batch, prev_diff = trips_per_sync, None
         closed = False

@@ -120,6 +120,8 @@ def test_standardize_kernel_matches_sklearn_semantics():
     for n in (57, 1500, 2049):
         X = rng.standard_normal((n, 40)) * rng.uniform(0.1, 30, 40) + rng.uniform(-4, 4, 40)
         X[:, 5] = 1.25
+        X[:, 6] *= 1e-90   # scales far from 1: the quotients stay ordinary numbers
+        X[:, 7] *= 1e+120
         X[rng.random(X.shape) < 0.07] = np.nan
         ref = OracleScaler().fit(X)
         for mode in (0, 1, 2):
@@ -134,6 +136,12 @@ def test_standardize_kernel_matches_sklearn_semantics():
             Z = Xt[:, :n].cpu().numpy().T
             assert np.allclose(Z, ref.transform(X), rtol=1e-12, atol=1e-14, equal_nan=True)
             assert bool((Xt[:, n:] == 0).all())
+            # the kernels divide by the scale through a reciprocal + FMA correction (csrc/common.cuh UniformDivisor), which is
+            # claimed to be the correctly rounded quotient: with the device's own statistics numpy's true division must give
+            # the same bits (also for the tiny / huge scales of columns 6 and 7)
+            m_d, s_d = st.mean[:40].cpu().numpy(), st.scale[:40].cpu().numpy()
+            want = (X - m_d) / s_d
+            assert np.array_equal(np.nan_to_num(Z, nan=-7.0), np.nan_to_num(want, nan=-7.0))
 
 
 def test_ingest_layouts_and_roundtrip():
