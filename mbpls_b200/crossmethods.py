@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -136,19 +137,20 @@ def _bip_corrected(a, sizes):
 
 def _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb, Tb, lazy_extra=None):
     """Register lazily materialised attributes shared by the three methods."""
+    mw = weakref.proxy(model)  # the closures below must not keep the model alive (model -> _lazy -> closure -> model)
     B = len(shard.sizes)
     lazy = {
-        "Ts_": lambda: model._gather_samples(Ts, n),
-        "U_": lambda: model._gather_samples(U, n) if U is not None else np.empty((n, 0)),
+        "Ts_": lambda: mw._gather_samples(Ts, n),
+        "U_": lambda: mw._gather_samples(U, n) if U is not None else np.empty((n, 0)),
         "V_": lambda: E.to_host(V, transpose=True),
-        "P_": lambda: model._features_T(P, shard, True),
-        "R_": lambda: model._features_T(R, shard, False),
-        "beta_": lambda: model._features_T(beta, shard, False),
+        "P_": lambda: mw._features_T(P, shard, True),
+        "R_": lambda: mw._features_T(R, shard, False),
+        "beta_": lambda: mw._features_T(beta, shard, False),
     }
     if Wb is not None:
-        lazy["W_"] = lambda: model._features_T(Wb, shard, True)
+        lazy["W_"] = lambda: mw._features_T(Wb, shard, True)
     if Tb is not None:
-        lazy["T_"] = lambda: [model._gather_samples(Tb[b], n) for b in range(B)]
+        lazy["T_"] = lambda: [mw._gather_samples(Tb[b], n) for b in range(B)]
     if lazy_extra:
         lazy.update(lazy_extra)
     model.__dict__["_lazy"] = lazy
@@ -169,6 +171,7 @@ def fit(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device):
 
 # ---- SIMPLS (mbpls.py:995-1048) ------------------------------------------------------------------
 def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
+    mw = weakref.proxy(model)
     warnings.warn("Method 'SIMPLS' does not calculate A_ and T_!")  # :996
     K, B = int(model.n_components), len(shard.sizes)
     p, ld = Xt.shape
@@ -211,7 +214,7 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
     model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
     model.W_concat_ = np.empty((shard.p_global, 0))
     _finish_common(model, shard, n, q, R, beta, P, Tm, U, Q, None, None,
-                   {"W_": lambda: model._features_T(W, shard, False)})
+                   {"W_": lambda: mw._features_T(W, shard, False)})
 
 
 # ---- UNIPALS (mbpls.py:384-574) ------------------------------------------------------------------
@@ -437,6 +440,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
     """rows_group: the SAMPLE axis is sharded over this group (Xt / Yt hold this rank's n rows of all features);
     sums over samples are all-reduced (p x p + p x q partial cross-products), everything indexed by
     features is replicated, everything indexed by samples stays row-local."""
+    mw = weakref.proxy(model)
     K, B = int(model.n_components), len(shard.sizes)
     p, ld = Xt.shape
     pg = shard.p_global
@@ -567,10 +571,10 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
     model.explained_var_x_, model.explained_var_y_, model.explained_var_xblocks_ = evx, evy, evxb
     model.W_non_normal_ = [np.empty((s, 0)) for s in shard.sizes]
     Wc_keep = Wc
-    extra = {"W_concat_": lambda: model._features_T(Wc_keep, shard, False)}
+    extra = {"W_concat_": lambda: mw._features_T(Wc_keep, shard, False)}
     if not calc_all:
         extra["W_"] = lambda: [np.empty((s, 0)) for s in shard.sizes]
         extra["T_"] = lambda: [np.empty((ng, 0)) for _ in shard.sizes]
-        extra["U_"] = (lambda: np.empty((ng, 0))) if ng >= pg else (lambda: model._gather_samples(U, n))
+        extra["U_"] = (lambda: np.empty((ng, 0))) if ng >= pg else (lambda: mw._gather_samples(U, n))
     _finish_common(model, shard, n, q, R, beta, P, Ts, U, V, Wb if calc_all else None, Tb, extra)
     model.__dict__["_cv_weights"] = Wc  # prefix models: R_k = W_k pinv(P_k'W_k) (the column scaling of P_ / V_ cancels in beta)

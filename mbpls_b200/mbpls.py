@@ -15,6 +15,7 @@ and ``get_params`` behave identically): ``n_iter_`` (NIPALS trips per component)
 from __future__ import annotations
 
 import warnings
+import weakref
 from typing import List, Optional
 
 import numpy as np
@@ -619,14 +620,15 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         use them there) and are gathered into scikit-learn StandardScaler objects on first access (32 MB of D2H per
         million features that a fit should not wait for)."""
         box = {}
+        me = weakref.proxy(self)  # no cycle self -> _lazy -> closure -> self: an unmaterialised model frees its device buffers at once
 
         def build():
             if not box:
-                mean = self._gather_features(xs.mean.view(1, -1), shard)[0]
-                var = self._gather_features(xs.var.view(1, -1), shard)[0]
-                scale = self._gather_features(xs.scale.view(1, -1), shard)[0]
-                seen = self._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
-                bounds = self._feature_bounds(shard)
+                mean = me._gather_features(xs.mean.view(1, -1), shard)[0]
+                var = me._gather_features(xs.var.view(1, -1), shard)[0]
+                scale = me._gather_features(xs.scale.view(1, -1), shard)[0]
+                seen = me._gather_features(xs.seen.view(1, -1).to(F64), shard)[0].astype(np.int64)
+                bounds = me._feature_bounds(shard)
                 box["x"] = [_make_scaler(mean[a:b], var[a:b], scale[a:b], seen[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
                 box["y"] = _make_scaler(ys.mean[:q].cpu().numpy(), ys.var[:q].cpu().numpy(), ys.scale[:q].cpu().numpy(),
                                         ys.seen[:q].cpu().numpy())
@@ -702,16 +704,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
             self.A_corrected_ = np.empty((B, 0))
         self.W_concat_ = np.empty((shard.p_global, 0))
 
+        me = weakref.proxy(self)  # (see _lazy_scalers)
         lazy = {
             "Ts_": lambda: E.to_host(res.Ts[:, :n], transpose=True),
             "U_": lambda: E.to_host(res.U[:, :n], transpose=True),
             "V_": lambda: E.to_host(res.V[:, :q], transpose=True),
             "T_": lambda: [E.to_host(res.Tb[b, :, :n], transpose=True) for b in range(B)],
-            "W_": lambda: self._features_T(res.W, shard, True),
-            "W_non_normal_": lambda: self._features_T(res.Wt, shard, True),
-            "P_": lambda: self._features_T(res.P, shard, True),
-            "R_": lambda: self._features_T(R, shard, False),
-            "beta_": lambda: self._features_T(beta, shard, False),
+            "W_": lambda: me._features_T(res.W, shard, True),
+            "W_non_normal_": lambda: me._features_T(res.Wt, shard, True),
+            "P_": lambda: me._features_T(res.P, shard, True),
+            "R_": lambda: me._features_T(R, shard, False),
+            "beta_": lambda: me._features_T(beta, shard, False),
         }
         self.__dict__["_lazy"] = lazy
 
