@@ -108,7 +108,8 @@ __device__ __forceinline__ double block_sum1(double x, double* scratch) {
 //     q0 = RN(a r);   e = a - b q0  (exact, one FMA);   q = RN(q0 + e r)  ==  RN(a / b)
 // (q0 is within an ulp of a/b because r is correctly rounded; the FMA residual is exact; the final FMA rounds once.)  The
 // result is bit-identical to `a / b`, so nothing downstream -- trip counts included -- can tell the difference.  Quotients that
-// are zero, denormal-range, huge or not finite, and divisors far from 1 in magnitude, take the ordinary division.
+// are zero, denormal-range, huge or infinite, and divisors far from 1 in magnitude, take the ordinary division (NaN stays NaN
+// on the fast path: in NaN mode every warp holds missing values, and sending them to the slow path made every warp run both).
 struct UniformDivisor {
   double b, r;
   bool fast;
@@ -121,7 +122,7 @@ struct UniformDivisor {
       const double q0 = a * r;
       const double q = fma(fma(-q0, b, a), r, q0);
       const double aq = fabs(q);
-      if (aq >= 0x1p-700 && aq <= 0x1p700) return q;
+      if (!(aq < 0x1p-700) && !(aq > 0x1p700)) return q;  // ordinary quotient -- or NaN (a missing value stays on the fast path)
     }
     return a / b;
   }

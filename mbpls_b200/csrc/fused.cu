@@ -86,7 +86,6 @@ struct Cfg {
   static constexpr int kTG = TG, EPTC = EPTC_, CPF = CPF_, S = S_;
   static constexpr int G = 512 / TG, EPT = EPTC_ * CPF_, NW = TG / 32;
   static constexpr int UC = TG * EPTC_;  // units per (full) chunk
-  static constexpr int MAX_UNITS = UC * CPF_;
 };
 
 // fixed-order sum over the TG threads of one worker; `buf` holds NV*NW doubles and must alternate between

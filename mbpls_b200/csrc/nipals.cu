@@ -841,13 +841,16 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_kernel(mbpls_xchg_args x) 
 // xchg_epilogue_mc: the same step with the superlevel arithmetic spread over ALL CTAs of the launch.
 //
 // One CTA doing the superlevel step moves ~1.5 MB through a single SM and makes ~10 dependent trips to L2 / HBM (everything small
-// has been evicted by the pass over X that precedes it): 50-65 us inside a fit (scripts/xchg_stamps.py), i.e. 15 % of a PLS2
-// trip on an 8-GPU shard.  Here CTA c owns the samples [c * ch, (c + 1) * ch): it forms their split sums (and, between GPUs,
-// their sums over the ranks), keeps block scores, superscore and Y rows of its samples in registers (one sample per thread), and
+// has been evicted by the pass over X that precedes it): 50-65 us inside a fit (scripts/xchg_stamps.py).  Here CTA c owns the
+// samples [c * ch, (c + 1) * ch): it forms their split sums,
+// keeps block scores, superscore and Y rows of its samples in registers (one sample per thread), and
 // the five sums over all samples -- T'u, |ts|, {diff_t, ts'ts, Y'ts}, |u|, u'u -- are grid-wide reductions: every CTA writes its
 // partial into `work` and releases a flag, every CTA acquires all G flags (all CTAs are resident) and adds the G partials in
 // the same fixed order, so all of them -- and all GPUs -- continue from bit-identical scalars.
-// Dense data, B <= 8, q <= 16, ch <= 1024 (n <= 1024 * CTAs); everything else takes xchg_epilogue_kernel.
+// Each grid-wide sum costs ~5 us (release, acquire and read are three trips to L2), so the step takes 50 instead of 65 us
+// (PLS2 trip of 8 blocks, n = 2,000: 85 instead of 99 us for the whole launch).  Single GPU, dense data, B <= 8, q <= 16,
+// ch <= 1024 (n <= 1024 * CTAs); everything else takes xchg_epilogue_kernel -- between GPUs the launch is dominated by the wait
+// for the slowest rank's trip kernel and the two forms measured the same (2 GPUs: 109.4 vs 108.6 ms per fit).
 // ------------------------------------------------------------------------------------------
 #define XMC_W 32       // doubles per (phase, CTA) slot of the work buffer
 #define XMC_GMAX 160   // slots per phase
@@ -902,17 +905,15 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_mc_kernel(mbpls_xchg_args 
   __shared__ double s_tot[32];
   __shared__ double s_norm[8], s_a[8], s_v[16];
   __shared__ double s_ext[64];
-  __shared__ int s_flag;
   const int n = a.n, B = a.B, q = a.q;
   const long ldt = a.ldt;
   const int tid = threadIdx.x, G = gridDim.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const bool multi = x.world > 1;
   const int ch = x.ch;                              // samples per CTA, a multiple of 32
   const int i0 = blockIdx.x * ch;
   const long norm_off = static_cast<long>(B) * ldt;  // B squared norms behind the B x ldt sums
-  double* mine = multi ? reinterpret_cast<double*>(x.peer_bufs[x.rank]) + (x.seq & 1ull) * x.slot_elems : const_cast<double*>(a.red);
   double* red = const_cast<double*>(a.red);
+  double* mine = red;  // (single GPU: the sums go straight into red)
   XSTAMP(0);
 
   // ---- A: split partials of this CTA's samples -> sums (tpi warps per item, see xchg_epilogue_kernel)
@@ -948,67 +949,17 @@ __global__ void __launch_bounds__(1024) xchg_epilogue_mc_kernel(mbpls_xchg_args 
       }
     }
   }
-  // squared block-weight norms of this rank: warp b adds the parts lane, lane + 32, ... in order, then the shuffle tree.
-  // Single GPU: every CTA forms them (identical bits); several GPUs: CTA 0 publishes this rank's, every CTA adds the ranks'.
-  if (warp < B && (!multi || blockIdx.x == 0)) {
+  // squared block-weight norms: warp b adds the parts lane, lane + 32, ... in order, then the shuffle tree; every CTA forms
+  // them (identical bits everywhere)
+  if (warp < B) {
     double t = 0.0;
     for (int c = lane; c < x.n_norm_parts; c += 32) t += x.norm_part[static_cast<size_t>(c) * B + warp];
     t = warp_sum(t);
-    if (lane == 0) {
-      if (multi) mine[norm_off + warp] = t;
-      else s_ext[warp] = t;
-    }
+    if (lane == 0) s_ext[warp] = t;
   }
   XSTAMP(1);
-  if (multi) {
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned old = atomicAdd(&x.counters[0], 1u);
-      if (old == static_cast<unsigned>(G) - 1u) {  // all CTAs of this rank have written their sums: publish
-        x.counters[0] = 0u;
-        __threadfence_system();
-        for (int r = 0; r < x.world; ++r) {
-          unsigned long long* flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[r]) + x.flags_off);
-          st_release_sys_u64(flags + x.rank, x.seq);
-        }
-      }
-      const unsigned long long* myflags =
-          reinterpret_cast<const unsigned long long*>(reinterpret_cast<double*>(x.peer_bufs[x.rank]) + x.flags_off);
-      const unsigned long long t0 = global_timer_ns();
-      int ok = 1;
-      for (int r = 0; r < x.world && ok; ++r) {
-        while (ld_acquire_sys_u64(myflags + r) < x.seq) {
-          if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) {
-            ok = 0;
-            break;
-          }
-        }
-      }
-      if (!ok) a.ctrl[MBPLS_CTRL_ERROR] = 1;  // a peer never arrived: the host raises; keep going so the grid barriers stay matched
-      s_flag = ok;
-    }
-    __syncthreads();
-    XSTAMP(2);
-    const size_t slot = (x.seq & 1ull) * x.slot_elems;
-    for (int l = tid; l < B * ch; l += 1024) {  // sums over the ranks, in rank order, of this CTA's items
-      const int b = l / ch, i = i0 + (l - b * ch);
-      if (i < n) {
-        const size_t off = static_cast<size_t>(b) * ldt + i;
-        double acc = 0.0;
-        for (int r = 0; r < x.world; ++r) acc += __ldcv(reinterpret_cast<const double*>(x.peer_bufs[r]) + slot + off);
-        red[off] = acc;
-      }
-    }
-    if (tid < B) {
-      double acc = 0.0;
-      for (int r = 0; r < x.world; ++r) acc += __ldcv(reinterpret_cast<const double*>(x.peer_bufs[r]) + slot + norm_off + tid);
-      s_ext[tid] = acc;
-      if (blockIdx.x == 0) red[norm_off + tid] = acc;
-    }
-  }
   __syncthreads();
-  if (!multi && blockIdx.x == 0 && tid < B) red[norm_off + tid] = s_ext[tid];  // record_component reads the norms from red
+  if (blockIdx.x == 0 && tid < B) red[norm_off + tid] = s_ext[tid];  // record_component reads the norms from red
   if (tid < B) s_norm[tid] = sqrt(s_ext[tid]);
   __syncthreads();
   XSTAMP(3);
@@ -1722,7 +1673,7 @@ int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* x, int ctas, void* str
   const long need = (items * tpi + 1023) / 1024;
   const int g = need < 1 ? 1 : (need > gmax ? gmax : static_cast<int>(need));
   static const bool mc_off = getenv("MBPLS_XCHG_MC") && atoi(getenv("MBPLS_XCHG_MC")) == 0;
-  if (x->work && x->epoch > 0 && !mc_off && !args->nanmode && args->B <= 8 && args->q <= 16 && gmax <= XMC_GMAX && args->n >= 1) {
+  if (x->work && x->epoch > 0 && x->world == 1 && !mc_off && !args->nanmode && args->B <= 8 && args->q <= 16 && gmax <= XMC_GMAX && args->n >= 1) {
     // superlevel step on all CTAs: ch samples per CTA (a multiple of 32), one sample per thread
     int ch = (args->n + gmax - 1) / gmax;
     ch = (ch + 31) / 32 * 32;
