@@ -625,10 +625,13 @@ def run_ours(args):
     for _ in range(max(args.warmup, 0)):
         ms, _m = one_fit()
         log("warmup fit ms", ms, "trips", _m.n_iter_)
+        del _m  # (a model kept alive across the timed steps changes the allocation pattern inside them: the second timed fit then
+        #          goes back to cudaMalloc, which costs 60-90 ms per call once peer mappings exist -- 228 ms instead of 111 at N = 8)
     clocks = Clocks(local) if rank == 0 else None
     profile, times, model = {}, [], None
     launches0 = _cabi.launch_count
     for _ in range(max(args.steps, 1)):
+        model = None  # steady state: the previous step's model is released before the next fit allocates
         ms, model = one_fit(profile)
         times.append(ms)
         log("timed fit ms", ms)
