@@ -178,10 +178,12 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 // ------------------------------------------------------------------------------------------
 #define TALL_TS 2048  // samples per tile = 16 KB per feature chunk
 #define TALL_TR 12    // ring stages (192 KB)
-#define TALL_U 4      // 16-byte units per consumer thread (256 consumer threads x 4 x 2 samples = TS)
+#define TALL_U 2      // 16-byte units per consumer thread (512 consumer threads x 2 x 2 samples = TS)
+#define TALL_NC 512   // consumer threads (16 warps: with 8 warps of 8 samples each the kernel issued on 53 % of the cycles, ncu:
+                      // `wait` / `math_pipe_throttle` with two warps per scheduler), + one producer warp
 
 template <int NC>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(TALL_NC + 32, 1)
 skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ coef, int C,
                    double* __restrict__ out, long ldo, int* __restrict__ flag, int tile_len) {
   // coef: p x 8 doubles, row j = {mean_j (0 without centring), b_0j, b_1j, b_2j, b_3j, -, -, -}: travels through the ring with
@@ -199,13 +201,13 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
   if (tid == 0) {
     for (int s = 0; s < TALL_TR; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 8);
+      mbar_init(&empty[s], TALL_NC / 32);
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == 8) {  // producer: one elected lane issues every bulk copy
+  if (warp == TALL_NC / 32) {  // producer: one elected lane issues every bulk copy
     if (lane == 0) {
       for (long c = 0; c < total; ++c) {
         const int s = static_cast<int>(c % TALL_TR);
@@ -232,9 +234,9 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
     bool live_x[TALL_U], live_y[TALL_U];
 #pragma unroll
     for (int k = 0; k < TALL_U; ++k) {
-      const long i = i0 + 2 * (tid + k * 256);
-      live_x[k] = i < n && (tid + k * 256) < valid_units;
-      live_y[k] = i + 1 < n && (tid + k * 256) < valid_units;
+      const long i = i0 + 2 * (tid + k * TALL_NC);
+      live_x[k] = i < n && (tid + k * TALL_NC) < valid_units;
+      live_y[k] = i + 1 < n && (tid + k * TALL_NC) < valid_units;
     }
     double2 acc[TALL_U][NC];
 #pragma unroll
@@ -248,7 +250,7 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
       const double2* __restrict__ cf = reinterpret_cast<const double2*>(cring + s * 8);
       double2 x[TALL_U];
 #pragma unroll
-      for (int k = 0; k < TALL_U; ++k) x[k] = live_x[k] ? xs[tid + k * 256] : make_double2(0.0, 0.0);
+      for (int k = 0; k < TALL_U; ++k) x[k] = live_x[k] ? xs[tid + k * TALL_NC] : make_double2(0.0, 0.0);
       const double2 c01 = cf[0], c23 = cf[1], c4 = cf[2];  // {mean, b0}, {b1, b2}, {b3, -}
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);  // the chunk sits in registers: hand the stage back
@@ -275,7 +277,7 @@ skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const d
     }
 #pragma unroll
     for (int k = 0; k < TALL_U; ++k) {
-      const long i = i0 + 2 * (tid + k * 256);
+      const long i = i0 + 2 * (tid + k * TALL_NC);
       if (live_x[k]) {
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
@@ -409,7 +411,7 @@ int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const do
 #define TALL_LAUNCH(NCV)                                                                                                   \
   do {                                                                                                                     \
     cudaFuncSetAttribute(skinny_tall_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
-    skinny_tall_kernel<NCV><<<grid, 288, smem, st>>>(Xt, ld, n, p, coef, C, out, ldo, nonfinite_flag, tile_len);           \
+    skinny_tall_kernel<NCV><<<grid, TALL_NC + 32, smem, st>>>(Xt, ld, n, p, coef, C, out, ldo, nonfinite_flag, tile_len);           \
   } while (0)
   if (C > 2) TALL_LAUNCH(4);
   else if (C > 1) TALL_LAUNCH(2);

@@ -836,6 +836,9 @@ def right_multiply(inp: torch.Tensor, p: int, rowscale: Optional[torch.Tensor], 
     return out[:, :p]
 
 
+_SKINNY_SPLITS: dict = {}
+
+
 def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[int], group=None,
                 mean: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
                 flag: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -860,10 +863,17 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
         allreduce_(out, group)
         return out
     if p > 0 and n > 0:
-        f0, f1, _ = make_splits(block_off, n, sm_count(dev))
-        ns = len(f0)
+        # the split table depends on the shapes only: built (two small uploads) once per shape, not once per product --
+        # SIMPLS / UNIPALS make two of these products per component and are bound by the host's launch rate at C2
+        key = (tuple(int(o) for o in block_off), int(n), dev.index)
+        tab = _SKINNY_SPLITS.get(key)
+        if tab is None:
+            f0, f1, _ = make_splits(block_off, n, sm_count(dev))
+            if len(_SKINNY_SPLITS) > 64:
+                _SKINNY_SPLITS.clear()
+            tab = _SKINNY_SPLITS[key] = (len(f0), _i32(f0, dev), _i32(f1, dev))
+        ns, sf0, sf1 = tab
         part = torch.zeros((ns, Cc * ld), dtype=F64, device=dev)
-        sf0, sf1 = _i32(f0, dev), _i32(f1, dev)  # keep alive: ptr() of a temporary would dangle
         call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(sf0), ptr(sf1),
              ns, ptr(part), ld, ptr(mean), ptr(scale), ptr(flag), stream_ptr(dev))
         call("mbpls_reduce_chunks_f64", ptr(part), ns, Cc * ld, ptr(out), stream_ptr(dev))
