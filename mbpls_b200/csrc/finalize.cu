@@ -178,9 +178,9 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 // ------------------------------------------------------------------------------------------
 #define TALL_TS 2048  // samples per tile = 16 KB per feature chunk
 #define TALL_TR 12    // ring stages (192 KB)
-#define TALL_U 2      // 16-byte units per consumer thread (512 consumer threads x 2 x 2 samples = TS)
-#define TALL_NC 512   // consumer threads (16 warps: with 8 warps of 8 samples each the kernel issued on 53 % of the cycles, ncu:
-                      // `wait` / `math_pipe_throttle` with two warps per scheduler), + one producer warp
+#define TALL_U 4      // 16-byte units per consumer thread (256 consumer threads x 4 x 2 samples = TS)
+#define TALL_NC 256   // consumer threads + one producer warp.  (16 consumer warps of 4 samples each: 3.56 instead of 3.16 ms --
+                      // twice the mbarrier waits and coefficient broadcasts per chunk outweigh the extra warps.)
 
 template <int NC>
 __global__ void __launch_bounds__(TALL_NC + 32, 1)
