@@ -128,7 +128,7 @@ __device__ __forceinline__ double obs_factor(unsigned m, int b) {
 // A lane owns one 32-bit mask word = 32 consecutive samples and keeps their 32 sums in registers, so one 4-byte load feeds
 // 32 predicated additions; a warp covers 1024 consecutive samples (its lanes read 128 contiguous bytes of a feature's bit
 // row), the 8 warps of a CTA take every 8th feature of the split and their partials are added in a fixed order.
-__global__ void __launch_bounds__(256, 3) masked_rowden_kernel(const unsigned* __restrict__ bits, long ldw, int n,
+__global__ void __launch_bounds__(256) masked_rowden_kernel(const unsigned* __restrict__ bits, long ldw, int n,
                                                             const double* __restrict__ w, const int* __restrict__ split_f0,
                                                             const int* __restrict__ split_f1, double* __restrict__ Tden, long ldt,
                                                             const int* __restrict__ done) {
