@@ -520,7 +520,7 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
                trips_per_sync: Optional[int] = None, profile: Optional[dict] = None,
                deflate_last: bool = False, one_pass: Optional[bool] = None,
                one_pass_deflate: Optional[bool] = None, col_nan: Optional[torch.Tensor] = None,
-               first_trip: Optional["FirstTrip"] = None) -> NipalsResult:
+               first_trip: Optional["FirstTrip"] = None, p_widest: Optional[int] = None) -> NipalsResult:
     """Multiblock NIPALS on a (local shard of a) feature-major matrix; deflates ``Xt`` in place.
 
     Follows mbpls/mbpls.py:821-983; see csrc/nipals.cu for the per-kernel citations.
@@ -649,7 +649,9 @@ def nipals_fit(Xt: torch.Tensor, Yt: torch.Tensor, n: int, block_off: Sequence[i
         # (the estimate must be the same on every rank -- shard widths differ -- or the ranks would enqueue different
         # numbers of per-trip all-reduces before the readback: use the widest shard)
         p_est = p
-        if group is not None:
+        if p_widest is not None:  # the caller knows the shard map: no collective, no host synchronisation
+            p_est = int(p_widest)
+        elif group is not None:
             import torch.distributed as dist
             pw = torch.tensor([p], dtype=torch.int64, device=dev)
             dist.all_reduce(pw, op=dist.ReduceOp.MAX, group=group)

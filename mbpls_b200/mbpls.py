@@ -389,11 +389,11 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                     prof.setdefault("standardize", []).append(ev)
                 if not sparse:
                     # NaN shows up as seen < n, +-inf as a non-finite column mean / variance: no extra pass over X
+                    # (one flag on the device, one read-back -- or none: between GPUs the flag itself is all-reduced)
                     pl = shard.p_local
-                    ok = bool((xs.seen[:pl] == n).all()) and bool(torch.isfinite(xs.mean[:pl]).all()) \
-                        and bool(torch.isfinite(xs.var[:pl]).all()) and bool((ys.seen[:q] == n).all()) \
-                        and bool(torch.isfinite(ys.mean[:q]).all()) and bool(torch.isfinite(ys.var[:q]).all())
-                    self._raise_if_any_rank(not ok, "Input contains NaN or infinity.", group)
+                    ok = (xs.seen[:pl] == n).all() & torch.isfinite(xs.mean[:pl]).all() & torch.isfinite(xs.var[:pl]).all() \
+                        & (ys.seen[:q] == n).all() & torch.isfinite(ys.mean[:q]).all() & torch.isfinite(ys.var[:q]).all()
+                    self._raise_if_any_rank(~ok, "Input contains NaN or infinity.", group)
                 pre_lazy = self._lazy_scalers(xs, ys, shard, q)
                 zss = xs.zss
                 self.__dict__["_dev_scalers"] = (xs.mean[:shard.p_local], xs.scale[:shard.p_local], ys.mean[:q], ys.scale[:q])
@@ -577,13 +577,17 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
         return True
 
     # ---- helpers of fit
-    def _raise_if_any_rank(self, bad: bool, msg: str, group):
+    def _raise_if_any_rank(self, bad, msg: str, group):
+        """bad: a Python bool or a 0-d boolean tensor on the device (then there is a single read-back)."""
         if group is not None:
             import torch.distributed as dist
-            flag = torch.tensor([1 if bad else 0], device=torch.device("cuda", torch.cuda.current_device()))
+            if isinstance(bad, torch.Tensor):
+                flag = bad.to(torch.int32).reshape(1)
+            else:
+                flag = torch.tensor([1 if bad else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
             dist.all_reduce(flag, group=group)
             bad = bool(flag.item())
-        if bad:
+        if bool(bad):
             raise ValueError(msg)
 
     def _require_finite(self, Xt, Yt, n):
@@ -671,7 +675,8 @@ class MBPLS(TransformerMixin, RegressorMixin, MultiOutputMixin, BaseEstimator):
                            max_iter=rt["max_iter"], group=group, fuse_next_xtu=rt["fuse_next_xtu"],
                            deflate_mode=rt["deflate_mode"], trips_per_sync=rt["trips_per_sync"], profile=rt["profile"],
                            deflate_last=rt["deflate_last"], one_pass=rt["one_pass"],
-                           one_pass_deflate=rt["one_pass_deflate"], first_trip=first_trip, col_nan=self.__dict__.pop("_col_nan", None) if sparse else None)
+                           one_pass_deflate=rt["one_pass_deflate"], first_trip=first_trip, col_nan=self.__dict__.pop("_col_nan", None) if sparse else None,
+                           p_widest=-(-shard.p_global // max(shard.world, 1)))
         self.n_iter_ = list(res.n_iter)
         self.__dict__["_exchange"] = res.exchange
         if any(it >= rt["max_iter"] for it in res.n_iter):
