@@ -173,17 +173,20 @@ skinny_gemm_kernel(const double* __restrict__ Xt, long ld, int n, const double* 
 // kernel above touches a different row; ncu (1 M x 2,000 -> 4) showed 79 % of its stall samples on those loads with
 // <= 74 KB in flight per SM (3.3 TB/s).  Here a persistent CTA owns tiles of TS samples: a producer warp streams the
 // tile's chunk of every feature (TS * 8 bytes, 1-D bulk / TMA copy) through a ring of TR stages tracked by full / empty
-// mbarriers (192 KB in flight per SM), 8 consumer warps hold the tile's NC x TS outputs in registers.  One CTA covers
-// all features of its tile, so results are written directly (no split partials, fixed summation order).
+// mbarriers, 8 consumer warps hold the tile's NC x TS outputs in registers.  One CTA covers all features of its tile, so
+// results are written directly (no split partials, fixed summation order).  TWO CTAs per SM on half rings (2 x 6 stages x
+// 16 KB = 192 KB in flight per SM): with one CTA the issue slots were 53 % busy behind `wait` / `math_pipe_throttle` stalls of
+// 2 warps per scheduler (ncu); a second CTA's warps fill them: 3.16 -> 2.71 ms for 16 GB = 5.9 TB/s = 0.90 of the copy peak.
+// (16 consumer warps in ONE CTA, 4 samples each, were slower -- 3.56 ms: twice the barrier waits and coefficient broadcasts
+// per chunk.)
 // ------------------------------------------------------------------------------------------
 #define TALL_TS 2048  // samples per tile = 16 KB per feature chunk
-#define TALL_TR 12    // ring stages (192 KB)
+#define TALL_TR 6     // ring stages (96 KB per CTA, two CTAs per SM)
 #define TALL_U 4      // 16-byte units per consumer thread (256 consumer threads x 4 x 2 samples = TS)
-#define TALL_NC 256   // consumer threads + one producer warp.  (16 consumer warps of 4 samples each: 3.56 instead of 3.16 ms --
-                      // twice the mbarrier waits and coefficient broadcasts per chunk outweigh the extra warps.)
+#define TALL_NC 256   // consumer threads + one producer warp
 
 template <int NC>
-__global__ void __launch_bounds__(TALL_NC + 32, 1)
+__global__ void __launch_bounds__(TALL_NC + 32, 2)
 skinny_tall_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ coef, int C,
                    double* __restrict__ out, long ldo, int* __restrict__ flag, int tile_len) {
   // coef: p x 8 doubles, row j = {mean_j (0 without centring), b_0j, b_1j, b_2j, b_3j, -, -, -}: travels through the ring with
@@ -398,7 +401,7 @@ int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const do
   // k with ceil(n / (k * CTAs)) <= TALL_TS, tiles of that length rounded up to 16 samples.
   int tile_len = TALL_TS;
   {
-    const long sms = num_sms();
+    const long sms = 2L * num_sms();  // two CTAs per SM
     const long k = (static_cast<long>(n) + sms * TALL_TS - 1) / (sms * TALL_TS);
     long t = (static_cast<long>(n) + k * sms - 1) / (k * sms);
     t = (t + 15) / 16 * 16;
@@ -406,7 +409,7 @@ int mbpls_skinny_gemm_tall_f64(const double* Xt, long ld, int n, int p, const do
     if (t < TALL_TS) tile_len = static_cast<int>(t);
   }
   const int ntiles = (n + tile_len - 1) / tile_len;
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TALL_LAUNCH(NCV)                                                                                                   \
   do {                                                                                                                     \
