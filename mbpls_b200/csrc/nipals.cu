@@ -1672,7 +1672,8 @@ int mbpls_nipals_xchg_epilogue_f64(const mbpls_xchg_args* x, int ctas, void* str
   xa.tpi = tpi;
   const long need = (items * tpi + 1023) / 1024;
   const int g = need < 1 ? 1 : (need > gmax ? gmax : static_cast<int>(need));
-  static const bool mc_off = getenv("MBPLS_XCHG_MC") && atoi(getenv("MBPLS_XCHG_MC")) == 0;
+  const char* mc_env = getenv("MBPLS_XCHG_MC");  // read per call (tests switch it between fits)
+  const bool mc_off = mc_env && atoi(mc_env) == 0;
   if (x->work && x->epoch > 0 && x->world == 1 && !mc_off && !args->nanmode && args->B <= 8 && args->q <= 16 && gmax <= XMC_GMAX && args->n >= 1) {
     // superlevel step on all CTAs: ch samples per CTA (a multiple of 32), one sample per thread
     int ch = (args->n + gmax - 1) / gmax;

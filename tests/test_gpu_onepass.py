@@ -2,6 +2,7 @@
 component's first trip in one read + write) against the live numpy oracle, for every worker configuration
 (feature lengths up to 640 / 1280 / 2560 / 5120 16-byte units per CTA, and features split over the CTA pair of a
 thread-block cluster up to 20,480 samples), dense and NaN-masked, and against the two-pass kernels they replace."""
+import os
 import warnings
 
 import numpy as np
@@ -175,3 +176,51 @@ def test_standardisation_fused_with_the_first_trip(n, sizes):
         assert np.allclose(a.var_, b.var_, rtol=1e-12, atol=1e-300)
     assert m.x_scalers_[0].scale_[2] == 1.0
     assert np.allclose(np.asarray(m.explained_var_xblocks_), np.asarray(s.explained_var_xblocks_), rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,sizes,q", [(31, (40, 25), 1), (100, (30, 30, 30), 2), (2000, (20, 35, 60, 95, 40, 80, 20, 50), 10),
+                                       (5000, (64,), 16), (10000, (48, 40), 3)])
+def test_superlevel_step_on_all_ctas_matches_the_single_cta_form(n, sizes, q):
+    """xchg_epilogue_mc_kernel (single GPU: the superlevel step spread over all CTAs of the exchange kernel, grid-wide sums in
+    CTA order) against xchg_epilogue_kernel (MBPLS_XCHG_MC=0) and the oracle: ragged n, 1 / 3 / 8 blocks, 1 / 16 responses."""
+    from oracle.cases import latent_blocks
+    from mbpls_b200 import MBPLS
+    X, Y = latent_blocks(n, sizes, q, 4, seed=n % 97 + q)
+    kw = dict(n_components=4, method="NIPALS")
+    m, o = _pair(kw, X, Y, one_pass=True)
+    _check(m, o, X, Y, kw, f"multi-CTA superlevel step n={n} B={len(sizes)} q={q}")
+    os.environ["MBPLS_XCHG_MC"] = "0"
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s = MBPLS(**kw).set_runtime(one_pass=True).fit([x.copy() for x in X], Y.copy())
+    finally:
+        del os.environ["MBPLS_XCHG_MC"]
+    assert list(m.n_iter_) == list(s.n_iter_)
+    assert rel_err(m.beta_, s.beta_) < 1e-11 and rel_err(m.Ts_, s.Ts_) < 1e-11
+
+
+def test_speculative_close_is_bitwise_the_same_fit():
+    """Components closed speculatively behind the trips (record_component / fused_deflate predicated on the device flag) run
+    the same kernels on the same data in the same order as the close-after-read-back form: identical bits, PLS1 and PLS2, and
+    under a max_iter cap that stops components before they converge."""
+    from oracle.cases import latent_blocks
+    from mbpls_b200 import MBPLS
+    for q, cap in ((1, 1000), (3, 1000), (3, 3)):
+        X, Y = latent_blocks(1300, (64, 48, 9), q, 5, seed=11 + q)
+        fits = []
+        for spec in ("1", "0"):
+            os.environ["MBPLS_SPECULATE"] = spec
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    fits.append(MBPLS(n_components=5, method="NIPALS").set_runtime(one_pass=True, max_iter=cap)
+                                .fit([x.copy() for x in X], Y.copy()))
+            finally:
+                del os.environ["MBPLS_SPECULATE"]
+        a, b = fits
+        assert list(a.n_iter_) == list(b.n_iter_)
+        for name in ("Ts_", "U_", "V_", "beta_", "A_"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        for pa, pb in zip(a.P_ + a.W_ + a.T_, b.P_ + b.W_ + b.T_):
+            assert np.array_equal(pa, pb)
