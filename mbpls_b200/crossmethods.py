@@ -187,13 +187,13 @@ def _fit_simpls(model, Xt, Yt, n, q, shard, boff_dev, group, device):
         qv = E.small_top_eigvec(E.gram(St, St, p, group))  # top singular vector of S'S, q x q (:1001)
         r = E.right_multiply(St, p, None, qv.view(q, 1))[0].contiguous()  # r = S q (:1004)
         W[k, :p] = r
-        t = E.skinny_gemm(Xt, n, r.view(1, -1), shard.block_off, group)[0].contiguous()  # t = X r (:1006)
+        t = E.skinny_gemm(Xt, n, r.view(1, -1), shard.block_off, group, dense=True)[0].contiguous()  # t = X r (:1006)
         normt = normalize_(t, n, center=True)  # :1007-1009
         if p > 0:
             scale_rows_(r.view(1, -1), p, normt, True)  # :1010
         pv = xt_vec(Xt, n, t, boff_dev, B)  # p = X't (:1011)
         qk = E.gram(Yt, t.view(1, -1), n)[:, 0].contiguous()  # q = Y't (:1012)
-        u = E.skinny_gemm(Yt, n, qk.view(1, -1), [0, q])[0].contiguous()  # u = Y q (:1013)
+        u = E.skinny_gemm(Yt, n, qk.view(1, -1), [0, q], dense=True)[0].contiguous()  # u = Y q (:1013)
         v = pv.clone() if p > 0 else pv
         if k > 0:  # :1015-1017
             cv = E.gram(V[:k, :p], pv.view(1, -1), p, group)[:, 0].contiguous()
@@ -278,7 +278,7 @@ def _fit_unipals_gram(model, Xt, Yt, n, q, shard, boff_dev, zss, device, rows_gr
         a = block_sumsq(w, boff_dev, B, None)     # :405-408
         Wb[k] = scale_by_block(w, boff_dev, B, a, p)
         A_dev[k] = a
-        u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # u = Y v / v'v, unit length (:423-424)
+        u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q], dense=True)[0].contiguous()  # u = Y v / v'v, unit length (:423-424)
         if rg is None:
             normalize_(u, n)
         else:
@@ -293,11 +293,11 @@ def _fit_unipals_gram(model, Xt, Yt, n, q, shard, boff_dev, zss, device, rows_gr
     M = E.small_pinv(E.gram(P, Wc, p))
     R = E.right_multiply(Wc, p, None, M)  # :476
     beta = E.right_multiply(R, p, None, V.contiguous())  # :477
-    Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # ts_k = X_k w_k / |X_k w_k| = X r_k: unit columns by construction
+    Ts = E.skinny_gemm(Xt, n, R, shard.block_off, dense=True)  # ts_k = X_k w_k / |X_k w_k| = X r_k: unit columns by construction
     Tb = torch.zeros((B, K, ld), dtype=F64, device=device)
     for b in range(B):
         o0, o1 = shard.block_off[b], shard.block_off[b + 1]
-        full = E.skinny_gemm(Xt[o0:o1], n, Wb[:, o0:o1], [0, o1 - o0])  # X_b W_b : K x ld
+        full = E.skinny_gemm(Xt[o0:o1], n, Wb[:, o0:o1], [0, o1 - o0], dense=True)  # X_b W_b : K x ld
         Cb = torch.triu(E.gram(P[:, o0:o1], Wb[:, o0:o1], o1 - o0), diagonal=1).contiguous()  # striu(P_b'W_b)
         Tb[b, 0] = full[0]
         for k in range(1, K):  # t_b,k = X_b^(k) w_b,k = X_b w_b,k - sum_{j<k} ts_j (p_b,j . w_b,k)  (:410-413 after :443)
@@ -371,17 +371,17 @@ def _fit_unipals(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_
             tt = E.rows_sumsq(ts.view(1, -1), n, rg)
             v = E.gram(Yt, ts.view(1, -1), n, rg)[:, 0].contiguous()
             scale_rows_(v.view(1, -1), q, tt, True)  # v = Y'ts / ts'ts (:420)
-            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # :423-424
+            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q], dense=True)[0].contiguous()  # :423-424
             normalize_rows_(u)
         else:  # :481-517
-            At = E.skinny_gemm(Xt, n, Ct, shard.block_off, group)  # (X X'Y)' : q x ld
+            At = E.skinny_gemm(Xt, n, Ct, shard.block_off, group, dense=True)  # (X X'Y)' : q x ld
             c = E.small_top_sv_product(GY, E.gram(At, At, n))
             ts = E.right_multiply(At, ld, None, c.view(q, 1))[0].contiguous()
             normalize_(ts, n)
             tt = E.rows_sumsq(ts.view(1, -1), n)
             v = E.gram(Yt, ts.view(1, -1), n)[:, 0].contiguous()
             scale_rows_(v.view(1, -1), q, tt, True)
-            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()
+            u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q], dense=True)[0].contiguous()
             normalize_(u, n)
             w = xt_vec(Xt, n, u, boff_dev, B).contiguous()  # :503-504
             normalize_over_features_(w, p, group)
@@ -486,7 +486,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
                 a = block_sumsq(w, boff_dev, B, None)
                 Wb[k] = scale_by_block(w, boff_dev, B, a, p)
                 A_dev[k] = a
-                u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q])[0].contiguous()  # Y v' / (v v') up to the scale ...
+                u = E.skinny_gemm(Yt, n, v.view(1, -1), [0, q], dense=True)[0].contiguous()  # Y v' / (v v') up to the scale ...
                 normalize_rows_(u)  # ... which the normalisation removes (:624-625)
                 U[k] = u
             # COVAR <- D'COVAR, VAR <- D'VAR D = VAR - den p'p  (:630-633)
@@ -496,7 +496,7 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
         M = E.small_pinv(E.gram(P, Wc, p))
         R = E.right_multiply(Wc, p, None, M)  # :642
         beta = E.right_multiply(R, p, None, V.contiguous())  # :643
-        Ts = E.skinny_gemm(Xt, n, R, shard.block_off)  # Ts = X R (:644)
+        Ts = E.skinny_gemm(Xt, n, R, shard.block_off, dense=True)  # Ts = X R (:644)
         nrm = torch.sqrt(E.rows_sumsq(Ts, n, rg))  # :646-650
         scale_rows_(V, q, nrm, False)
         scale_rows_(P, p, nrm, False)
@@ -508,13 +508,13 @@ def _fit_kernel(model, Xt, Yt, n, q, shard, boff_dev, zss, group, device, rows_g
         Ts = torch.zeros((K, ld), dtype=F64, device=device)
         scal = torch.zeros(4, dtype=F64, device=device)
         for k in range(K):
-            At = E.skinny_gemm(AX[:, :], n, Yc, [0, n])  # (AS_X Y)' : q x ld;  S = AS_X AS_Y = (AS_X Y) Y' (:707, :725)
+            At = E.skinny_gemm(AX[:, :], n, Yc, [0, n], dense=True)  # (AS_X Y)' : q x ld;  S = AS_X AS_Y = (AS_X Y) Y' (:707, :725)
             c = E.small_top_sv_product(E.gram(Yc, Yc, n), E.gram(At, At, n))
             ts = E.right_multiply(At, ld, None, c.view(q, 1))[0].contiguous()
             ts[n:] = 0.0
             normalize_(ts, n)  # :713
             yt = E.gram(Yc, ts.view(1, -1), n)[:, 0].contiguous()  # Y'ts
-            u = E.skinny_gemm(Yc, n, yt.view(1, -1), [0, q])[0].contiguous()  # AS_Y ts (:718)
+            u = E.skinny_gemm(Yc, n, yt.view(1, -1), [0, q], dense=True)[0].contiguous()  # AS_Y ts (:718)
             normalize_(u, n)
             kv = torch.zeros(ld, dtype=F64, device=device)
             call("mbpls_dense_gemv_f64", ptr(AX), ld, n, n, ptr(ts), ptr(kv), st)

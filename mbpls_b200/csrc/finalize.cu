@@ -54,6 +54,37 @@ gram_partial_kernel(const double* __restrict__ A, long lda, int K1, const double
   }
 }
 
+// Few outputs (K1 * K2 <= 16: the q x q, K x 1 and 1 x 1 contractions of SIMPLS / UNIPALS / KERNEL, most of them with q = 1):
+// the tiled kernel above spends its time in 64 shared-memory staging rounds per chunk (75 us per call at p = 50,000, 48 calls per
+// SIMPLS fit at C2).  Here a thread takes every 256th feature of the chunk with all outputs in registers (coalesced loads),
+// then one fixed-order block sum per output.  Same Cpart layout, so reduce_chunks applies unchanged.
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+gram_small_kernel(const double* __restrict__ A, long lda, int K1, const double* __restrict__ Bm, long ldb, int K2, int p,
+                  double* __restrict__ Cpart) {
+  __shared__ double scratch[32 * NOUT];
+  const int f_begin = blockIdx.x * GRAM_CHUNK, f_end = min(p, f_begin + GRAM_CHUNK);
+  const int nout = K1 * K2;
+  double acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
+  for (int f = f_begin + threadIdx.x; f < f_end; f += 256) {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      if (o < nout) {
+        const int i = o / K2, j = o - i * K2;
+        acc[o] = fma(A[static_cast<size_t>(i) * lda + f], Bm[static_cast<size_t>(j) * ldb + f], acc[o]);
+      }
+    }
+  }
+  block_sum<NOUT>(acc, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+      if (o < nout) Cpart[static_cast<size_t>(blockIdx.x) * nout + o] = acc[o];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_chunks_kernel(const double* __restrict__ Cpart, int nchunks, int len, double* __restrict__ C) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,8 +374,26 @@ int mbpls_gram_partial_f64(const double* A, long lda, int K1, const double* Bm, 
   if (K1 > 64 || K2 > 64) return MBPLS_ERR_SIZE;
   if (p <= 0) return MBPLS_OK;
   const int grid = mbpls_gram_num_chunks(p);
+  const int nout = K1 * K2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nout == 1) {
+    gram_small_kernel<1><<<grid, 256, 0, st>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+    MBPLS_RETURN_LAST();
+  }
+  if (nout <= 4) {
+    gram_small_kernel<4><<<grid, 256, 0, st>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+    MBPLS_RETURN_LAST();
+  }
+  if (nout <= 16) {
+    gram_small_kernel<16><<<grid, 256, 0, st>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+    MBPLS_RETURN_LAST();
+  }
+  if (nout <= 64 && (K1 == 1 || K2 == 1)) {  // up to 64 earlier components against one vector
+    gram_small_kernel<64><<<grid, 256, 0, st>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+    MBPLS_RETURN_LAST();
+  }
   const size_t smem = static_cast<size_t>(K1 + K2) * (GRAM_TILE + 1) * sizeof(double);
-  gram_partial_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
+  gram_partial_kernel<<<grid, 256, smem, st>>>(A, lda, K1, Bm, ldb, K2, p, Cpart);
   MBPLS_RETURN_LAST();
 }
 

@@ -843,9 +843,10 @@ _SKINNY_SPLITS: dict = {}
 
 def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[int], group=None,
                 mean: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
-                flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+                flag: Optional[torch.Tensor] = None, dense: bool = False) -> torch.Tensor:
     """out[c][i] = sum_j nan0(z_ij) * Bm[c][j]  ->  C x ld (feature-major result); z = Xt, or the standardised
-    value (Xt - mean_j) / scale_j computed on the fly when mean/scale are given."""
+    value (Xt - mean_j) / scale_j computed on the fly when mean/scale are given.  dense: the caller guarantees that Xt holds no
+    NaN (fit-time products of SIMPLS / UNIPALS / KERNEL), which opens the faster one-output route below."""
     dev = Xt.device
     p, ld = Xt.shape
     Cc = Bm.shape[0]
@@ -875,6 +876,16 @@ def skinny_gemm(Xt: torch.Tensor, n: int, Bm: torch.Tensor, block_off: Sequence[
                 _SKINNY_SPLITS.clear()
             tab = _SKINNY_SPLITS[key] = (len(f0), _i32(f0, dev), _i32(f1, dev))
         ns, sf0, sf1 = tab
+        if dense and Cc == 1 and mean is None and scale is None and flag is None and os.environ.get("MBPLS_SKINNY_XW", "1") != "0":
+            # one output, plain product (t = X r of SIMPLS, X X'y of UNIPALS): the NIPALS X w kernel streams it at 6.7 TB/s where
+            # the kernel below, laid out for several outputs per thread, reaches 2.3 TB/s (5,000 x 50,000); same split table,
+            # the split partials are then added in split order
+            part = torch.zeros((ns, ld), dtype=F64, device=dev)
+            w1 = Bm[0, :p].contiguous()
+            call("mbpls_nipals_xw_f64", ptr(Xt), ld, n, ptr(w1), ptr(sf0), ptr(sf1), ns, ptr(part), None, ld, 0, None, stream_ptr(dev))
+            call("mbpls_reduce_chunks_f64", ptr(part), ns, ld, ptr(out), stream_ptr(dev))
+            allreduce_(out, group)
+            return out
         part = torch.zeros((ns, Cc * ld), dtype=F64, device=dev)
         call("mbpls_skinny_gemm_f64", ptr(Xt), ld, n, ptr(Bm), Bm.stride(0), Cc, ptr(sf0), ptr(sf1),
              ns, ptr(part), ld, ptr(mean), ptr(scale), ptr(flag), stream_ptr(dev))
