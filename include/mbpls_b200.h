@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MBPLS_ABI_VERSION 14
+#define MBPLS_ABI_VERSION 15
 
 /* indices into the per-fit scalar / control buffers */
 #define MBPLS_SCAL_UU 0    /* u'u of the current Y-score vector (mbpls.py:847,856,879) */
@@ -324,6 +324,12 @@ int mbpls_rows_scale_f64(double* M, long ld, int rows, int n, const double* scal
 /* out[c][j] = sum_i nan0(Xt[j][i]) * M[c][i]: X'Y (:396,:587,:998), X'U (:731), X'Ts (:734) */
 int mbpls_xt_multi_f64(const double* Xt, long ld, int n, int p, const double* M, long ldm, int C, double* out, long ldo,
                        void* stream);
+/* few, long features (n >= 2^16): the same product with every feature cut into mbpls_xt_multi_chunks(n, p) sample ranges so that
+ * the whole GPU streams it; part[s][c][j] (C * ldo doubles per chunk s) receives the partial products, which are then added
+ * in chunk order: mbpls_reduce_chunks_f64(part, chunks, C * ldo, out) */
+int mbpls_xt_multi_chunks(int n, int p);
+int mbpls_xt_multi_split_f64(const double* Xt, long ld, int n, int p, const double* M, long ldm, int C, double* part, long ldo,
+                             int chunks, void* stream);
 /* out[j] = base[j] - sum_k V[k][j]*coef[k]: SIMPLS orthogonalisation (:1016-1017) */
 int mbpls_lincomb_sub_f64(double* out, const double* base, const double* V, long ldv, int K, const double* coef, int len,
                           void* stream);

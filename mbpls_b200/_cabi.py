@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmbpls_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # indices shared with the header
 SCAL_UU, SCAL_DIFF, SCAL_TT, SCAL_VV, SCAL_COUNT = 0, 1, 2, 3, 8
@@ -118,6 +118,8 @@ SIGNATURES = {
     "mbpls_rows_sumsq_f64": [_p, _l, _i, _i, _p, _p],
     "mbpls_rows_scale_f64": [_p, _l, _i, _i, _p, _i, _p],
     "mbpls_xt_multi_f64": [_p, _l, _i, _i, _p, _l, _i, _p, _l, _p],
+    "mbpls_xt_multi_chunks": [_i, _i],
+    "mbpls_xt_multi_split_f64": [_p, _l, _i, _i, _p, _l, _i, _p, _l, _i, _p],
     "mbpls_lincomb_sub_f64": [_p, _p, _p, _l, _i, _p, _i, _p],
     "mbpls_center_normalize_f64": [_p, _i, _i, _i, _p, _p],
     "mbpls_block_sumsq_f64": [_p, _p, _i, _p, _p],
@@ -134,7 +136,7 @@ SIGNATURES = {
 
 # functions whose int return value is a plain number, not a status
 _PLAIN = {"mbpls_abi_version", "mbpls_smallfit_scratch_doubles", "mbpls_fused_workers_per_sm_pair", "mbpls_fused_total_workers", "mbpls_fused_uses_clusters", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
-          "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits"}
+          "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits", "mbpls_xt_multi_chunks"}
 
 
 class MbplsCudaError(RuntimeError):

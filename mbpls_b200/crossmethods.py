@@ -33,7 +33,14 @@ def xt_multi(Xt, n, M):
     Cc = M.shape[0]
     out = torch.zeros((Cc, max(p, 1)), dtype=F64, device=Xt.device)
     if p > 0:
-        call("mbpls_xt_multi_f64", ptr(Xt), ld, n, p, ptr(M), M.stride(0), Cc, ptr(out), out.stride(0), stream_ptr(Xt.device))
+        chunks = call("mbpls_xt_multi_chunks", n, p)
+        if chunks > 1:  # few, long features: cut the sample axis, add the partial products in chunk order
+            part = torch.zeros((chunks, Cc * out.stride(0)), dtype=F64, device=Xt.device)
+            call("mbpls_xt_multi_split_f64", ptr(Xt), ld, n, p, ptr(M), M.stride(0), Cc, ptr(part), out.stride(0), chunks,
+                 stream_ptr(Xt.device))
+            call("mbpls_reduce_chunks_f64", ptr(part), chunks, Cc * out.stride(0), ptr(out), stream_ptr(Xt.device))
+        else:
+            call("mbpls_xt_multi_f64", ptr(Xt), ld, n, p, ptr(M), M.stride(0), Cc, ptr(out), out.stride(0), stream_ptr(Xt.device))
     return out[:, :p]
 
 

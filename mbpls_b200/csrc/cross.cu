@@ -14,12 +14,18 @@ using namespace mbpls;
 template <int NC>
 __global__ void __launch_bounds__(256)
 xt_multi_kernel(const double* __restrict__ Xt, long ld, int n, int p, const double* __restrict__ M, long ldm, int c0, int C,
-                double* __restrict__ out, long ldo) {
+                double* __restrict__ out, long ldo, int chunk2, long part_stride) {
+  // blockIdx.y = sample chunk (chunk2 16-byte units each; one chunk = the whole feature when gridDim.y == 1): with few, long
+  // features (1 M samples x 2,000 features: 500 warp tasks) one warp per 4 whole features leaves the GPU at 0.5 TB/s, so the
+  // sample axis is cut and the partial products of chunk s land in out + s * part_stride, to be added in chunk order
   constexpr int F = 4;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nc = min(NC, C - c0);
-  const int n2 = n >> 1;
+  const int n2 = min(n >> 1, static_cast<int>(blockIdx.y + 1) * chunk2);
+  const int i_begin = static_cast<int>(blockIdx.y) * chunk2;
+  const bool tail_chunk = blockIdx.y == gridDim.y - 1;
+  out += static_cast<size_t>(blockIdx.y) * part_stride;
   for (int j0 = gw * F; j0 < p; j0 += nwarps * F) {
     double acc[F][NC];
 #pragma unroll
@@ -29,7 +35,7 @@ xt_multi_kernel(const double* __restrict__ Xt, long ld, int n, int p, const doub
     const double2* xr[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) xr[f] = reinterpret_cast<const double2*>(Xt + static_cast<size_t>(min(j0 + f, p - 1)) * ld);
-    for (int i = lane; i < n2; i += 32) {
+    for (int i = i_begin + lane; i < n2; i += 32) {
       double2 x[F];
 #pragma unroll
       for (int f = 0; f < F; ++f) {
@@ -49,7 +55,7 @@ xt_multi_kernel(const double* __restrict__ Xt, long ld, int n, int p, const doub
         }
       }
     }
-    if ((n & 1) && lane == 0) {
+    if ((n & 1) && lane == 0 && tail_chunk) {
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         double xv = Xt[static_cast<size_t>(min(j0 + f, p - 1)) * ld + n - 1];
@@ -307,12 +313,50 @@ int mbpls_xt_multi_f64(const double* Xt, long ld, int n, int p, const double* M,
   int grid = (p + 31) / 32;  // 8 warps x 4 features
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunk2 = (n >> 1) + 1;
   for (int c0 = 0; c0 < C; c0 += 8) {
     const int nc = C - c0;
-    if (nc > 4) xt_multi_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
-    else if (nc > 2) xt_multi_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
-    else if (nc > 1) xt_multi_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
-    else xt_multi_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo);
+    if (nc > 4) xt_multi_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo, chunk2, 0);
+    else if (nc > 2) xt_multi_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo, chunk2, 0);
+    else if (nc > 1) xt_multi_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo, chunk2, 0);
+    else xt_multi_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, out, ldo, chunk2, 0);
+  }
+  MBPLS_RETURN_LAST();
+}
+
+/* sample chunks worth cutting the features of an X'M product into (1: use mbpls_xt_multi_f64) */
+int mbpls_xt_multi_chunks(int n, int p) {
+  if (p <= 0 || n < (1 << 16)) return 1;
+  const long tasks = (static_cast<long>(p) + 3) / 4;          // warp tasks without a cut
+  const long want = static_cast<long>(num_sms()) * 8 * 6;     // ~6 tasks per resident warp
+  long s = (want + tasks - 1) / tasks;
+  const long smax = n / (1 << 14);                            // chunks of at least 16k samples
+  if (s > smax) s = smax;
+  if (s > 256) s = 256;
+  return s < 1 ? 1 : static_cast<int>(s);
+}
+
+/* the same product with every feature cut into `chunks` sample ranges: part[s][c][j] (part_stride = C * ldo doubles per
+ * chunk) holds the partial products of chunk s; add them in chunk order (mbpls_reduce_chunks_f64(part, chunks, C * ldo, out)) */
+int mbpls_xt_multi_split_f64(const double* Xt, long ld, int n, int p, const double* M, long ldm, int C, double* part, long ldo,
+                             int chunks, void* stream) {
+  if (!Xt || !M || !part || C < 1 || chunks < 1 || chunks > 65535 || (ld % 2) != 0 || (ldm % 2) != 0) return MBPLS_ERR_ARG;
+  if (p == 0) return MBPLS_OK;
+  int gx = (p + 31) / 32;  // 8 warps x 4 features
+  if (gx > num_sms() * 8) gx = num_sms() * 8;
+  const dim3 grid(gx, chunks);
+  const int n2 = n >> 1;
+  int chunk2 = (n2 + chunks - 1) / chunks;
+  chunk2 = (chunk2 + 31) / 32 * 32;
+  if (chunk2 < 32) chunk2 = 32;
+  const long stride = static_cast<long>(C) * ldo;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    const int nc = C - c0;
+    if (nc > 4) xt_multi_kernel<8><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, part, ldo, chunk2, stride);
+    else if (nc > 2) xt_multi_kernel<4><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, part, ldo, chunk2, stride);
+    else if (nc > 1) xt_multi_kernel<2><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, part, ldo, chunk2, stride);
+    else xt_multi_kernel<1><<<grid, 256, 0, st>>>(Xt, ld, n, p, M, ldm, c0, C, part, ldo, chunk2, stride);
   }
   MBPLS_RETURN_LAST();
 }

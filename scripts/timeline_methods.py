@@ -1,6 +1,6 @@
 """Kernel timeline (torch.profiler) of one SIMPLS / KERNEL / UNIPALS fit at the C2 shape (PLS1, n = 5,000 x p = 50,000, K = 10):
 GPU busy time per kernel name and idle time between kernels -- is the fit bound by the host's launch rate?
-    python scripts/timeline_methods.py [method] [n] [p] [K]"""
+    python scripts/timeline_methods.py [method] [n] [p] [K] [q] [blocks] [calc_all]"""
 import os
 import sys
 import warnings
@@ -17,10 +17,14 @@ method = sys.argv[1] if len(sys.argv) > 1 else "SIMPLS"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 p = int(sys.argv[3]) if len(sys.argv) > 3 else 50000
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+q = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+nblocks = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+calc_all = (sys.argv[7] != "0") if len(sys.argv) > 7 else True
 dev = torch.device("cuda:0")
 ld = E.round_ld(n)
 Xbuf = torch.empty((p, ld), dtype=torch.float64, device=dev)
-Y = synth.response(n, 1, K, dev, 5, decay=0.85)
+Y = synth.response(n, q, K, dev, 5, decay=0.85)
+bounds = [p * b // nblocks for b in range(nblocks + 1)]
 
 
 def fit():
@@ -30,7 +34,7 @@ def fit():
     e0.record()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        m = MBPLS(n_components=K, method=method, copy=False).set_runtime(materialize=False).fit([Xbuf[:, :n].t()], Y)
+        m = MBPLS(n_components=K, method=method, copy=False, calc_all=calc_all).set_runtime(materialize=False).fit([Xbuf[bounds[b]:bounds[b + 1], :n].t() for b in range(nblocks)], Y)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1), m
@@ -45,7 +49,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     mark0 = torch.cuda.Event(enable_timing=True)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        m = MBPLS(n_components=K, method=method, copy=False).set_runtime(materialize=False).fit([Xbuf[:, :n].t()], Y)
+        m = MBPLS(n_components=K, method=method, copy=False, calc_all=calc_all).set_runtime(materialize=False).fit([Xbuf[bounds[b]:bounds[b + 1], :n].t() for b in range(nblocks)], Y)
     torch.cuda.synchronize()
 kern = []
 for ev in prof.events():

@@ -248,6 +248,13 @@ def test_tall_batches_take_the_tma_ring_product_kernel():
         assert rel_err(model.predict(Xn), want) < 1e-12
     finally:
         del os.environ["MBPLS_TALL"]
+    # more than four outputs: the ring kernel makes one pass per four (superscores of a 6-component model)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model6 = MBPLS(n_components=6).fit([x.copy() for x in X], Y.copy())
+        Ts6 = model6.transform(Xn)
+    Z6 = np.hstack([sc.transform(x) for sc, x in zip(model6.x_scalers_, Xn)])
+    assert Ts6.shape == (m, 6) and rel_err(Ts6, Z6 @ model6.R_) < 1e-12
     # NaN mode: missing entries of new data count as zero after scaling
     Xm = [x.copy() for x in Xn]
     Xm[0][::7, 3] = np.nan

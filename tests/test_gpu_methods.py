@@ -153,3 +153,22 @@ def test_small_device_linear_algebra_matches_numpy(m):
     u /= np.linalg.norm(u)
     uref = np.linalg.svd(A @ Bm.T)[0][:, 0]
     assert min(rel_err(u, uref), rel_err(-u, uref)) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["KERNEL", "UNIPALS", "SIMPLS"])
+def test_few_long_features_cut_the_sample_axis(method):
+    """n >= 2^16 with a handful of features: X'Y / X'U / X'Ts cut every feature into sample chunks (mbpls_xt_multi_split_f64,
+    partial products added in chunk order) and the n-space products of the fit go through the tall ring kernel; against the
+    oracle on an odd n."""
+    from oracle.cases import latent_blocks
+    from oracle import OracleMBPLS
+    from mbpls_b200 import MBPLS
+    n = (1 << 18) + 4099
+    X, Y = latent_blocks(n, (14, 10), 2, 3, seed=23)
+    kw = dict(n_components=3, method=method)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = OracleMBPLS(**kw, **({"full_svd": True} if method == "SIMPLS" else {})).fit([x.copy() for x in X], Y.copy())
+        m = MBPLS(**kw).fit([x.copy() for x in X], Y.copy())
+    ref, ours = snapshot_model(o, [x.copy() for x in X], Y.copy()), snapshot_model(m, [x.copy() for x in X], Y.copy())
+    compare(ours, ref, 1e-8, f"{method} n={n}")
