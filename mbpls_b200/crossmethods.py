@@ -61,6 +61,12 @@ def lincomb_sub(base, V, K, coef, length):
 
 
 def normalize_(t, n, center=False):
+    if n >= (1 << 16) and not center:
+        # long vectors: the single-CTA kernel below makes three passes through one SM (435 us for 1 M samples); sum of squares
+        # + a grid-wide scaling pass instead
+        nrm = torch.sqrt(E.rows_sumsq(t.view(1, -1), n))
+        scale_rows_(t.view(1, -1), n, nrm, True)
+        return nrm
     nrm = torch.zeros(1, dtype=F64, device=t.device)
     call("mbpls_center_normalize_f64", ptr(t), n, 1 if center else 0, 1, ptr(nrm), stream_ptr(t.device))
     return nrm

@@ -138,14 +138,18 @@ scale_by_block_kernel(const double* __restrict__ w, const int* __restrict__ off,
 // ------------------------------------------------------------------------------------------
 #define XP_BM 128
 #define XP_BN 128
-#define XP_BK 16
-#define XP_LD 20  // padded k-stride of a smem row (20 = 4 mod 16 -> conflict-free 64-bit fragment loads)
+#ifndef XP_BK
+#define XP_BK 16  // 32 (221 KB of tiles) measured: X'X on 1 M x 2,000 156 -> 150 ms, XX' on 5,000 x 50,000 49 -> 54 ms; fragment
+#endif            // prefetch across k-steps: no change (the compiler already hoists the loads)
+#define XP_LD (XP_BK + 4)  // padded k-stride of a smem row (4 mod 16 -> conflict-free 64-bit fragment loads)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+#ifndef XP_STAGES
 #define XP_STAGES 3
+#endif
 
 // cp.async (LDGSTS): asynchronous global -> shared copies of 8 / 16 bytes; src_bytes = 0 zero-fills the slot
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
@@ -185,9 +189,9 @@ crossprod_kernel(const double* __restrict__ A, long lda, const double* __restric
     double* bs = Bs + slot * TILE;
     if (KMAJOR) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {  // 16-byte copies along k (lda, ldb even; k0 even)
+      for (int e = 0; e < XP_BK / 4; ++e) {  // 16-byte copies along k (lda, ldb even; k0 even)
         const int idx = tid + e * 256;
-        const int row = idx >> 3, kk = (idx & 7) * 2;
+        const int row = idx / (XP_BK / 2), kk = (idx % (XP_BK / 2)) * 2;
         const long k = k0 + kk;
         const int kbytes = k + 1 < ke ? 16 : (k < ke ? 8 : 0);
         const bool oka = (m0 + row < M) && kbytes > 0, okb = (n0 + row < N) && kbytes > 0;
@@ -196,7 +200,7 @@ crossprod_kernel(const double* __restrict__ A, long lda, const double* __restric
       }
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {  // 8-byte copies, coalesced along the row (m / n) index
+      for (int e = 0; e < XP_BK / 2; ++e) {  // 8-byte copies, coalesced along the row (m / n) index
         const int idx = tid + e * 256;
         const int kk = idx >> 7, row = idx & 127;
         const long k = k0 + kk;

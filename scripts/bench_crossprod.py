@@ -2,6 +2,9 @@
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from mbpls_b200 import _cabi
+if os.environ.get("MBPLS_LIB"):  # A/B builds of the library (scripts/probes/*.so)
+    _cabi.LIB_PATH = os.path.abspath(os.environ["MBPLS_LIB"])
 from mbpls_b200 import crossmethods as CM, engine as E
 dev = torch.device("cuda:0")
 
