@@ -343,6 +343,9 @@ int mbpls_scale_by_block_f64(const double* w, const int* off, int B, const doubl
  * kmajor=0: C = A' B (A: Kdim x M, B: Kdim x N)  -> X X' from the feature-major matrix (:704)
  * Cpart: splits x M x ldc partials (splits = mbpls_crossprod_splits); sum them with mbpls_reduce_chunks_f64. */
 int mbpls_crossprod_splits(int M, int N, long Kdim);
+/* split count for symmetric=1 (X'X / XX'): balances the CTAs that do work (tiles on / above the diagonal) over whole rounds of
+ * the SMs; a pure function of (M, Kdim, SM count) */
+int mbpls_crossprod_splits_syrk(int M, long Kdim);
 int mbpls_crossprod_f64(const double* A, long lda, const double* B, long ldb, int M, int N, long Kdim, int kmajor, int splits,
                         double* Cpart, long ldc, int symmetric, void* stream);
 /* symmetric=1 (A == B, M == N): only the tiles on/above the diagonal are computed (SYRK); after the split-K

@@ -125,6 +125,7 @@ SIGNATURES = {
     "mbpls_block_sumsq_f64": [_p, _p, _i, _p, _p],
     "mbpls_scale_by_block_f64": [_p, _p, _i, _p, _p, _i, _p],
     "mbpls_crossprod_splits": [_i, _i, _l],
+    "mbpls_crossprod_splits_syrk": [_i, _l],
     "mbpls_crossprod_f64": [_p, _l, _p, _l, _i, _i, _l, _i, _i, _p, _l, _i, _p],
     "mbpls_symmetrize_f64": [_p, _l, _i, _p],
     "mbpls_small_top_eigvec_f64": [_p, _l, _i, _p, _p],
@@ -136,7 +137,7 @@ SIGNATURES = {
 
 # functions whose int return value is a plain number, not a status
 _PLAIN = {"mbpls_abi_version", "mbpls_smallfit_scratch_doubles", "mbpls_fused_workers_per_sm_pair", "mbpls_fused_total_workers", "mbpls_fused_uses_clusters", "mbpls_nan_bitmask_ldw", "mbpls_xtu_feats_per_cta", "mbpls_xtu_num_ctas", "mbpls_gram_num_chunks",
-          "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits", "mbpls_xt_multi_chunks"}
+          "mbpls_xw_ctas_per_sm", "mbpls_crossprod_splits", "mbpls_crossprod_splits_syrk", "mbpls_xt_multi_chunks"}
 
 
 class MbplsCudaError(RuntimeError):

@@ -14,6 +14,7 @@ so a fit enqueues asynchronously without per-component host round-trips.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import warnings
 import weakref
 
@@ -438,7 +439,10 @@ def crossprod(A, Bm, M, N, Kdim, kmajor, ldc):
     """FP64 tensor-core cross product; A is Bm (X'X / XX') -> SYRK: upper tiles only, then mirrored."""
     dev = A.device
     sym = 1 if (A.data_ptr() == Bm.data_ptr() and M == N) else 0
-    splits = call("mbpls_crossprod_splits", M, N, Kdim)
+    if sym and os.environ.get("MBPLS_XP_SPLITS", "balanced") != "rectangular":
+        splits = call("mbpls_crossprod_splits_syrk", M, Kdim)  # whole rounds of the CTAs on / above the diagonal
+    else:
+        splits = call("mbpls_crossprod_splits", M, N, Kdim)
     part = torch.zeros((splits, M * ldc), dtype=F64, device=dev)
     call("mbpls_crossprod_f64", ptr(A), A.stride(0), ptr(Bm), Bm.stride(0), M, N, Kdim, 1 if kmajor else 0, splits, ptr(part),
          ldc, sym, stream_ptr(dev))

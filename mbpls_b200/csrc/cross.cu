@@ -406,6 +406,36 @@ int mbpls_crossprod_splits(int M, int N, long Kdim) {
   return static_cast<int>(want);
 }
 
+// Split count of a SYMMETRIC cross product (A == B, M == N): only the nb (nb + 1) / 2 tiles on / above the diagonal do work and
+// every CTA owns a whole SM (123 KB of tiles), so the launch takes ceil(working CTAs / SMs) rounds of one CTA's k range.  With the
+// rectangular rule above X'X of 1 M x 2,000 runs 272 working CTAs on 148 SMs (two rounds, 8 % of the SM-time idle: ncu shows the
+// FP64 tensor pipe 84 % busy while active but 77 % of the elapsed time, 42 % on the least loaded SM).  Here the count minimises
+// rounds x k-slabs per CTA (+ a few slabs of pipeline fill / epilogue per round) + the traffic of the partial matrices, under
+// a 1 GiB cap on the partials; the choice depends on the shape and the SM count only, so it is the same on every rank and run.
+int mbpls_crossprod_splits_syrk(int M, long Kdim) {
+  if (M < 1 || Kdim < 1) return 1;
+  const long nb = (M + XP_BM - 1) / XP_BM, working = nb * (nb + 1) / 2, nsm = num_sms() > 0 ? num_sms() : 148;
+  long maxs = (Kdim + 4 * XP_BK - 1) / (4 * XP_BK);
+  const long cap = (1L << 30) / (8L * M * ((M + 15) / 16 * 16));
+  if (maxs > cap) maxs = cap;
+  if (maxs > 64) maxs = 64;
+  if (maxs < 1) maxs = 1;
+  const double slab_us = 2.6;                                         // one 128 x 128 x 16 slab on one SM at ~0.2 TFLOP/s
+  const double part_us = 2.5 * 8.0 * M * static_cast<double>(M) / 6.0e6;  // zero-fill + write + read of one partial at 6 TB/s
+  long best = 1;
+  double best_us = 0.0;
+  for (long s = 1; s <= maxs; ++s) {
+    const long rounds = (working * s + nsm - 1) / nsm;
+    const long slabs = ((Kdim + s - 1) / s + XP_BK - 1) / XP_BK;
+    const double us = rounds * (slabs + 4) * slab_us + s * part_us;
+    if (s == 1 || us < best_us * (1.0 - 1e-3)) {  // a later count has to win by more than 0.1 %
+      best = s;
+      best_us = us;
+    }
+  }
+  return static_cast<int>(best);
+}
+
 // kmajor = 1: C = A B' with A (M x Kdim, lda), B (N x Kdim, ldb); kmajor = 0: C = A' B with A (Kdim x M), B (Kdim x N).
 // Cpart holds `splits` partial M x ldc matrices (splits = mbpls_crossprod_splits); reduce with mbpls_reduce_chunks_f64.
 int mbpls_symmetrize_f64(double* C, long ldc, int M, void* stream) {
