@@ -43,3 +43,17 @@ def test_product_never_imports_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no CPU fallback", ""), fn
+
+
+def test_symmetric_crossprod_split_count_fills_whole_rounds():
+    """mbpls_crossprod_splits_syrk is integer arithmetic on (M, Kdim, SM count; 148 without a device): the CTAs on / above the
+    diagonal times the split count must fill whole rounds of the SMs on the BASELINE shapes, within the caps."""
+    import math
+    from mbpls_b200 import _cabi
+    for M, K, min_eff in ((2000, 1_000_000, 0.98), (2000, 125_000, 0.98), (5000, 50_000, 0.98), (8192, 8192, 0.95)):
+        s = _cabi.call("mbpls_crossprod_splits_syrk", M, K)
+        nb = -(-M // 128)
+        working = nb * (nb + 1) // 2 * s
+        assert 1 <= s <= 64 and s * 8 * M * (-(-M // 16) * 16) <= 1 << 30
+        assert working / 148 / math.ceil(working / 148) >= min_eff, (M, K, s)
+    assert _cabi.call("mbpls_crossprod_splits_syrk", 1, 1) == 1 and _cabi.call("mbpls_crossprod_splits_syrk", 0, 0) == 1
